@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py — probe-rays/s of the DDGI probe update on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One step = one frame's probe update over the whole probe field: 4 dynamic lights are
+moved (host), every probe ray is traced (ddgi_probe_update) and, on N > 1 GPUs, the
+probe-row shards are exchanged (NCCL all-gather or the fused peer-store kernel).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "probe_rays_per_s"
+UNIT = "probe-rays/s"
+
+
+# ----------------------------------------------------------------------------- helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class DevPtr:
+    """Wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, cfg_name):
+    """The reference's CPU implementation of the path = the oracle port (the GLSL cannot be
+    built here or on the box: no glslang / Vulkan / lavapipe), all host threads, on a
+    bounded sample of the same workload: `sample_rows` probe rows per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bench_support import reference_arm
+
+    print(json.dumps(reference_arm(args, cfg_name)), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="field_32")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"])
+    ap.add_argument("--variant", type=int, default=1)
+    ap.add_argument("--march-min", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args, args.workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import ddgi_b200
+    from bench_support import cpu_baseline, workload_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workload_config(args.workload)
+    import importlib
+
+    configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
+
+    r = ddgi_b200.RVPT(*cfg["screen"], device=local)
+    configs.apply(r, cfg, time=0.0)
+    r.generate_probe_rays(reseed=True)
+    r.set_kernel_variant(args.variant)
+    if args.march_min is not None:
+        r.set_tuning(args.march_min)
+    r.update(advance_time=False)
+    stream = torch.cuda.current_stream()
+    r.stream = stream.cuda_stream
+
+    X, Y, Z = cfg["probe_count"]
+    rx, ry = cfg["tile"]
+    n_rays = X * Y * Z * rx * ry
+    W, H = r.probe_texture_size
+    y0, y1 = ddgi_b200.probe_row_shard(Y, rank, world)
+    r.set_probe_rows(y0, y1)
+
+    # the probe texture as a torch tensor (for the NCCL exchange)
+    ptr, nbytes = r.probe_texture_device_ptr(0)
+    tex = torch.as_tensor(DevPtr(ptr, 2 * nbytes), device=f"cuda:{local}")
+    planes = [tex[:nbytes], tex[nbytes:]]
+    even = Y % world == 0
+    row_bytes = W * 4 * ry
+
+    if world > 1 and args.exchange == "fused":
+        handles = [None] * world
+        dist.all_gather_object(handles, r.export_texture_handle())
+        r.open_peers(handles, rank)
+    sync_flag = torch.zeros(1, device=f"cuda:{local}")
+
+    def exchange():
+        if world == 1:
+            return
+        if args.exchange == "fused":
+            # texels were stored into every replica by the kernel; one tiny all-reduce is
+            # the cross-GPU completion barrier on the stream
+            dist.all_reduce(sync_flag)
+            return
+        for pl in planes:
+            if even:
+                chunk = (Y // world) * row_bytes
+                dist.all_gather_into_tensor(pl, pl[rank * chunk:(rank + 1) * chunk])
+            else:
+                outs = []
+                for g in range(world):
+                    a, b = ddgi_b200.probe_row_shard(Y, g, world)
+                    outs.append(pl[a * row_bytes:b * row_bytes])
+                dist.all_gather(outs, pl[y0 * row_bytes:y1 * row_bytes])
+
+    frame_no = [0]
+
+    def step():
+        # update_lights: 4 dynamic lights, time += 2 per frame (rvpt.cpp:281)
+        frame_no[0] += 1
+        r.render_settings.time = 2.0 * frame_no[0]
+        r.lights = configs.lights_for(cfg, r.render_settings.time)
+        r.update(advance_time=False)
+        r.probe_update()
+        exchange()
+
+    flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def flush_l2():
+        if flush_buf is not None:
+            flush_buf.fill_(frame_no[0] & 255)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush_l2()
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = r.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, m, b in evs:
+        flush_l2()
+        a.record(stream)
+        frame_no[0] += 1
+        r.render_settings.time = 2.0 * frame_no[0]
+        r.lights = configs.lights_for(cfg, r.render_settings.time)
+        r.update(advance_time=False)
+        r.probe_update()
+        m.record(stream)
+        exchange()
+        b.record(stream)
+    barrier()
+    launches = r.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, m, b in evs)
+    kernel_ms = sum(a.elapsed_time(m) for a, m, b in evs) / args.steps
+    t = torch.tensor([total_ms, kernel_ms], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = n_rays / (ms_per_step * 1e-3)
+
+    # ---- FPS at the config's resolution: probe update + exchange + pixel pass ----
+    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_frames = max(3, min(args.steps, 10))
+    barrier()
+    fa.record(stream)
+    for _ in range(n_frames):
+        step()
+        r.render_frame()
+    fb.record(stream)
+    barrier()
+    ft = torch.tensor([fa.elapsed_time(fb) / n_frames], device=f"cuda:{local}", dtype=torch.float64)
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record(stream)
+    r.render_frame()
+    pb.record(stream)
+    barrier()
+    if world > 1:
+        dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+    frame_ms = float(ft[0])
+    pixel_ms = pa.elapsed_time(pb)
+
+    # ---- algorithmic bytes: voxel lookups counted by the instrumented kernel (untimed) ----
+    r.set_debug(True)
+    r.probe_update()
+    r.sync()
+    per_row = X * Z * rx * ry
+    lk = r.read_lookup_counts(0)[y0 * per_row:y1 * per_row]
+    lk_sum = torch.tensor([float(lk.sum(dtype=np.float64))], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(lk_sum)
+    mean_lookups = float(lk_sum[0]) / n_rays
+    r.set_debug(False)
+    bytes_per_ray = 4.0 * mean_lookups + 8.0
+    peak, peak_src = load_peaks()
+    rays_this_rank = (y1 - y0) * per_row
+    achieved = rays_this_rank * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
+
+    # ---- e2e through the C-ABI with host buffers (pinned), per step:
+    #      H2D: ray-sample table + uniforms/lights; D2H: the rank's albedo rows ----
+    e2e = None
+    if not args.no_e2e:
+        samples = r.ray_samples       # the stratified sample table generate_samples drew
+        rays_host = r.probe_rays      # the reference's std::vector<ProbeRay>
+        pinned_samples = torch.from_numpy(samples).pin_memory()
+        host_tex = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        lib = ddgi_b200.capi.load()
+        h2d = pinned_samples.numel() * 4 + 32 + 48 + 80 + 4 * 28
+        d2h = nbytes if world == 1 else (y1 - y0) * row_bytes
+
+        def e2e_step():
+            frame_no[0] += 1
+            r.render_settings.time = 2.0 * frame_no[0]
+            r.lights = configs.lights_for(cfg, r.render_settings.time)
+            r.update(advance_time=False)
+            rc = lib.ddgi_set_ray_samples(r._ctx, pinned_samples.data_ptr(), rx * ry)
+            assert rc == 0
+            r.probe_update()
+            exchange()
+            if world == 1:
+                rc = lib.ddgi_read_probe_texture(r._ctx, 0, 0, host_tex.data_ptr(), nbytes)
+                assert rc == 0
+            else:
+                torch.cuda.current_stream().synchronize()
+                host_tex[: d2h].copy_(planes[0][y0 * row_bytes:y1 * row_bytes])
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_rays * args.steps / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "inputs": "ray-sample table + uniforms + lights (pinned host)",
+               "result": "albedo probe texture rows of this rank (pinned host)"}
+        # literal storage-buffer mode: the whole ProbeRay array re-uploaded every frame, as
+        # RVPT::update does (rvpt.cpp:285)
+        if world == 1:
+            pinned_rays = torch.from_numpy(rays_host).pin_memory()
+
+            def ssbo_step():
+                frame_no[0] += 1
+                r.update(advance_time=False)
+                rc = lib.ddgi_set_probe_rays(r._ctx, pinned_rays.data_ptr(), n_rays)
+                assert rc == 0
+                r.probe_update()
+                rc = lib.ddgi_read_probe_texture(r._ctx, 0, 0, host_tex.data_ptr(), nbytes)
+                assert rc == 0
+
+            for _ in range(2):
+                ssbo_step()
+            barrier()
+            t0 = time.perf_counter()
+            ns = max(3, args.steps // 4)
+            for _ in range(ns):
+                ssbo_step()
+            barrier()
+            e2e["ssbo_mode"] = {"value": n_rays * ns / (time.perf_counter() - t0), "unit": UNIT,
+                                "h2d_bytes_per_step": int(n_rays * 48 + 160), "d2h_bytes_per_step": int(nbytes)}
+            r.generate_probe_rays(reseed=True)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(r, cfg, args.workload)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "probes": [X, Y, Z], "rays_per_probe": rx * ry,
+                       "probe_rays": n_rays, "voxels": list(cfg["voxels"][1]), "lights": 4 if cfg["lights"] == "cave4" else 1,
+                       "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"]),
+                       "l2": "flushed between timed steps (256 MiB write)" if flush_buf is not None else "not flushed",
+                       "kernel_variant": args.variant, "exchange": args.exchange if world > 1 else "none",
+                       "sharding": f"probe rows {Y}/{world}"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "probe_update_wavefront" if args.variant == 1 else "probe_update_direct",
+                         "kernel_ms": kernel_ms, "bytes_per_ray": bytes_per_ray, "mean_lookups_per_ray": mean_lookups,
+                         "note": "algorithmic bytes = rays x (4 B x voxel lookups of the reference algorithm + 8 B texel stores), SURVEY 8d"},
+            "cpu_baseline": cpu,
+            "fps": {"value": 1000.0 / frame_ms, "frame_ms": frame_ms, "pixel_pass_ms": pixel_ms,
+                    "resolution": list(cfg["screen"])},
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    tj = json.load(f)
+                if tj.get("workload") == args.workload:
+                    out["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        if args.exchange == "fused":
+            r.close_peers()
+        dist.barrier()
+        dist.destroy_process_group()
+    r.close()
+
+
+if __name__ == "__main__":
+    main()

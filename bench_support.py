@@ -1,0 +1,112 @@
+"""bench_support.py — the CPU legs of bench.py: `cpu_baseline` and `--impl reference`.
+
+This is the ONE place outside tests/ and __graft_entry__.smoke() that executes oracle/:
+it times the CPU restatement of the reference's path (the reference's GLSL cannot be
+built or run: no glslang / Vulkan / lavapipe here or on the GPU box; DESIGN.md "Oracle")
+on the box's host cores, on a bounded sample of the bench workload.  Nothing here is on
+the product path.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def workload_config(name: str) -> dict:
+    import ddgi_b200
+
+    configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
+    if name.startswith("sweep_"):
+        return configs.sweep_config(int(name.split("_")[1]))
+    return configs.CONFIGS[name]
+
+
+def _sample_rows(cfg):
+    """Middle probe rows (the representative part of the field): Y/8 rows, at least 1."""
+    Y = cfg["probe_count"][1]
+    n = max(1, Y // 8)
+    y0 = Y // 2 - n // 2
+    return y0, y0 + n
+
+
+def _oracle_scene(cfg, voxels, time_value):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+
+    return util.oracle_scene(cfg, time=time_value, voxels=voxels)
+
+
+def _time_oracle(cfg, voxels, steps, warmup, time0=0.0):
+    from oracle import oracle
+
+    rx, ry = cfg["tile"]
+    X, Y, Z = cfg["probe_count"]
+    sc = _oracle_scene(cfg, voxels, time0)
+    rays = oracle.generate_probe_rays(sc, oracle.generate_samples(rx, ry, reseed=True))
+    y0, y1 = _sample_rows(cfg)
+    per_row = X * Z * rx * ry
+    k0, k1 = y0 * per_row, y1 * per_row
+    threads = oracle.load().orc_num_threads()
+    W, H = sc.tex_size
+    tex = np.zeros((H, W), dtype=np.uint32)
+    times = []
+    lookups = None
+    for i in range(warmup + steps):
+        sc = _oracle_scene(cfg, sc.vox, time0 + 2.0 * (i + 1))
+        t0 = time.perf_counter()
+        _, _, _, st, _ = oracle.probe_update(sc, rays, k0, k1, threads=0, tex=tex)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        lookups = st[k0:k1]
+    n = k1 - k0
+    return {"rays": n, "seconds": float(np.mean(times)), "threads": threads, "rows": (y0, y1),
+            "mean_lookups": float(lookups.mean()), "tex": tex, "k": (k0, k1)}
+
+
+def cpu_baseline(rvpt, cfg, name):
+    """Oracle ("port") timed on the host cores over a bounded sample of the workload."""
+    X, Y, Z = cfg["probe_count"]
+    vox = rvpt.read_voxels(cfg["voxels"][1])
+    res = _time_oracle(cfg, vox, steps=2, warmup=1)
+    y0, y1 = res["rows"]
+    return {"value": res["rays"] / res["seconds"], "unit": "probe-rays/s", "cores": res["threads"], "kind": "port",
+            "sample": f"probe rows [{y0},{y1}) of {Y} = {res['rays']} of {X*Y*Z*cfg['tile'][0]*cfg['tile'][1]} rays "
+                      f"per step, mean of 2 steps, oracle/ddgi_oracle.c with OpenMP",
+            "mean_lookups_per_ray_in_sample": res["mean_lookups"]}
+
+
+def reference_arm(args, name):
+    """`bench.py --impl reference`: same JSON shape, the oracle on the host cores."""
+    cfg = workload_config(name)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+
+    X, Y, Z = cfg["probe_count"]
+    rx, ry = cfg["tile"]
+    vox, _ = util.oracle_voxels(cfg)
+    res = _time_oracle(cfg, vox, steps=max(1, min(args.steps, 5)), warmup=1)
+    y0, y1 = res["rows"]
+    value = res["rays"] / res["seconds"]
+    sample = (f"probe rows [{y0},{y1}) of {Y} = {res['rays']} rays per step (the GLSL reference cannot be built: "
+              f"no glslang/Vulkan/lavapipe; this is the CPU oracle port, OpenMP, all host threads)")
+    return {
+        "impl": "reference", "metric": "probe_rays_per_s", "value": value, "unit": "probe-rays/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": max(1, min(args.steps, 5)), "warmup": 1,
+        "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "probes": [X, Y, Z], "rays_per_probe": rx * ry, "probe_rays": X * Y * Z * rx * ry,
+                   "voxels": list(cfg["voxels"][1]), "lights": 4 if cfg["lights"] == "cave4" else 1,
+                   "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"])},
+        "cpu_baseline": {"value": value, "unit": "probe-rays/s", "cores": res["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "probe-rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }

@@ -1,0 +1,803 @@
+// ddgi_engine.cu — host side of libddgi_b200.so: the context that owns the device
+// buffers (what class RVPT's per-frame UBOs / SSBO / storage images were,
+// src/rvpt/rvpt.h:150-201) and the C-ABI of include/ddgi.h.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ddgi.h"
+#include "ddgi_internal.h"
+
+using namespace ddgi;
+
+struct ddgi_ctx {
+    int device = 0;
+    char err[512] = {0};
+    uint64_t launches = 0;
+    int debug = 0;
+    int variant = 1;
+    int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
+    uint32_t* d_counter = nullptr;
+
+    ddgi_render_settings rs{};
+    ddgi_irradiance_field field{};
+    bool have_field = false;
+    int rx = 0, ry = 0;
+    float cam[20] = {0};
+    bool have_cam = false;
+    int n_lights = 0;
+    Light lights[kMaxLights];
+
+    // voxel field
+    int vdim[3] = {0, 0, 0}, vorg[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
+    uint8_t* d_types = nullptr;
+    unsigned long long* d_occ = nullptr;
+    float* d_palette = nullptr;
+
+    // rays
+    std::vector<float> samples;  // rx*ry raw sphere samples (xyz)
+    float* d_dirs = nullptr;     // normalised, generated mode
+    float4* d_rays = nullptr;    // literal storage-buffer mode
+    size_t n_rays_ssbo = 0;
+    int ray_mode = 0;  // 0 none, 1 generated, 2 storage buffer
+
+    // probe textures: one allocation, albedo then distance
+    int tex_w = 0, tex_h = 0;
+    uint32_t* d_tex = nullptr;
+    float4* d_tex_f32 = nullptr;
+    uint32_t* d_ray_lookups = nullptr;
+    int row0 = 0, row1 = 0;  // probe rows owned by this context
+
+    // frame
+    int frame_w = 0, frame_h = 0;
+    uint32_t* d_frame = nullptr;
+    float4* d_frame_f32 = nullptr;
+    uint32_t* d_px_lookups = nullptr;
+
+    // fused exchange
+    int n_peers = 0, self_index = 0;
+    void* peer_base[kMaxPeers] = {nullptr};
+    bool peer_opened[kMaxPeers] = {false};
+};
+
+// ------------------------------------------------------------------ helpers
+static int fail(ddgi_ctx* c, int code, const char* fmt, ...)
+{
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, DDGI_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define NEED(cond, ...)                                        \
+    do {                                                       \
+        if (!(cond)) return fail(ctx, DDGI_E_INVALID, __VA_ARGS__); \
+    } while (0)
+
+template <typename T>
+static void dfree(T*& p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static size_t tex_texels(const ddgi_ctx* c) { return (size_t)c->tex_w * c->tex_h; }
+static size_t num_rays(const ddgi_ctx* c)
+{
+    if (!c->have_field) return 0;
+    return (size_t)c->field.probe_count[0] * c->field.probe_count[1] * c->field.probe_count[2] * c->rx * c->ry;
+}
+
+// (Re)creates the probe textures for the current field, as recreate_probe_textures
+// does when probe counts or rays/probe change (src/rvpt/rvpt.cpp:661-755).
+static int resize_textures(ddgi_ctx* ctx)
+{
+    int w = ctx->field.probe_count[0] * ctx->field.probe_count[2] * ctx->rx;
+    int h = ctx->field.probe_count[1] * ctx->ry;
+    if (w == ctx->tex_w && h == ctx->tex_h && ctx->d_tex) return DDGI_OK;
+    if (ctx->n_peers) return fail(ctx, DDGI_E_STATE, "close peers before resizing the probe textures");
+    dfree(ctx->d_tex);
+    dfree(ctx->d_tex_f32);
+    dfree(ctx->d_ray_lookups);
+    ctx->tex_w = w;
+    ctx->tex_h = h;
+    size_t n = tex_texels(ctx);
+    CU(cudaMalloc(&ctx->d_tex, 2 * n * sizeof(uint32_t)));
+    CU(cudaMemset(ctx->d_tex, 0, 2 * n * sizeof(uint32_t)));
+    return DDGI_OK;
+}
+
+static int ensure_debug_buffers(ddgi_ctx* ctx)
+{
+    if (!ctx->debug) return DDGI_OK;
+    size_t n = tex_texels(ctx);
+    if (n && !ctx->d_tex_f32) {
+        CU(cudaMalloc(&ctx->d_tex_f32, n * sizeof(float4)));
+        CU(cudaMemset(ctx->d_tex_f32, 0, n * sizeof(float4)));
+    }
+    if (n && !ctx->d_ray_lookups) {
+        CU(cudaMalloc(&ctx->d_ray_lookups, num_rays(ctx) * sizeof(uint32_t)));
+        CU(cudaMemset(ctx->d_ray_lookups, 0, num_rays(ctx) * sizeof(uint32_t)));
+    }
+    size_t px = (size_t)ctx->frame_w * ctx->frame_h;
+    if (px && !ctx->d_frame_f32) {
+        CU(cudaMalloc(&ctx->d_frame_f32, px * sizeof(float4)));
+        CU(cudaMemset(ctx->d_frame_f32, 0, px * sizeof(float4)));
+    }
+    if (px && !ctx->d_px_lookups) {
+        CU(cudaMalloc(&ctx->d_px_lookups, px * sizeof(uint32_t)));
+        CU(cudaMemset(ctx->d_px_lookups, 0, px * sizeof(uint32_t)));
+    }
+    return DDGI_OK;
+}
+
+static int resize_frame(ddgi_ctx* ctx)
+{
+    int w = ctx->rs.screen_width, h = ctx->rs.screen_height;
+    if (w == ctx->frame_w && h == ctx->frame_h && ctx->d_frame) return DDGI_OK;
+    dfree(ctx->d_frame);
+    dfree(ctx->d_frame_f32);
+    dfree(ctx->d_px_lookups);
+    ctx->frame_w = w;
+    ctx->frame_h = h;
+    if ((size_t)w * h == 0) return DDGI_OK;
+    CU(cudaMalloc(&ctx->d_frame, (size_t)w * h * sizeof(uint32_t)));
+    CU(cudaMemset(ctx->d_frame, 0, (size_t)w * h * sizeof(uint32_t)));
+    return DDGI_OK;
+}
+
+static void fill_params(const ddgi_ctx* c, FrameParams* P)
+{
+    memset(P, 0, sizeof(*P));
+    P->scene.occ = c->d_occ;
+    P->scene.types = c->d_types;
+    P->scene.palette = c->d_palette;
+    for (int a = 0; a < 3; a++) {
+        P->scene.vorg[a] = c->vorg[a];
+        P->scene.vdim[a] = c->vdim[a];
+        P->scene.nb[a] = c->nb[a];
+        P->scene.lo[a] = (float)c->vorg[a];
+        P->scene.hi[a] = (float)(c->vorg[a] + c->vdim[a] - 1);
+        P->probe_count[a] = c->field.probe_count[a];
+        P->field_origin[a] = c->field.field_origin[a];
+    }
+    P->n_lights = c->n_lights;
+    for (int i = 0; i < c->n_lights; i++) P->lights[i] = c->lights[i];
+    P->side_length = c->field.side_length;
+    P->rx = c->rx;
+    P->ry = c->ry;
+    P->max_bounces = c->rs.max_bounces;
+    P->screen_w = c->rs.screen_width;
+    P->screen_h = c->rs.screen_height;
+    memcpy(P->cam, c->cam, sizeof(P->cam));
+    // camera.glsl:37  w = 1.0/tan(0.5*hfov): a per-frame uniform, evaluated once here
+    P->cam_w = 1.0f / (float)tan((double)(0.5f * c->cam[17]));
+}
+
+// The flat-colour table of the reference's block types: 2-5 are getColorAt's own flat
+// colours (intersection.glsl:908-919); the procedural types take the base colour of
+// their branch (README.md:266 "flat colors" variant).
+static void default_palette(float* pal)
+{
+    static const float t[14][3] = {{0.f, 0.f, 0.f},       {0.99f, 0.3f, 0.3f},   {.95f, 0.f, 0.f},
+                                   {0.f, .95f, 0.f},      {0.f, 0.f, .95f},      {0.95f, 0.95f, 0.95f},
+                                   {1.f, 0.2f, 0.f},      {1.f, 0.f, 0.011f},    {1.f, 0.5f, 0.f},
+                                   {1.f, 0.5f, 0.f},      {1.f, 0.5f, 0.f},      {1.f, 0.f, 0.f},
+                                   {0.619f, 1.f, 0.278f}, {0.356f, 1.f, 0.101f}};
+    memset(pal, 0, 256 * 3 * sizeof(float));
+    memcpy(pal, t, sizeof(t));
+}
+
+static int alloc_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t origin[3], const float* palette)
+{
+    NEED(dims && origin, "null dims/origin");
+    NEED(dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "voxel dims must be positive");
+    NEED((size_t)dims[0] * dims[1] * dims[2] <= ((size_t)1 << 34), "voxel field too large");
+    for (int a = 0; a < 3; a++)
+        NEED(origin[a] > -(1 << 22) && origin[a] + dims[a] < (1 << 22), "voxel ids must stay below 2^22");
+    dfree(ctx->d_types);
+    dfree(ctx->d_occ);
+    for (int a = 0; a < 3; a++) {
+        ctx->vdim[a] = dims[a];
+        ctx->vorg[a] = origin[a];
+        ctx->nb[a] = (dims[a] + 3) / 4;
+    }
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    size_t nbk = (size_t)ctx->nb[0] * ctx->nb[1] * ctx->nb[2];
+    CU(cudaMalloc(&ctx->d_types, n));
+    CU(cudaMalloc(&ctx->d_occ, nbk * sizeof(unsigned long long)));
+    if (!ctx->d_palette) CU(cudaMalloc(&ctx->d_palette, 256 * 3 * sizeof(float)));
+    float pal[256 * 3];
+    if (palette) memcpy(pal, palette, sizeof(pal));
+    else default_palette(pal);
+    CU(cudaMemcpy(ctx->d_palette, pal, sizeof(pal), cudaMemcpyHostToDevice));
+    return DDGI_OK;
+}
+
+static int finish_voxels(ddgi_ctx* ctx)
+{
+    int l = 0;
+    CU(launch_build_occupancy(ctx->vdim, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
+    ctx->launches += l;
+    CU(cudaDeviceSynchronize());
+    return DDGI_OK;
+}
+
+// generate_samples, src/rvpt/rvpt.cpp:1147-1173, generalised to an rx x ry tile: libc
+// rand() jitter (x first), PI = 3.1415926 as a double, libm cosf/sinf/sqrtf.
+static void host_generate_samples(int rx, int ry, std::vector<float>& out)
+{
+    const double host_pi = 3.1415926;
+    float inv_x = 1.f / float(rx), inv_y = 1.f / float(ry);
+    out.resize((size_t)rx * ry * 3);
+    size_t i = 0;
+    for (int y = 0; y < ry; y++)
+        for (int x = 0; x < rx; x++) {
+            float jx = float(rand()) / float(RAND_MAX);
+            float jy = float(rand()) / float(RAND_MAX);
+            float su = (x + jx) * inv_x;
+            float sv = (y + jy) * inv_y;
+            float z = 1 - (2 * su);
+            float ang = (float)(2.0f * host_pi * sv);
+            float ring = sqrtf(1 - (z * z));
+            out[i++] = cosf(ang) * ring;
+            out[i++] = sinf(ang) * ring;
+            out[i++] = z;
+        }
+}
+
+static int upload_dirs(ddgi_ctx* ctx)
+{
+    size_t n = (size_t)ctx->rx * ctx->ry;
+    std::vector<float> dirs(n * 3);
+    for (size_t i = 0; i < n; i++) {
+        v3 d = normalize(V3(ctx->samples[3 * i], ctx->samples[3 * i + 1], ctx->samples[3 * i + 2]));
+        dirs[3 * i] = d.x;
+        dirs[3 * i + 1] = d.y;
+        dirs[3 * i + 2] = d.z;
+    }
+    dfree(ctx->d_dirs);
+    CU(cudaMalloc(&ctx->d_dirs, n * 3 * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_dirs, dirs.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->ray_mode = 1;
+    return DDGI_OK;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* ddgi_version(void) { return "0.1 sm_100a"; }
+
+int ddgi_create(ddgi_ctx** out, int device)
+{
+    if (!out) return DDGI_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return DDGI_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return DDGI_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DDGI_E_CUDA;
+    if (prop.major != 10) return DDGI_E_CUDA;  // sm_100a code only
+    ddgi_ctx* ctx = new ddgi_ctx();
+    ctx->device = device;
+    if (cudaMalloc(&ctx->d_counter, sizeof(uint32_t)) != cudaSuccess) {
+        delete ctx;
+        return DDGI_E_CUDA;
+    }
+    *out = ctx;
+    return DDGI_OK;
+}
+
+void ddgi_destroy(ddgi_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ddgi_close_peers(ctx);
+    dfree(ctx->d_counter);
+    dfree(ctx->d_types);
+    dfree(ctx->d_occ);
+    dfree(ctx->d_palette);
+    dfree(ctx->d_dirs);
+    dfree(ctx->d_rays);
+    dfree(ctx->d_tex);
+    dfree(ctx->d_tex_f32);
+    dfree(ctx->d_ray_lookups);
+    dfree(ctx->d_frame);
+    dfree(ctx->d_frame_f32);
+    dfree(ctx->d_px_lookups);
+    delete ctx;
+}
+
+const char* ddgi_last_error(const ddgi_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+uint64_t ddgi_launch_count(const ddgi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ddgi_set_render_settings(ddgi_ctx* ctx, const ddgi_render_settings* rs)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(rs, "null settings");
+    NEED(rs->screen_width >= 0 && rs->screen_height >= 0 && rs->screen_width <= 16384 && rs->screen_height <= 16384,
+         "bad screen size");
+    NEED(rs->max_bounces >= 0 && rs->max_bounces <= 64, "max_bounces out of range");
+    NEED(rs->camera_mode == 0, "only the pinhole camera (camera_mode 0) is supported");
+    NEED(rs->render_mode == 0, "only the DDGI integrator (render_mode 0) is supported");
+    NEED(rs->visualize_probes == 0, "probe visualisation is not supported");
+    CU(cudaSetDevice(ctx->device));
+    ctx->rs = *rs;
+    return resize_frame(ctx);
+}
+
+int ddgi_set_irradiance_field(ddgi_ctx* ctx, const ddgi_irradiance_field* f)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(f, "null field");
+    for (int a = 0; a < 3; a++) NEED(f->probe_count[a] >= 1 && f->probe_count[a] <= 1024, "probe_count out of range");
+    NEED(f->side_length >= 1, "side_length must be >= 1");
+    NEED(f->sqrt_rays_per_probe >= 1 && f->sqrt_rays_per_probe <= 64, "sqrt_rays_per_probe out of range");
+    size_t probes = (size_t)f->probe_count[0] * f->probe_count[1] * f->probe_count[2];
+    NEED(probes < ((size_t)1 << 24), "probe index must be exact in fp32 (< 2^24), src/rvpt/probe.h:13");
+    NEED(probes * f->sqrt_rays_per_probe * f->sqrt_rays_per_probe < ((size_t)1 << 32), "too many rays");
+    CU(cudaSetDevice(ctx->device));
+    bool shape_changed = !ctx->have_field || memcmp(ctx->field.probe_count, f->probe_count, sizeof(f->probe_count)) ||
+                         ctx->field.sqrt_rays_per_probe != f->sqrt_rays_per_probe;
+    ctx->field = *f;
+    ctx->have_field = true;
+    if (shape_changed) {
+        ctx->rx = ctx->ry = f->sqrt_rays_per_probe;
+        ctx->ray_mode = 0;
+        ctx->row0 = 0;
+        ctx->row1 = f->probe_count[1];
+        return resize_textures(ctx);
+    }
+    return DDGI_OK;
+}
+
+int ddgi_set_ray_tile(ddgi_ctx* ctx, int32_t rx, int32_t ry)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    NEED(rx >= 1 && ry >= 1 && rx <= 64 && ry <= 64, "tile out of range");
+    CU(cudaSetDevice(ctx->device));
+    if (rx != ctx->rx || ry != ctx->ry) {
+        ctx->rx = rx;
+        ctx->ry = ry;
+        ctx->ray_mode = 0;
+        return resize_textures(ctx);
+    }
+    return DDGI_OK;
+}
+
+int ddgi_set_camera(ddgi_ctx* ctx, const float cam[20])
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(cam, "null camera");
+    memcpy(ctx->cam, cam, sizeof(ctx->cam));
+    ctx->have_cam = true;
+    return DDGI_OK;
+}
+
+int ddgi_set_lights(ddgi_ctx* ctx, int32_t n, const ddgi_light* lights)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(n >= 0 && n <= DDGI_MAX_LIGHTS, "at most %d lights", DDGI_MAX_LIGHTS);
+    NEED(n == 0 || lights, "null lights");
+    ctx->n_lights = n;
+    for (int i = 0; i < n; i++) {
+        ctx->lights[i].intensity = lights[i].intensity;
+        for (int a = 0; a < 3; a++) {
+            ctx->lights[i].col[a] = lights[i].col[a];
+            ctx->lights[i].pos[a] = lights[i].pos[a];
+        }
+    }
+    return DDGI_OK;
+}
+
+int ddgi_default_lights(int32_t scene, ddgi_light* out, int32_t* n)
+{
+    if (!out || !n) return DDGI_E_INVALID;
+    static const ddgi_light cave = {100.f, {1.f, 1.f, 1.f}, {4.f, 17.5f, 8.5f}};
+    static const ddgi_light cornell = {15.f, {1.f, 1.f, 1.f}, {0.f, 8.f, 13.f}};
+    static const ddgi_light house[2] = {{1.f, {1.f, 1.f, 1.f}, {5.f, 9.3f, 36.5f}}, {1.f, {1.f, 1.f, 1.f}, {0.f, 0.f, 0.f}}};
+    switch (scene) {
+        case 0: out[0] = cave; *n = 1; return DDGI_OK;
+        case 1: out[0] = cornell; *n = 1; return DDGI_OK;
+        case 2: out[0] = house[0]; out[1] = house[1]; *n = 2; return DDGI_OK;
+    }
+    *n = 0;
+    return DDGI_E_INVALID;
+}
+
+int ddgi_cave_lights4(float time, ddgi_light* out)
+{
+    if (!out) return DDGI_E_INVALID;
+    static const ddgi_light base[4] = {{20.f, {1.f, 1.f, 1.f}, {4.f, 17.5f, 8.5f}},
+                                       {10.f, {1.f, 0.5f, 0.1f}, {0.f, 2.f, 0.f}},
+                                       {10.f, {0.1f, 1.1f, 1.f}, {5.f, 0.f, 0.f}},
+                                       {10.f, {1.1f, 0.f, 1.1f}, {0.f, 5.f, 0.f}}};
+    float t = 0.05f * time;
+    for (int i = 0; i < 4; i++) {
+        out[i] = base[i];
+        if (i == 0) {
+            out[i].pos[2] = base[i].pos[2] + 10.0f * pin_cos(t * 0.1f);
+            continue;
+        }
+        float s = pin_sin(t * 0.5f), c = pin_cos(t * 0.5f);
+        out[i].pos[0] = base[i].pos[0] + (float)((i + 1) * 2) * s;
+        out[i].pos[1] = base[i].pos[1] + (float)((i / 2) * 4) * s;
+        out[i].pos[2] = base[i].pos[2] + (float)((i + 1) * 2) * c;
+    }
+    return DDGI_OK;
+}
+
+int ddgi_upload_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t origin[3], const uint8_t* types,
+                       const float* palette)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(types, "null voxel types");
+    CU(cudaSetDevice(ctx->device));
+    int rc = alloc_voxels(ctx, dims, origin, palette);
+    if (rc) return rc;
+    CU(cudaMemcpy(ctx->d_types, types, (size_t)dims[0] * dims[1] * dims[2], cudaMemcpyHostToDevice));
+    return finish_voxels(ctx);
+}
+
+int ddgi_bake_scene(ddgi_ctx* ctx, int32_t scene, const int32_t dims[3], const int32_t origin[3])
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(scene >= 0 && scene <= 2, "scene must be 0, 1 or 2");
+    CU(cudaSetDevice(ctx->device));
+    int rc = alloc_voxels(ctx, dims, origin, nullptr);
+    if (rc) return rc;
+    int l = 0;
+    CU(launch_bake_scene(scene, ctx->vdim, ctx->vorg, ctx->d_types, 0, &l));
+    ctx->launches += l;
+    return finish_voxels(ctx);
+}
+
+int ddgi_bake_synthetic(ddgi_ctx* ctx, const int32_t dims[3], const int32_t origin[3], int32_t solid_permille,
+                        uint32_t seed)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(solid_permille >= 0 && solid_permille <= 1000, "solid_permille in [0,1000]");
+    CU(cudaSetDevice(ctx->device));
+    int rc = alloc_voxels(ctx, dims, origin, nullptr);
+    if (rc) return rc;
+    int l = 0;
+    CU(launch_bake_synthetic(ctx->vdim, ctx->vorg, solid_permille, seed, ctx->d_types, 0, &l));
+    ctx->launches += l;
+    return finish_voxels(ctx);
+}
+
+int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_types, "no voxel field");
+    NEED(dst && bytes == (size_t)ctx->vdim[0] * ctx->vdim[1] * ctx->vdim[2], "size mismatch");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(dst, ctx->d_types, bytes, cudaMemcpyDeviceToHost));
+    return DDGI_OK;
+}
+
+int ddgi_generate_probe_rays(ddgi_ctx* ctx, int32_t reseed)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    CU(cudaSetDevice(ctx->device));
+    if (reseed) srand(1);
+    host_generate_samples(ctx->rx, ctx->ry, ctx->samples);
+    return upload_dirs(ctx);
+}
+
+int ddgi_set_ray_samples(ddgi_ctx* ctx, const float* samples, size_t count)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    NEED(samples && count == (size_t)ctx->rx * ctx->ry, "expected rx*ry samples");
+    CU(cudaSetDevice(ctx->device));
+    ctx->samples.assign(samples, samples + 3 * count);
+    return upload_dirs(ctx);
+}
+
+int ddgi_get_ray_samples(ddgi_ctx* ctx, float* dst, size_t count)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->ray_mode == 1, "no generated ray set");
+    NEED(dst && count * 3 == ctx->samples.size(), "expected rx*ry samples");
+    memcpy(dst, ctx->samples.data(), ctx->samples.size() * sizeof(float));
+    return DDGI_OK;
+}
+
+int ddgi_set_probe_rays(ddgi_ctx* ctx, const ddgi_probe_ray* rays, size_t count)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    NEED(rays && count == num_rays(ctx), "expected probes*rx*ry rays");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n_rays_ssbo != count) {
+        dfree(ctx->d_rays);
+        CU(cudaMalloc(&ctx->d_rays, count * sizeof(ddgi_probe_ray)));
+        ctx->n_rays_ssbo = count;
+    }
+    CU(cudaMemcpy(ctx->d_rays, rays, count * sizeof(ddgi_probe_ray), cudaMemcpyHostToDevice));
+    ctx->ray_mode = 2;
+    return DDGI_OK;
+}
+
+size_t ddgi_num_probe_rays(const ddgi_ctx* ctx) { return ctx ? num_rays(ctx) : 0; }
+
+// RVPT::generate_probe_rays, src/rvpt/rvpt.cpp:1177-1224
+int ddgi_get_probe_rays(ddgi_ctx* ctx, ddgi_probe_ray* dst, size_t count)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->ray_mode != 0, "no ray set");
+    NEED(dst && count == num_rays(ctx), "expected probes*rx*ry rays");
+    if (ctx->ray_mode == 2) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMemcpy(dst, ctx->d_rays, count * sizeof(ddgi_probe_ray), cudaMemcpyDeviceToHost));
+        return DDGI_OK;
+    }
+    FrameParams P;
+    fill_params(ctx, &P);
+    int n = ctx->rx * ctx->ry;
+    int probes = (int)(count / n);
+    size_t o = 0;
+    for (int p = 0; p < probes; p++) {
+        v3 org = probe_origin(P, p);
+        for (int i = 0; i < n; i++) {
+            v3 d = normalize(V3(ctx->samples[3 * i], ctx->samples[3 * i + 1], ctx->samples[3 * i + 2]));
+            ddgi_probe_ray* r = &dst[o++];
+            memset(r, 0, sizeof(*r));
+            r->origin[0] = org.x; r->origin[1] = org.y; r->origin[2] = org.z;
+            r->direction[0] = d.x; r->direction[1] = d.y; r->direction[2] = d.z;
+            r->probe_info[0] = (float)p;
+            r->probe_info[1] = (float)(i % ctx->rx);
+            r->probe_info[2] = (float)(i / ctx->rx);
+        }
+    }
+    return DDGI_OK;
+}
+
+int ddgi_set_probe_rows(ddgi_ctx* ctx, int32_t y0, int32_t y1)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    NEED(0 <= y0 && y0 <= y1 && y1 <= ctx->field.probe_count[1], "rows out of range");
+    ctx->row0 = y0;
+    ctx->row1 = y1;
+    return DDGI_OK;
+}
+
+int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** ptr, size_t* bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex, "no probe texture");
+    NEED(ptr && bytes && (which == 0 || which == 1), "bad arguments");
+    *ptr = ctx->d_tex + (which ? tex_texels(ctx) : 0);
+    *bytes = tex_texels(ctx) * sizeof(uint32_t);
+    return DDGI_OK;
+}
+
+int ddgi_export_texture_handle(ddgi_ctx* ctx, void* handle64)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex && handle64, "no probe texture");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_tex));
+    memcpy(handle64, &h, 64);
+    return DDGI_OK;
+}
+
+int ddgi_open_peers(ddgi_ctx* ctx, int32_t n_peers, const void* handles64, int32_t self_index)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex, "no probe texture");
+    NEED(n_peers >= 1 && n_peers <= kMaxPeers && handles64 && self_index >= 0 && self_index < n_peers, "bad peers");
+    CU(cudaSetDevice(ctx->device));
+    ddgi_close_peers(ctx);
+    for (int g = 0; g < n_peers; g++) {
+        if (g == self_index) {
+            ctx->peer_base[g] = ctx->d_tex;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles64 + 64 * g, 64);
+        CU(cudaIpcOpenMemHandle(&ctx->peer_base[g], h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_opened[g] = true;
+    }
+    ctx->n_peers = n_peers;
+    ctx->self_index = self_index;
+    return DDGI_OK;
+}
+
+int ddgi_close_peers(ddgi_ctx* ctx)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    for (int g = 0; g < kMaxPeers; g++) {
+        if (ctx->peer_opened[g]) cudaIpcCloseMemHandle(ctx->peer_base[g]);
+        ctx->peer_opened[g] = false;
+        ctx->peer_base[g] = nullptr;
+    }
+    ctx->n_peers = 0;
+    return DDGI_OK;
+}
+
+int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (!ctx->have_field || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no irradiance field");
+    if (!ctx->d_occ) return fail(ctx, DDGI_E_STATE, "no voxel field");
+    if (ctx->ray_mode == 0) return fail(ctx, DDGI_E_STATE, "no probe rays: call ddgi_generate_probe_rays or ddgi_set_probe_rays");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_debug_buffers(ctx);
+    if (rc) return rc;
+    FrameParams P;
+    fill_params(ctx, &P);
+    ProbeJob J;
+    memset(&J, 0, sizeof(J));
+    J.rays = ctx->ray_mode == 2 ? ctx->d_rays : nullptr;
+    J.dirs = ctx->d_dirs;
+    uint32_t per_row = (uint32_t)(ctx->field.probe_count[0] * ctx->field.probe_count[2] * ctx->rx * ctx->ry);
+    J.ray_begin = (uint32_t)ctx->row0 * per_row;
+    J.ray_end = (uint32_t)ctx->row1 * per_row;
+    J.tex_w = ctx->tex_w;
+    J.tex_h = ctx->tex_h;
+    J.albedo = ctx->d_tex;
+    J.distance = ctx->d_tex + tex_texels(ctx);
+    J.albedo_f32 = ctx->debug ? ctx->d_tex_f32 : nullptr;
+    J.lookups = ctx->debug ? ctx->d_ray_lookups : nullptr;
+    for (int g = 0; g < ctx->n_peers; g++) {
+        if (g == ctx->self_index) continue;
+        J.peer_albedo[J.n_peers] = (uint32_t*)ctx->peer_base[g];
+        J.peer_distance[J.n_peers] = (uint32_t*)ctx->peer_base[g] + tex_texels(ctx);
+        J.n_peers++;
+    }
+    int l = 0;
+    CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, (cudaStream_t)stream, &l));
+    ctx->launches += l;
+    return DDGI_OK;
+}
+
+int ddgi_render_frame(ddgi_ctx* ctx, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (!ctx->have_field || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no irradiance field");
+    if (!ctx->d_occ) return fail(ctx, DDGI_E_STATE, "no voxel field");
+    if (!ctx->have_cam) return fail(ctx, DDGI_E_STATE, "no camera");
+    if (!ctx->d_frame) return fail(ctx, DDGI_E_STATE, "no frame: set render settings with a non-empty screen");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_debug_buffers(ctx);
+    if (rc) return rc;
+    FrameParams P;
+    fill_params(ctx, &P);
+    PixelJob J;
+    memset(&J, 0, sizeof(J));
+    J.albedo = ctx->d_tex;
+    J.tex_w = ctx->tex_w;
+    J.frame = ctx->d_frame;
+    J.frame_f32 = ctx->debug ? ctx->d_frame_f32 : nullptr;
+    J.lookups = ctx->debug ? ctx->d_px_lookups : nullptr;
+    int l = 0;
+    CU(launch_render_frame(P, J, (cudaStream_t)stream, &l));
+    ctx->launches += l;
+    return DDGI_OK;
+}
+
+int ddgi_sync(ddgi_ctx* ctx)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    return DDGI_OK;
+}
+
+int ddgi_probe_texture_size(const ddgi_ctx* ctx, int32_t* width, int32_t* height)
+{
+    if (!ctx || !width || !height) return DDGI_E_INVALID;
+    *width = ctx->tex_w;
+    *height = ctx->tex_h;
+    return DDGI_OK;
+}
+
+int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, void* dst, size_t bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex, "no probe texture");
+    NEED(dst && (which == 0 || which == 1), "bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = tex_texels(ctx);
+    if (fmt == DDGI_FMT_RGBA8) {
+        NEED(bytes == n * 4, "expected width*height*4 bytes");
+        CU(cudaMemcpy(dst, ctx->d_tex + (which ? n : 0), bytes, cudaMemcpyDeviceToHost));
+        return DDGI_OK;
+    }
+    if (fmt == DDGI_FMT_F32) {
+        NEED(which == 0 && ctx->d_tex_f32, "fp32 copy exists only for the albedo texture in debug mode");
+        NEED(bytes == n * 16, "expected width*height*16 bytes");
+        CU(cudaMemcpy(dst, ctx->d_tex_f32, bytes, cudaMemcpyDeviceToHost));
+        return DDGI_OK;
+    }
+    return fail(ctx, DDGI_E_INVALID, "unknown format");
+}
+
+int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size_t bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex, "no probe texture");
+    NEED(src && (which == 0 || which == 1) && bytes == tex_texels(ctx) * 4, "expected width*height*4 bytes");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(ctx->d_tex + (which ? tex_texels(ctx) : 0), src, bytes, cudaMemcpyHostToDevice));
+    return DDGI_OK;
+}
+
+int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_frame && dst, "no frame");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = (size_t)ctx->frame_w * ctx->frame_h;
+    if (fmt == DDGI_FMT_RGBA8) {
+        NEED(bytes == n * 4, "expected w*h*4 bytes");
+        CU(cudaMemcpy(dst, ctx->d_frame, bytes, cudaMemcpyDeviceToHost));
+        return DDGI_OK;
+    }
+    if (fmt == DDGI_FMT_F32) {
+        NEED(ctx->d_frame_f32, "fp32 frame exists only in debug mode");
+        NEED(bytes == n * 16, "expected w*h*16 bytes");
+        CU(cudaMemcpy(dst, ctx->d_frame_f32, bytes, cudaMemcpyDeviceToHost));
+        return DDGI_OK;
+    }
+    return fail(ctx, DDGI_E_INVALID, "unknown format");
+}
+
+int ddgi_set_debug(ddgi_ctx* ctx, int32_t debug)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    ctx->debug = debug != 0;
+    return DDGI_OK;
+}
+
+int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t count)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(dst, "null dst");
+    CU(cudaSetDevice(ctx->device));
+    if (which == 0) {
+        NEED(ctx->d_ray_lookups && count == num_rays(ctx), "no per-ray counts (debug mode off?)");
+        CU(cudaMemcpy(dst, ctx->d_ray_lookups, count * 4, cudaMemcpyDeviceToHost));
+        return DDGI_OK;
+    }
+    NEED(ctx->d_px_lookups && count == (size_t)ctx->frame_w * ctx->frame_h, "no per-pixel counts (debug mode off?)");
+    CU(cudaMemcpy(dst, ctx->d_px_lookups, count * 4, cudaMemcpyDeviceToHost));
+    return DDGI_OK;
+}
+
+int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(variant == 0 || variant == 1, "variant must be 0 or 1");
+    ctx->variant = variant;
+    return DDGI_OK;
+}
+
+int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(march_min >= 1 && march_min <= 32, "march_min in [1,32]");
+    ctx->march_min = march_min;
+    return DDGI_OK;
+}
+
+}  // extern "C"

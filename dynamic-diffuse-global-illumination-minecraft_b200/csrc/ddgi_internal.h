@@ -1,0 +1,46 @@
+// ddgi_internal.h — launcher interface between the C-ABI host code (ddgi_engine.cu)
+// and the kernels (ddgi_kernels.cu).  Not installed; the public surface is include/ddgi.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ddgi_trace.cuh"
+
+namespace ddgi {
+
+constexpr int kMaxPeers = 8;
+
+// Everything the probe-update kernels need besides FrameParams.
+struct ProbeJob {
+    const float4* rays;   // literal 48-byte ProbeRay records (3 x float4) or nullptr
+    const float* dirs;    // generated mode: rx*ry normalised directions (xyz)
+    uint32_t ray_begin;   // first / one-past-last linear ray index of this shard
+    uint32_t ray_end;
+    int tex_w, tex_h;
+    uint32_t* albedo;     // W*H RGBA8
+    uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)
+    float4* albedo_f32;   // debug: pre-quantisation values, or nullptr
+    uint32_t* lookups;    // debug: per-ray voxel lookups, or nullptr
+    int n_peers;          // fused exchange: replicas to store every texel into
+    uint32_t* peer_albedo[kMaxPeers];
+    uint32_t* peer_distance[kMaxPeers];
+};
+
+struct PixelJob {
+    const uint32_t* albedo;  // probe texture
+    int tex_w;
+    uint32_t* frame;        // w*h RGBA8
+    float4* frame_f32;      // debug or nullptr
+    uint32_t* lookups;      // debug or nullptr
+};
+
+cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
+                                int march_min, cudaStream_t s, int* launches);
+cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStream_t s, int* launches);
+cudaError_t launch_bake_scene(int scene, const int dims[3], const int org[3], uint8_t* types,
+                              cudaStream_t s, int* launches);
+cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permille, uint32_t seed,
+                                  uint8_t* types, cudaStream_t s, int* launches);
+cudaError_t launch_build_occupancy(const int dims[3], const int nb[3], const uint8_t* types,
+                                   unsigned long long* occ, cudaStream_t s, int* launches);
+
+}  // namespace ddgi

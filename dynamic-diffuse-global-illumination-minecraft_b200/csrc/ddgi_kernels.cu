@@ -1,0 +1,311 @@
+// ddgi_kernels.cu — sm_100a kernels of the DDGI probe-field engine.
+//
+//   probe_update_direct   one thread per probe ray, reference loop order
+//                         (assets/shaders/probe_pass.comp:253-303)
+//   render_frame_kernel   one thread per pixel (assets/shaders/compute_pass.comp:162-191)
+//   bake_* / build_occupancy   scene preparation
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (see csrc/Makefile).
+#include "ddgi_internal.h"
+#include "ddgi_shade.cuh"
+#include "ddgi_wavefront.cuh"
+
+namespace ddgi {
+
+// ------------------------------------------------------------------ ray fetch
+struct RayIn {
+    v3 origin, direction;
+    int tx, ty;  // destination texel
+};
+
+// Ray k either from the caller's storage buffer (48-byte records, three 16-byte
+// loads) or derived from the lattice formula and the per-probe direction table.
+__device__ __forceinline__ RayIn fetch_ray(const FrameParams& P, const ProbeJob& J, uint32_t k)
+{
+    RayIn r;
+    int tiles_x = P.probe_count[0] * P.probe_count[2];
+    if (J.rays) {
+        float4 a = __ldg(J.rays + 3 * (size_t)k);
+        float4 b = __ldg(J.rays + 3 * (size_t)k + 1);
+        float4 c = __ldg(J.rays + 3 * (size_t)k + 2);
+        r.origin = V3(a.x, a.y, a.z);
+        r.direction = V3(b.x, b.y, b.z);
+        int p = f2i(c.x);
+        int yp = p / tiles_x;
+        int xp = p - yp * tiles_x;
+        r.tx = xp * P.rx + f2i(c.y);
+        r.ty = yp * P.ry + f2i(c.z);
+    } else {
+        int n = P.rx * P.ry;
+        int p = (int)(k / (uint32_t)n);
+        int i = (int)(k - (uint32_t)p * (uint32_t)n);
+        r.origin = probe_origin(P, p);
+        r.direction = V3(__ldg(J.dirs + 3 * i), __ldg(J.dirs + 3 * i + 1), __ldg(J.dirs + 3 * i + 2));
+        int yp = p / tiles_x;
+        int xp = p - yp * tiles_x;
+        int iy = i / P.rx;
+        r.tx = xp * P.rx + (i - iy * P.rx);
+        r.ty = yp * P.ry + iy;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v3 color, uint32_t k,
+                                            uint32_t lookups)
+{
+    size_t t = (size_t)ty * J.tex_w + tx;
+    uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);
+    J.albedo[t] = rgba;
+    J.distance[t] = 0u;  // probe_pass.comp:276,302: distances = vec2(0)
+    for (int g = 0; g < J.n_peers; g++) {
+        J.peer_albedo[g][t] = rgba;
+        J.peer_distance[g][t] = 0u;
+    }
+    if (J.albedo_f32) J.albedo_f32[t] = make_float4(color.x, color.y, color.z, 1.0f);
+    if (J.lookups) J.lookups[k] = lookups;
+}
+
+// ------------------------------------------------------------------ variant 0
+__global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant__ FrameParams P,
+                                                           const __grid_constant__ ProbeJob J)
+{
+    uint32_t k = J.ray_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= J.ray_end) return;
+    RayIn r = fetch_ray(P, J, k);
+    uint32_t lookups = 0;
+    v3 color = trace_probe_ray(P, r.origin, r.direction, k, lookups);
+    store_texel(J, r.tx, r.ty, color, k, lookups);
+}
+
+// ------------------------------------------------------------------ variant 1
+// Persistent warps over a global ray counter.  Each lane owns one probe ray as a WfRay
+// state machine.  The warp spins in the DDA step loop while at least `march_min/32` of
+// its live lanes are still marching, then runs the transition code once for every lane
+// whose march ended, retires finished rays (one texel store each) and refills the free
+// lanes with the next rays from the counter.
+constexpr int kWfThreads = 128;
+
+__global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __grid_constant__ FrameParams P,
+                                                                     const __grid_constant__ ProbeJob J,
+                                                                     uint32_t* __restrict__ next_ray,
+                                                                     int march_min)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    WfRay R;
+    R.mode = WF_DONE;
+    bool has_ray = false;
+    bool exhausted = false;
+    uint32_t k = 0;
+    int tx = 0, ty = 0;
+
+    for (;;) {
+        // ---- retire + refill ----
+        if (has_ray && R.mode == WF_DONE) {
+            store_texel(J, tx, ty, R.color, k, R.lookups);
+            has_ray = false;
+        }
+        unsigned want = __ballot_sync(full, !has_ray);
+        if (want && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next_ray, (uint32_t)__popc(want));
+            base = __shfl_sync(full, base, 0);
+            if (base >= J.ray_end - J.ray_begin) exhausted = true;
+            if (!has_ray) {
+                uint32_t idx = base + (uint32_t)__popc(want & ((1u << lane) - 1u));
+                if (idx < J.ray_end - J.ray_begin) {
+                    k = J.ray_begin + idx;
+                    RayIn r = fetch_ray(P, J, k);
+                    tx = r.tx;
+                    ty = r.ty;
+                    wf_init(P, R, r.origin, r.direction, k);
+                    has_ray = true;
+                }
+            }
+        }
+        unsigned live = __ballot_sync(full, has_ray);
+        if (live == 0) break;
+        const int n_live = __popc(live);
+
+        // ---- march phase ----
+        for (;;) {
+            bool marching = has_ray && R.mode == WF_MARCH;
+            int n_march = __popc(__ballot_sync(full, marching));
+            if (n_march == 0 || n_march * 32 < n_live * march_min) break;
+            if (marching) wf_step(P, R);
+        }
+
+        // ---- transition phase ----
+        if (has_ray && R.mode == WF_PENDING) wf_transition(P, R);
+    }
+}
+
+// ------------------------------------------------------------------ pixel pass
+// The reference dispatches floor(w/16) x floor(h/16) groups of 16x16: pixels beyond
+// that are never written (src/rvpt/rvpt.cpp:1139-1140).
+__global__ void __launch_bounds__(256) render_frame_kernel(const __grid_constant__ FrameParams P,
+                                                           const __grid_constant__ PixelJob J)
+{
+    int gx = blockIdx.x * 16 + (threadIdx.x & 15);
+    int gy = blockIdx.y * 16 + (threadIdx.x >> 4);
+    float cx = (float)gx / (float)P.screen_w;
+    float cy = (float)gy / (float)P.screen_h;
+    cy = 1.0f - cy;
+    v3 o, d;
+    pinhole_ray(P, cx, cy, &o, &d);
+    uint32_t lookups = 0;
+    v3 s = shade_ddgi(P, J.albedo, J.tex_w, o, d, lookups);
+    s = V3(0, 0, 0) + s;  // `sampled += ...`
+    size_t at = (size_t)gy * P.screen_w + gx;
+    J.frame[at] = pack_rgba8(s.x, s.y, s.z, 1.0f);
+    if (J.frame_f32) J.frame_f32[at] = make_float4(s.x, s.y, s.z, 1.0f);
+    if (J.lookups) J.lookups[at] = lookups;
+}
+
+// ------------------------------------------------------------------ scene preparation
+__global__ void bake_scene_kernel(int scene, int dx, int dy, int dz, int ox, int oy, int oz, uint8_t* types)
+{
+    size_t n = (size_t)dx * dy * dz;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % dx);
+        int y = (int)((i / dx) % dy);
+        int z = (int)(i / ((size_t)dx * dy));
+        v3 c = V3((float)(x + ox), (float)(y + oy), (float)(z + oz));
+        types[i] = (uint8_t)block_procedural(c, scene);
+    }
+}
+
+// Integer-only synthetic cave: the reference cave's four spheres (radii 20,20,18,21 at
+// offsets (0,0,0), (-16,-8,10), (13,1,-19), (-20,-15,-15), intersection.glsl:744-750)
+// scaled by dims/64 around the grid centre; rock (type 10) outside their union, and
+// inside it `permille` of the cells solid with one of six flat block types 2..7.
+__global__ void bake_synthetic_kernel(int dx, int dy, int dz, int permille, uint32_t seed, uint8_t* types)
+{
+    const int sph[4][4] = {{0, 0, 0, 20}, {-16, -8, 10, 20}, {13, 1, -19, 18}, {-20, -15, -15, 21}};
+    size_t n = (size_t)dx * dy * dz;
+    int mind = min(dx, min(dy, dz));
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % dx);
+        int y = (int)((i / dx) % dy);
+        int z = (int)(i / ((size_t)dx * dy));
+        // position relative to the grid centre in 1/64ths of the grid: compare
+        // |64*(g - dim/2) - mind*centre|^2 < (mind*radius)^2 in 64-bit integers
+        bool inside = false;
+        for (int s = 0; s < 4; s++) {
+            long long ex = 64ll * x - 32ll * dx - (long long)mind * sph[s][0];
+            long long ey = 64ll * y - 32ll * dy - (long long)mind * sph[s][1];
+            long long ez = 64ll * z - 32ll * dz - (long long)mind * sph[s][2];
+            long long rr = (long long)mind * sph[s][3];
+            if (ex * ex + ey * ey + ez * ez < rr * rr) inside = true;
+        }
+        uint8_t t = 10;
+        if (inside) {
+            uint32_t h = wang_hash((uint32_t)i ^ seed);
+            h ^= (uint32_t)(i >> 32) * 0x9E3779B9u;
+            h ^= h << 13;
+            h ^= h >> 17;
+            h ^= h << 5;
+            t = (h % 1000u) < (uint32_t)permille ? (uint8_t)(2 + (h >> 10) % 6u) : 0;
+        }
+        types[i] = t;
+    }
+}
+
+// One thread per 4x4x4 brick: gathers 64 type bytes into the occupancy word.
+__global__ void build_occupancy_kernel(int dx, int dy, int dz, int nbx, int nby, int nbz,
+                                       const uint8_t* types, unsigned long long* occ)
+{
+    size_t nb = (size_t)nbx * nby * nbz;
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+        int bx = (int)(b % nbx);
+        int by = (int)((b / nbx) % nby);
+        int bz = (int)(b / ((size_t)nbx * nby));
+        unsigned long long w = 0ull;
+        for (int z = 0; z < 4; z++)
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++) {
+                    int gx = bx * 4 + x, gy = by * 4 + y, gz = bz * 4 + z;
+                    if (gx < dx && gy < dy && gz < dz &&
+                        types[((size_t)gz * dy + gy) * dx + gx] != 0)
+                        w |= 1ull << (x | (y << 2) | (z << 4));
+                }
+        occ[b] = w;
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
+                                int march_min, cudaStream_t s, int* launches)
+{
+    uint32_t n = J.ray_end - J.ray_begin;
+    if (n == 0) return cudaSuccess;
+    if (variant == 0) {
+        dim3 block(256), grid((n + 255) / 256);
+        probe_update_direct<<<grid, block, 0, s>>>(P, J);
+        (*launches)++;
+        return cudaGetLastError();
+    }
+    static int blocks_per_sm = 0, sms = 0;
+    if (!blocks_per_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront, kWfThreads, 0);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    uint32_t warps_needed = (n + 31) / 32;
+    uint32_t blocks_needed = (warps_needed + kWfThreads / 32 - 1) / (kWfThreads / 32);
+    uint32_t grid = (uint32_t)(sms * blocks_per_sm);
+    if (grid > blocks_needed) grid = blocks_needed;
+    probe_update_wavefront<<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStream_t s, int* launches)
+{
+    dim3 grid(P.screen_w / 16, P.screen_h / 16);
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+    render_frame_kernel<<<grid, 256, 0, s>>>(P, J);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+static int grid_for(size_t n)
+{
+    size_t g = (n + 255) / 256;
+    size_t cap = 148 * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+cudaError_t launch_bake_scene(int scene, const int dims[3], const int org[3], uint8_t* types,
+                              cudaStream_t s, int* launches)
+{
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    bake_scene_kernel<<<grid_for(n), 256, 0, s>>>(scene, dims[0], dims[1], dims[2], org[0], org[1], org[2], types);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permille, uint32_t seed,
+                                  uint8_t* types, cudaStream_t s, int* launches)
+{
+    (void)org;
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    bake_synthetic_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], permille, seed, types);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_occupancy(const int dims[3], const int nb[3], const uint8_t* types,
+                                   unsigned long long* occ, cudaStream_t s, int* launches)
+{
+    size_t n = (size_t)nb[0] * nb[1] * nb[2];
+    build_occupancy_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], nb[0], nb[1], nb[2], types, occ);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace ddgi

@@ -1,0 +1,229 @@
+// ddgi_scene.cuh — stored voxel field (what replaces the reference's compiled-in
+// procedural getBlockAt, assets/shaders/intersection.glsl:699-826) and the built-in
+// scene bakers that evaluate that procedural function once per voxel.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   occ   : one uint64 per 4x4x4 voxel brick, bit (x&3)|(y&3)<<2|(z&3)<<4 set = solid.
+//           Brick index ((bz*nby)+by)*nbx+bx.  512^3 voxels -> 16 MiB: L2-resident, and
+//           a marching ray re-uses one 8-byte word for every step it spends in a brick.
+//   types : one uint8 block type per voxel, linear x-fastest; read only on a hit.
+//   palette: 256 x rgb fp32 albedo by block type (flat-colour variant, README.md:266).
+// Voxel id c (an integer-valued float, c = ceil(position)) covers (c-1, c] per axis;
+// grid cell g = c - vorg.  Anything outside the grid, or a NaN id, is empty.
+#pragma once
+#include "ddgi_math.cuh"
+
+namespace ddgi {
+
+struct SceneView {
+    const unsigned long long* occ;
+    const uint8_t* types;
+    const float* palette;
+    int vorg[3];
+    int vdim[3];
+    int nb[3];
+    float lo[3];  // (float)vorg
+    float hi[3];  // (float)(vorg + vdim - 1)
+};
+
+// Returns the block type (0 = empty) of voxel id c.
+DDGI_HD int scene_lookup(const SceneView& S, v3 c)
+{
+    if (!(c.x >= S.lo[0] && c.x <= S.hi[0] && c.y >= S.lo[1] && c.y <= S.hi[1] && c.z >= S.lo[2] &&
+          c.z <= S.hi[2]))
+        return 0;
+    int gx = (int)c.x - S.vorg[0], gy = (int)c.y - S.vorg[1], gz = (int)c.z - S.vorg[2];
+    size_t b = ((size_t)(gz >> 2) * S.nb[1] + (gy >> 2)) * S.nb[0] + (gx >> 2);
+    unsigned long long w = S.occ[b];
+    int bit = (gx & 3) | ((gy & 3) << 2) | ((gz & 3) << 4);
+    if (!((w >> bit) & 1ull)) return 0;
+    return S.types[((size_t)gz * S.vdim[1] + gy) * S.vdim[0] + gx];
+}
+
+DDGI_HD v3 scene_albedo(const SceneView& S, int type)
+{
+    const float* c = S.palette + 3 * (type & 255);
+    return V3(c[0], c[1], c[2]);
+}
+
+// ---------------------------------------------------------------------------------
+// Procedural block function, evaluated by the bakers only.
+// Noise: intersection.glsl:400-435.  Mushrooms: :538-697.  getBlockAt: :699-826.
+// ---------------------------------------------------------------------------------
+DDGI_HD float noise2D(float px, float py)
+{
+    float d = px * 127.1f + py * 311.7f;
+    return gfract(pin_sin(d) * 43758.5453f);
+}
+DDGI_HD float interp_noise2D(float x, float y)
+{
+    int ix = f2i(floorf(x));
+    float fx = gfract(x);
+    int iy = f2i(floorf(y));
+    float fy = gfract(y);
+    float v1 = noise2D((float)ix, (float)iy);
+    float v2 = noise2D((float)(ix + 1), (float)iy);
+    float v3_ = noise2D((float)ix, (float)(iy + 1));
+    float v4 = noise2D((float)(ix + 1), (float)(iy + 1));
+    float i1 = gmix(v1, v2, fx);
+    float i2 = gmix(v3_, v4, fx);
+    return gmix(i1, i2, fy);
+}
+DDGI_HD float fbm2D(float x, float y)
+{
+    float total = 0.0f;
+    float freq = 1.0f, amp = 1.0f;
+    for (int i = 1; i <= 8; i++) {
+        freq = freq * 2.0f;  // pow(2, i), exact
+        amp = amp * 0.5f;    // pow(0.5, i), exact
+        total += interp_noise2D(x * freq, y * freq) * amp;
+    }
+    return total;
+}
+
+DDGI_HD float sd_round_box(v3 p, v3 b, float r)
+{
+    v3 q = V3(fabsf(p.x) - b.x, fabsf(p.y) - b.y, fabsf(p.z) - b.z);
+    v3 qm = V3(gmax(q.x, 0.0f), gmax(q.y, 0.0f), gmax(q.z, 0.0f));
+    return length(qm) + gmin(gmax(q.x, gmax(q.y, q.z)), 0.0f) - r;
+}
+
+// The four mushroom shapes: a rounded-box cap split into three layers by sign(y)
+// and a stem made of up to three vertical segments.
+struct CapSpec {
+    float bx, by, bz, r;
+    int above, level, below;  // block types for y>0, y==0, y<0 inside the cap
+};
+DDGI_HD int cap_layers(v3 p, CapSpec c)
+{
+    if (sd_round_box(p, V3(c.bx, c.by, c.bz), c.r) <= 0) {
+        if (p.y > 0) return c.above;
+        if (p.y == 0) return c.level;
+        if (p.y < 0) return c.below;
+    }
+    return -1;
+}
+DDGI_HD int mushroom_tiny(v3 p)
+{
+    if (sd_round_box(p, V3(1.0f, 0.5f, 1.0f), 0.0f) <= 0) return 7;
+    if (p.x == 0 && p.z == 0 && p.y < 0) return 9;
+    return 0;
+}
+DDGI_HD int mushroom_small(v3 p)
+{
+    CapSpec c = {1.0f, 0.5f, 1.0f, 1.0f, 8, 7, 6};
+    int k = cap_layers(p, c);
+    if (k >= 0) return k;
+    if (p.x == 0 && p.z == 0 && p.y < 0) return 9;
+    return 0;
+}
+DDGI_HD int mushroom_medium(v3 p)
+{
+    CapSpec c = {2.0f, 0.5f, 2.0f, 1.0f, 6, 7, 8};
+    int k = cap_layers(p, c);
+    if (k >= 0) return k;
+    if (p.x == 0 && p.z == 0 && p.y < 0 && p.y > -7) return 9;
+    if (p.x == 1 && p.z == 0 && p.y < -5 && p.y > -12) return 9;
+    if (p.x == 2 && p.z == 0 && p.y < -10) return 9;
+    return 0;
+}
+DDGI_HD int mushroom_large(v3 p, int dir)
+{
+    CapSpec c = {3.0f, 0.5f, 3.0f, 1.5f, 6, 8, 7};
+    int k = cap_layers(p, c);
+    if (k >= 0) return k;
+    if (p.x == 0 && p.z == 0 && p.y < 0 && p.y > -9) return 9;
+    if (p.x == 0 && p.z == (float)dir && p.y < -7 && p.y > -18) return 9;
+    if (p.x == 0 && p.z == (float)(2 * dir) && p.y < -16) return 9;
+    return 0;
+}
+
+// Placement table of the cave's mushrooms by quadrant (intersection.glsl:630-697).
+DDGI_HD int cave_mushrooms(v3 c)
+{
+    if (c.x < 0 && c.z > 0) {
+        if (c.x < -16) {
+            if (c.z > 20) return mushroom_tiny(c - V3(-19, -12, 22));
+            if (c.z < 4) return mushroom_tiny(c - V3(-18, -12, 2));
+            int k = mushroom_large(c - V3(-22, 3, 8), -1);
+            if (k != 0) return k;
+            return mushroom_medium(c - V3(-27, -4, 16));
+        }
+        if (c.z > 10 && c.x > -6) return mushroom_tiny(c - V3(-4, -14, 12));
+        if (c.z < 14) return mushroom_medium(c - V3(-4, -1, 6));
+        return mushroom_small(c - V3(-10, -8, 18));
+    }
+    if (c.x < 0 && c.z < 0) {
+        if (c.x < -16) {
+            if (c.x < -28) {
+                if (c.z < -16) return mushroom_tiny(c - V3(-32, -14, -20));
+                return mushroom_tiny(c - V3(-30, -12, -12));
+            }
+            if (c.z > -10) return mushroom_small(c - V3(-25, -7, -4));
+            return mushroom_medium(c - V3(-20, -3, -20));
+        }
+        if (c.x < -12 && c.z > -12) return mushroom_tiny(c - V3(-14, -15, -10));
+        if (c.z > -10 && c.x > -4) return mushroom_tiny(c - V3(-2, -12, -2));
+        if (c.z < -10) return mushroom_small(c - V3(-5, -9, -14));
+        return mushroom_large(c - V3(-8, 8, -6), 1);
+    }
+    if (c.x > 0 && c.z < 0) {
+        if (c.z > -5) return mushroom_tiny(c - V3(6, -14, -3));
+        if (c.z < -14) {
+            if (c.x > 18) return mushroom_tiny(c - V3(20, -7, -16));
+            return mushroom_large(c - V3(14, 10, -20), -1);
+        }
+        return mushroom_medium(c - V3(6, -6, -10));
+    }
+    return 0;
+}
+
+DDGI_HD int block_cave(v3 c)
+{
+    if (c.y > 17.0f) return 0;
+    if (c.y < -15) {
+        if (c.y < -18) {
+            float r = fbm2D(c.x * 0.3f, c.z * 0.3f);
+            if (f2i(floorf(r * 2.0f)) == 0) return 12;
+        }
+        float r = fbm2D(c.x * 0.058f, c.z * 0.058f);
+        int d = f2i(floorf(r * 5.0f));
+        if ((float)(-21 + d) >= c.y) return c.y == -18 ? 13 : 11;
+    }
+    bool outside = length(c) - 20.0f > 0.0f && length(c + V3(16, 8, -10)) - 20.0f > 0.0f &&
+                   length(c + V3(-13, -1, 19)) - 18.0f > 0.0f && length(c + V3(20, 15, 15)) - 21.0f > 0.0f;
+    if (outside) return 10;
+    return cave_mushrooms(c);
+}
+DDGI_HD int block_cornell(v3 c)
+{
+    bool in_yz = fabsf(c.y) < 10 && fabsf(c.z - 15) < 10;
+    if (c.x == -10 && in_yz) return 2;
+    if (c.x == 10 && in_yz) return 3;
+    if (fabsf(c.y) == 10 && fabsf(c.x) < 10 && fabsf(c.z - 15) < 10) return 5;
+    if (c.z == 25 && fabsf(c.x) < 10 && fabsf(c.y) < 10) return 5;
+    if (fabsf(c.x + 3) < 3 && fabsf(c.y + 7) < 3 && fabsf(c.z - 13) < 3) return 5;
+    if (fabsf(c.x - 4) < 3 && fabsf(c.y + 4) < 6 && fabsf(c.z - 16) < 3) return 5;
+    return 0;
+}
+DDGI_HD int block_house(v3 c)
+{
+    if (c.y == -5) return 1;
+    if (fabsf(c.x) == 25 && fabsf(c.y) < 5 && fabsf(c.z) < 15) return 2;
+    if (c.y == 5 && fabsf(c.x) < 25 && fabsf(c.z) < 15) return 5;
+    if (c.z == -15 && fabsf(c.x) < 25 && fabsf(c.y) < 5) return 3;
+    if (c.z == 15) {
+        if (fabsf(c.x - 10) < 2 && fabsf(c.y + 1) < 4) return 0;
+        if (fabsf(c.x) < 25 && fabsf(c.y) < 5) return 3;
+    }
+    return 0;
+}
+DDGI_HD int block_procedural(v3 c, int scene)
+{
+    if (scene == 0) return block_cave(c);
+    if (scene == 1) return block_cornell(c);
+    if (scene == 2) return block_house(c);
+    return 0;
+}
+
+}  // namespace ddgi

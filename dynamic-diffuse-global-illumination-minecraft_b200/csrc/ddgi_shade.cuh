@@ -1,0 +1,139 @@
+// ddgi_shade.cuh — per-pixel side of the path: probe-tile lookup, the 8-probe-cage
+// weighted sample, the DDGI integrator and the pinhole camera.
+//   tile_origin / sample_tile   assets/shaders/intersection.glsl:1152-1240
+//   cage_irradiance             assets/shaders/intersection.glsl:1306-1409
+//   shade_ddgi                  assets/shaders/integrators.glsl:27-106
+//   pinhole_ray                 assets/shaders/camera.glsl:29-51
+#pragma once
+#include "ddgi_trace.cuh"
+
+namespace ddgi {
+
+// Tile origin of probe `p` in the packed texture, or (-1,-1).
+DDGI_HD void tile_origin(const FrameParams& P, int p, int* ox, int* oy)
+{
+    int x_dim = P.probe_count[0] * P.probe_count[2];
+    *ox = -1;
+    *oy = -1;
+    if (p >= x_dim * P.probe_count[1]) return;
+    if (p < 0 || x_dim < 0) return;
+    int col = f2i(gmod((float)p, (float)x_dim));
+    int row = p / x_dim;
+    if (row >= P.probe_count[1]) return;
+    *ox = col * P.rx;
+    *oy = row * P.ry;
+}
+
+// Direction -> texel of the probe tile, then the mean of the centre texel plus the
+// in-tile part of the 5x5 window around it (centre counted twice).
+DDGI_HD v3 sample_tile(const FrameParams& P, const uint32_t* tex, int W, int p, v3 dir)
+{
+    const float pi = 3.1415926535897932384626433832795f;
+    int cx, cy;
+    tile_origin(P, p, &cx, &cy);
+    if (cx == -1 && cy == -1) return V3(1, 0, 1);
+    v3 d = normalize(dir);
+    int relx = f2i(((-1.0f * (d.z - 1.0f)) / 2.0f) * (float)P.rx);
+    if (relx == P.rx) relx = 0;
+    float sq = sqrtf(1.0f - (d.z * d.z));
+    int rely = f2i((pin_acos(d.x / sq) / (2.0f * pi)) * (float)P.ry);
+    int sx = cx + relx, sy = cy + rely;
+    v3 sum = unpack_rgb8(tex[(size_t)sy * W + sx]);
+    int count = 0;
+    for (int x = -2; x <= 2; x++) {
+        int tx = sx + x;
+        if (tx < cx || tx >= cx + P.rx) continue;
+        for (int y = -2; y <= 2; y++) {
+            int ty = sy + y;
+            if (ty < cy || ty >= cy + P.ry) continue;
+            count++;
+            sum = sum + unpack_rgb8(tex[(size_t)ty * W + tx]);
+        }
+    }
+    return sum / (float)count;
+}
+
+DDGI_HD v3 cage_irradiance(const FrameParams& P, const uint32_t* tex, int W, const Hit& info)
+{
+    v3 pos = info.pos;
+    v3 N = normalize(info.normal);
+    v3 fo = V3(P.field_origin[0], P.field_origin[1], P.field_origin[2]);
+    float side = (float)P.side_length;
+    v3 q = (pos - fo) / side;
+    int base[3] = {f2i(floorf(q.x)), f2i(floorf(q.y)), f2i(floorf(q.z))};
+    // the reference bounds every axis with the x probe count (int(vec3) = .x)
+    int lo = f2i(-floorf((float)P.probe_count[0] / 2.0f));
+    int hi = f2i(floorf((float)P.probe_count[0] / 2.0f) - 1.0f);
+    for (int i = 0; i < 3; i++)
+        if (base[i] < lo || base[i] > hi) return V3(1, 0, 1);
+
+    v3 base_world = V3((float)(base[0] * P.side_length), (float)(base[1] * P.side_length),
+                       (float)(base[2] * P.side_length)) + fo;
+    v3 a = (pos - base_world) / side;
+    v3 alpha = V3(gclamp(a.x, 0.0f, 1.0f), gclamp(a.y, 0.0f, 1.0f), gclamp(a.z, 0.0f, 1.0f));
+    int X = P.probe_count[0], Y = P.probe_count[1], Z = P.probe_count[2];
+    v3 irradiance = V3(0, 0, 0);
+    float sum_w = 0.0f;
+    for (int i = 0; i < 8; i++) {
+        int ox = (i >> 2) & 1, oy = (i >> 1) & 1, oz = i & 1;
+        int sx = base[0] + ox + X / 2, sy = base[1] + oy + Y / 2, sz = base[2] + oz + Z / 2;
+        int p = sy * X * Z + sz * X + sx;
+        if (p < 0 || p >= X * Y * Z) return V3(1, 0, 1);
+        v3 off = V3((float)ox, (float)oy, (float)oz);
+        v3 tri = V3(gmix(1.0f - alpha.x, alpha.x, off.x), gmix(1.0f - alpha.y, alpha.y, off.y),
+                    gmix(1.0f - alpha.z, alpha.z, off.z));
+        v3 probe_pos = base_world + off * side;
+        v3 dir = normalize(probe_pos - pos);
+        float bf = gmax(0.0001f, (dot(dir, N) + 1.0f) * 0.5f);
+        float w = bf * bf + 0.2f;
+        // (the reference's Chebyshev visibility term is computed and then discarded)
+        w = gmax(0.000001f, w);
+        const float crush = 0.2f;
+        if (w < crush) w *= w * w * (1.f / (crush * crush));
+        w *= tri.x * tri.y * tri.z;
+        irradiance = irradiance + sample_tile(P, tex, W, p, N) * w;
+        sum_w += w;
+    }
+    return irradiance / sum_w;
+}
+
+DDGI_HD v3 shade_ddgi(const FrameParams& P, const uint32_t* tex, int W, v3 origin, v3 direction,
+                      uint32_t& lookups)
+{
+    Hit info;
+    if (!nearest_hit(P, origin, direction, info, lookups)) return V3(0.898f, 0.968f, 1.0f);
+    if (info.type == 2) return info.emissive;
+    v3 indirect = cage_irradiance(P, tex, W, info);
+    v3 direct = V3(0, 0, 0);
+    int visible = 0;
+    for (int i = 0; i < P.n_lights; i++) {
+        const Light& l = P.lights[i];
+        v3 to_light = normalize(lpos(l) - info.pos);
+        Hit fh;
+        if (nearest_hit(P, info.pos, to_light, fh, lookups) && fh.type == 2) {
+            float lambert = gclamp(dot(normalize(info.normal), to_light), 0.0f, 1.0f);
+            float dist = length(lpos(l) - info.pos);
+            direct = direct + ((lcol(l) * lambert) * l.intensity) / dist;
+            visible++;
+        }
+    }
+    v3 half_base = info.base_color * 0.5f;
+    if (visible != 0) return half_base * (direct / (float)visible) + half_base * indirect;
+    return (indirect * 0.5f) * info.base_color;
+}
+
+DDGI_HD void pinhole_ray(const FrameParams& P, float x, float y, v3* origin, v3* direction)
+{
+    const float* m = P.cam;
+    float u = m[16] * (2.0f * x - 1.0f);
+    float v = 2.0f * y - 1.0f;
+    float w = P.cam_w;
+    *origin = V3(m[12], m[13], m[14]);
+    v3 d;
+    d.x = ((m[0] * u + m[4] * v) + m[8] * w) + m[12] * 0.0f;
+    d.y = ((m[1] * u + m[5] * v) + m[9] * w) + m[13] * 0.0f;
+    d.z = ((m[2] * u + m[6] * v) + m[10] * w) + m[14] * 0.0f;
+    *direction = normalize(d);
+}
+
+}  // namespace ddgi

@@ -1,0 +1,277 @@
+// ddgi_trace.cuh — per-ray building blocks of the probe update and the pixel pass:
+// RNG, hemisphere sampling, light-sphere test, voxel DDA march, nearest-hit query and
+// the shadow-tested direct term.  Operation order follows the reference shaders so
+// results are bit-identical to the CPU oracle (fp32, no contraction):
+//   RNG                      assets/shaders/probe_pass.comp:45-71
+//   hemisphere_dir           assets/shaders/probe_pass.comp:150-178
+//   light_sphere             assets/shaders/intersection.glsl:78-121 (via :1264-1279)
+//   march / nearest_hit      assets/shaders/intersection.glsl:1051-1100, :1244-1301
+//   probe_direct_lighting    assets/shaders/probe_pass.comp:180-215
+#pragma once
+#include "ddgi_scene.cuh"
+
+namespace ddgi {
+
+struct Light {
+    float intensity;
+    float col[3];
+    float pos[3];
+};
+
+constexpr int kMaxLights = 8;
+constexpr int kMarchSteps = 125;  // intersection.glsl:1059
+
+struct FrameParams {
+    SceneView scene;
+    int n_lights;
+    Light lights[kMaxLights];
+    // irradiance field (src/rvpt/rvpt.h:82-90)
+    int probe_count[3];
+    int side_length;
+    int rx, ry;  // ray-tile shape; the reference has rx == ry == sqrt_rays_per_probe
+    float field_origin[3];
+    // render settings (src/rvpt/rvpt.h:70-80)
+    int max_bounces;
+    int screen_w, screen_h;
+    // camera block (src/rvpt/camera.cpp:100-111) + host-evaluated 1/tan(hfov/2)
+    float cam[20];
+    float cam_w;
+};
+
+struct Hit {
+    float t;
+    v3 pos;
+    v3 normal;
+    v3 base_color;
+    v3 emissive;
+    int type;  // 2 light sphere, 3 block, 0 none
+};
+
+DDGI_HD float inf_f()
+{
+#ifdef __CUDA_ARCH__
+    return __int_as_float(0x7f800000);
+#else
+    return INFINITY;
+#endif
+}
+
+DDGI_HD v3 lpos(const Light& l) { return V3(l.pos[0], l.pos[1], l.pos[2]); }
+DDGI_HD v3 lcol(const Light& l) { return V3(l.col[0], l.col[1], l.col[2]); }
+
+// ------------------------------------------------------------------ RNG
+DDGI_HD uint32_t wang_hash(uint32_t seed)
+{
+    seed = (seed ^ 61u) ^ (seed >> 16);
+    seed *= 9u;
+    seed = seed ^ (seed >> 4);
+    seed *= 0x27d4eb2du;
+    seed = seed ^ (seed >> 15);
+    return seed;
+}
+DDGI_HD float rng_next(uint32_t& st)
+{
+    st ^= (st << 13);
+    st ^= (st >> 17);
+    st ^= (st << 5);
+    // float(uint) rounds to nearest; the scale by 2^-32 is exact (can yield 1.0)
+    return (float)st / 4294967296.0f;
+}
+
+DDGI_HD v3 hemisphere_dir(v3 normal, uint32_t& st)
+{
+    const float two_pi = 6.2831853071795864769252867665590057683943f;
+    const float sqrt_third = 0.5773502691896257645091487805019574556476f;
+    float up = sqrtf(rng_next(st));
+    float over = sqrtf(1.0f - up * up);
+    float around = rng_next(st) * two_pi;
+    v3 other;
+    if (fabsf(normal.x) < sqrt_third) other = V3(1, 0, 0);
+    else if (fabsf(normal.y) < sqrt_third) other = V3(0, 1, 0);
+    else other = V3(0, 0, 1);
+    v3 p1 = normalize(cross(normal, other));
+    v3 p2 = normalize(cross(normal, p1));
+    float sn, cs;
+    pin_sincos(around, &sn, &cs);
+    return (normal * up + p1 * (cs * over)) + p2 * (sn * over);
+}
+
+// ------------------------------------------------------------------ light spheres
+// Ray vs. the radius-0.1 sphere of light l: the unit-sphere quadratic on the
+// ray scaled by 1/0.1.  Returns t (INF on a miss) and the unnormalised normal.
+DDGI_HD float light_sphere(v3 origin, v3 direction, const Light& l, float maxt, v3* normal)
+{
+    v3 o = (origin - lpos(l)) / 0.1f;
+    v3 d = direction / 0.1f;
+    float A = dot(d, d);
+    float B = -dot(d, o);
+    float C = dot(o, o) - 1.0f;
+    float D = B * B - A * C;
+    D = D > 0 ? sqrtf(D) : inf_f();
+    float t1 = (B - D) / A;
+    float t2 = (B + D) / A;
+    t1 = (0.0f < t1 && t1 < maxt) ? t1 : inf_f();
+    t2 = (0.0f < t2 && t2 < maxt) ? t2 : inf_f();
+    float t = gmin(t1, t2);
+    *normal = o + d * t;
+    return t;
+}
+
+// ------------------------------------------------------------------ voxel march
+// Axis normal of the face a hit point lies on: sign of the dominant component of
+// normalize(p - cell_centre), first axis wins ties.
+DDGI_HD v3 face_normal(v3 p, v3 cell)
+{
+    v3 centre = V3(cell.x - 0.5f, cell.y - 0.5f, cell.z - 0.5f);
+    v3 diff = normalize(p - centre);
+    v3 n = V3(0, 0, 0);
+    float mx = 0.0f;
+    if (fabsf(diff.x) > mx) {
+        mx = fabsf(diff.x);
+        n = V3(gsign(diff.x), 0, 0);
+    }
+    if (fabsf(diff.y) > mx) {
+        mx = fabsf(diff.y);
+        n = V3(0, gsign(diff.y), 0);
+    }
+    if (fabsf(diff.z) > mx) {
+        mx = fabsf(diff.z);
+        n = V3(0, 0, gsign(diff.z));
+    }
+    return n;
+}
+
+// One DDA advance: distance to the next lattice plane along each axis, the
+// smallest plus the 1e-4 nudge, accumulate, re-evaluate the position.
+DDGI_HD void march_advance(v3 origin, v3 dir, float& t, v3& p)
+{
+    v3 f = V3(gfract(p.x), gfract(p.y), gfract(p.z));
+    float tx = gmax((-f.x) / dir.x, (1.0f - f.x) / dir.x);
+    float ty = gmax((-f.y) / dir.y, (1.0f - f.y) / dir.y);
+    float tz = gmax((-f.z) / dir.z, (1.0f - f.z) / dir.z);
+    float step = gmin(gmin(tx, ty), tz) + 0.0001f;
+    t += step;
+    p = origin + dir * t;
+}
+
+// Marches at most 125 cells.  On a hit fills t, the (un-normalised) axis normal and
+// the albedo.  `lookups` counts voxel queries (the reference's getBlockAt calls).
+DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32_t& lookups)
+{
+    v3 dir = normalize(direction);
+    v3 p = origin;
+    float t = 0.0f;
+    for (int i = 0; i < kMarchSteps; i++) {
+        march_advance(origin, dir, t, p);
+        v3 cell = V3(ceilf(p.x), ceilf(p.y), ceilf(p.z));
+        lookups++;
+        int type = scene_lookup(S, cell);
+        if (type > 0) {
+            out.t = t;
+            v3 n = face_normal(p, cell);
+            out.normal = normalize(n);
+            out.base_color = scene_albedo(S, type);
+            out.emissive = V3(0, 0, 0);
+            return true;
+        }
+    }
+    return false;
+}
+
+// Nearest of {light spheres, voxel march}.
+DDGI_HD bool nearest_hit(const FrameParams& P, v3 origin, v3 direction, Hit& info, uint32_t& lookups)
+{
+    float closest = inf_f();
+    info.t = closest;
+    info.pos = V3(0, 0, 0);
+    info.normal = V3(0, 0, 0);
+    info.base_color = V3(0, 0, 0);
+    info.emissive = V3(0, 0, 0);
+    info.type = 0;
+    for (int i = 0; i < P.n_lights; i++) {
+        v3 n;
+        float t = light_sphere(origin, direction, P.lights[i], closest, &n);
+        if (t < closest) {
+            info.t = t;
+            info.normal = n;
+            info.base_color = V3(0, 0, 0);
+            info.emissive = lcol(P.lights[i]);
+            info.type = 2;
+        }
+        closest = gmin(t, closest);
+    }
+    Hit m;
+    if (march(P.scene, origin, direction, m, lookups)) {
+        if (m.t < closest) {
+            info.t = m.t;
+            info.normal = m.normal;
+            info.base_color = m.base_color;
+            info.emissive = m.emissive;
+            closest = m.t;
+            info.type = 3;
+        }
+    }
+    bool hit = closest < inf_f();
+    info.normal = hit ? normalize(info.normal) : V3(0, 0, 0);
+    info.pos = hit ? origin + direction * info.t : V3(0, 0, 0);
+    info.pos = info.pos + info.normal * 0.001f;
+    return hit;
+}
+
+// Direct term at a probe-ray hit: one shadow feeler per light; a feeler blocked by a
+// voxel ends the loop with the 0.2*albedo*lambert ambient term.
+DDGI_HD v3 probe_direct_lighting(const FrameParams& P, const Hit& info, uint32_t& lookups)
+{
+    v3 direct = V3(0, 0, 0);
+    int visible = 0;
+    for (int i = 0; i < P.n_lights; i++) {
+        const Light& l = P.lights[i];
+        v3 to_light = normalize(lpos(l) - info.pos);
+        Hit fh;
+        if (nearest_hit(P, info.pos, to_light, fh, lookups)) {
+            float lambert = gclamp(dot(normalize(info.normal), to_light), 0.0f, 1.0f);
+            if (fh.type == 2) {
+                float dist = length(lpos(l) - info.pos);
+                direct = direct + ((lcol(l) * lambert) * l.intensity) / dist;
+            } else {
+                return (info.base_color * 0.2f) * lambert;
+            }
+            visible++;
+        }
+    }
+    if (visible != 0) return (info.base_color * direct) / (float)visible;
+    return V3(0, 0, 0);
+}
+
+// Whole probe-ray path: up to max_bounces hits, each adding its direct term.
+DDGI_HD v3 trace_probe_ray(const FrameParams& P, v3 origin, v3 direction, uint32_t ray_index,
+                           uint32_t& lookups)
+{
+    uint32_t rng = wang_hash(ray_index);
+    v3 color = V3(0, 0, 0);
+    v3 o = origin, d = direction;
+    Hit hit;
+    for (int b = 0; b < P.max_bounces; b++) {
+        if (!nearest_hit(P, o, d, hit, lookups)) break;
+        color = color + probe_direct_lighting(P, hit, lookups);
+        o = hit.pos + hit.normal * 0.0001f;
+        d = hemisphere_dir(hit.normal, rng);
+    }
+    return color / (float)P.max_bounces;
+}
+
+// Probe lattice position and tile addressing (src/rvpt/rvpt.cpp:1190-1205,
+// assets/shaders/probe_pass.comp:139-145).
+DDGI_HD v3 probe_origin(const FrameParams& P, int p)
+{
+    int X = P.probe_count[0], Y = P.probe_count[1], Z = P.probe_count[2];
+    int py = p / (X * Z);
+    int rest = p - py * X * Z;
+    int pz = rest / X;
+    int px = rest - pz * X;
+    v3 o = V3((float)(px - (X - 1) / 2), (float)(py - (Y - 1) / 2), (float)(pz - (Z - 1) / 2));
+    o = o * (float)P.side_length;
+    return o + V3(P.field_origin[0], P.field_origin[1], P.field_origin[2]);
+}
+
+}  // namespace ddgi

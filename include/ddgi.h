@@ -1,0 +1,200 @@
+/*
+ * ddgi.h — C ABI of the B200-native DDGI probe-field engine (libddgi_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of
+ * helenl9098/Dynamic-Diffuse-Global-Illumination-Minecraft: the two Vulkan compute
+ * dispatches recorded by RVPT::record_compute_command_buffer (src/rvpt/rvpt.cpp:1096-1143)
+ * and the per-frame uniform / storage-buffer uploads of RVPT::update
+ * (src/rvpt/rvpt.cpp:265-290).  Each entry point cites the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *  - Every function returns DDGI_OK (0) or a negative DDGI_E_* code; it never aborts or
+ *    throws (the reference asserts on VkResult < 0, src/rvpt/vk_util.h:18-27).
+ *    ddgi_last_error(ctx) gives a human-readable message for the last failure.
+ *  - Host pointers are copied during the call; the caller keeps ownership (as
+ *    VK::Buffer::copy_to memcpys, src/rvpt/vk_util.cpp:1141-1146).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *    ddgi_probe_update / ddgi_render_frame are asynchronous on it; ddgi_sync waits.
+ *  - A context is bound to one CUDA device and is not thread-safe (the reference is a
+ *    single-threaded caller, src/rvpt/main.cpp:80-96).
+ *  - There is no CPU fallback: without a CUDA device ddgi_create fails with
+ *    DDGI_E_CUDA.
+ */
+#ifndef DDGI_H
+#define DDGI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DDGI_API __attribute__((visibility("default")))
+#else
+#define DDGI_API
+#endif
+
+#define DDGI_OK 0
+#define DDGI_E_INVALID (-1) /* bad argument / call order */
+#define DDGI_E_CUDA (-2)    /* CUDA runtime error or no device */
+#define DDGI_E_STATE (-3)   /* missing voxels / rays / field before a dispatch */
+
+#define DDGI_MAX_LIGHTS 8
+
+typedef struct ddgi_ctx ddgi_ctx;
+
+/* RVPT::RenderSettings, src/rvpt/rvpt.h:70-80 (32 bytes, uniform binding 0 of both shaders) */
+typedef struct ddgi_render_settings {
+    int32_t screen_width;
+    int32_t screen_height;
+    int32_t max_bounces;
+    int32_t camera_mode; /* only 0 (pinhole) is on the path */
+    int32_t render_mode; /* only 0 (DDGI) is on the path */
+    int32_t scene;       /* 0 cave, 1 Cornell, 2 house: selects the built-in baker / lights */
+    float time;
+    int32_t visualize_probes; /* must be 0 */
+} ddgi_render_settings;
+
+/* RVPT::IrradianceField, src/rvpt/rvpt.h:82-90 (48 bytes, std140) */
+typedef struct ddgi_irradiance_field {
+    int32_t probe_count[3];      /* @0  */
+    int32_t side_length;         /* @12 */
+    float hysteresis;            /* @16 plumbed, unused by the reference (probe_pass.comp:298-299) */
+    int32_t sqrt_rays_per_probe; /* @20 */
+    int32_t _pad0[2];            /* @24 */
+    float field_origin[3];       /* @32 */
+    int32_t visualize;           /* @44 host-only bool */
+} ddgi_irradiance_field;
+
+/* struct ProbeRay, src/rvpt/probe.h:5-20 == assets/shaders/structs.glsl:22-27 (48 bytes) */
+typedef struct ddgi_probe_ray {
+    float origin[3];
+    float _p0;
+    float direction[3];
+    float _p1;
+    float probe_info[3]; /* (probe index, tile x, tile y) stored as floats */
+    float _p2;
+} ddgi_probe_ray;
+
+/* struct Light, assets/shaders/structs.glsl:54-59 */
+typedef struct ddgi_light {
+    float intensity;
+    float col[3];
+    float pos[3];
+} ddgi_light;
+
+/* ---- lifetime: RVPT::RVPT + RVPT::initialize (rvpt.cpp:212-264), RVPT::shutdown ---- */
+DDGI_API int ddgi_create(ddgi_ctx** out, int device);
+DDGI_API void ddgi_destroy(ddgi_ctx* ctx);
+DDGI_API const char* ddgi_last_error(const ddgi_ctx* ctx);
+/* "major.minor sm_XX" of the build */
+DDGI_API const char* ddgi_version(void);
+
+/* ---- per-frame uniforms: RVPT::update, rvpt.cpp:281-287 ---- */
+/* settings_uniform.copy_to (rvpt.cpp:282) */
+DDGI_API int ddgi_set_render_settings(ddgi_ctx* ctx, const ddgi_render_settings* rs);
+/* irradiance_field_uniform.copy_to (rvpt.cpp:287); a change of probe_count or
+   sqrt_rays_per_probe re-creates the probe textures as recreate_probe_textures does
+   (rvpt.cpp:661-755, 873-890) and invalidates the ray set. */
+DDGI_API int ddgi_set_irradiance_field(ddgi_ctx* ctx, const ddgi_irradiance_field* field);
+/* Extension: rectangular rx x ry ray tile for non-square rays/probe (128 = 8x16).
+   Call after ddgi_set_irradiance_field; rx == ry == sqrt_rays_per_probe is the default. */
+DDGI_API int ddgi_set_ray_tile(ddgi_ctx* ctx, int32_t rx, int32_t ry);
+/* camera_uniform.copy_to (rvpt.cpp:283): Camera::get_data(), src/rvpt/camera.cpp:100-111 —
+   16 floats column-major camera-to-world + (aspect, hfov_rad, scale, 0) */
+DDGI_API int ddgi_set_camera(ddgi_ctx* ctx, const float cam[20]);
+
+/* ---- scene: compiled into the reference's GLSL, explicit inputs here ---- */
+/* Light table (assets/shaders/structs.glsl:61-89, get_light intersection.glsl:1131-1150). */
+DDGI_API int ddgi_set_lights(ddgi_ctx* ctx, int32_t n, const ddgi_light* lights);
+/* The reference's table for `scene` (n = 1,1,2) */
+DDGI_API int ddgi_default_lights(int32_t scene, ddgi_light* out, int32_t* n);
+/* The commented 4-light cave table (structs.glsl:65-69) moved by update_lights' cave
+   branch (probe_pass.comp:219-235) for `time`. */
+DDGI_API int ddgi_cave_lights4(float time, ddgi_light* out);
+/* Stored voxel field replacing getBlockAt (intersection.glsl:699-826): `types` is
+   dims[0]*dims[1]*dims[2] block types, x fastest; cell (0,0,0) is voxel id `origin`
+   (voxel id c covers (c-1, c] per axis).  palette: 256 rgb triples or NULL for the
+   flat-colour table of the reference's block types. */
+DDGI_API int ddgi_upload_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t origin[3],
+                       const uint8_t* types, const float* palette);
+/* Built-in baker: evaluates the reference's procedural block function for `scene` on
+   the device over the given box. */
+DDGI_API int ddgi_bake_scene(ddgi_ctx* ctx, int32_t scene, const int32_t dims[3], const int32_t origin[3]);
+/* Synthetic cave-like field for the 32^3-probe benchmark (SURVEY.md 8d cfg 4): the
+   reference cave's four-sphere cavity scaled to the grid, `solid_permille` of the cavity
+   cells filled at random (xorshift32, seed), six flat block types. */
+DDGI_API int ddgi_bake_synthetic(ddgi_ctx* ctx, const int32_t dims[3], const int32_t origin[3],
+                        int32_t solid_permille, uint32_t seed);
+/* Copies the block types back (dims product bytes). */
+DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
+
+/* ---- probe rays: RVPT::generate_probe_rays (rvpt.h:63, rvpt.cpp:1177-1224) ---- */
+/* Generates the stratified sample set with libc rand() exactly as generate_samples
+   (rvpt.cpp:1147-1173) and keeps only the per-probe direction table on the device; the
+   kernel derives origin / direction / tile offset of ray k itself (no 48 B/ray read).
+   reseed != 0 calls srand(1) first (the state of a fresh process). */
+DDGI_API int ddgi_generate_probe_rays(ddgi_ctx* ctx, int32_t reseed);
+/* Same, from a caller-supplied table of rx*ry un-normalised sphere samples (xyz). */
+DDGI_API int ddgi_set_ray_samples(ddgi_ctx* ctx, const float* samples, size_t count);
+/* Reads the current rx*ry sample table back (3 floats each). */
+DDGI_API int ddgi_get_ray_samples(ddgi_ctx* ctx, float* dst, size_t count);
+/* probe_buffer.copy_to(probe_rays) (rvpt.cpp:285): literal storage-buffer mode, the
+   kernel reads the caller's 48-byte records. */
+DDGI_API int ddgi_set_probe_rays(ddgi_ctx* ctx, const ddgi_probe_ray* rays, size_t count);
+/* Writes the full ray list (what the reference's std::vector<ProbeRay> holds). */
+DDGI_API int ddgi_get_probe_rays(ddgi_ctx* ctx, ddgi_probe_ray* dst, size_t count);
+DDGI_API size_t ddgi_num_probe_rays(const ddgi_ctx* ctx);
+
+/* ---- probe sharding across GPUs (no reference counterpart) ---- */
+/* This context updates only probe rows [y0, y1) (texture rows [y0*ry, y1*ry)). */
+DDGI_API int ddgi_set_probe_rows(ddgi_ctx* ctx, int32_t y0, int32_t y1);
+/* Device address and size of probe texture `which` (0 albedo, 1 distance); both live in
+   one allocation, albedo first, so one collective can move both. */
+DDGI_API int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** ptr, size_t* bytes);
+/* Fused exchange: 64-byte CUDA IPC handle of the texture allocation / open the peers'.
+   After ddgi_open_peers, ddgi_probe_update stores every texel into all replicas. */
+DDGI_API int ddgi_export_texture_handle(ddgi_ctx* ctx, void* handle64);
+DDGI_API int ddgi_open_peers(ddgi_ctx* ctx, int32_t n_peers, const void* handles64, int32_t self_index);
+DDGI_API int ddgi_close_peers(ddgi_ctx* ctx);
+
+/* ---- the two dispatches ---- */
+/* vkCmdDispatch #1, probe_pass.comp (rvpt.cpp:1121-1129) */
+DDGI_API int ddgi_probe_update(ddgi_ctx* ctx, void* stream);
+/* vkCmdDispatch #2, compute_pass.comp (rvpt.cpp:1133-1140) */
+DDGI_API int ddgi_render_frame(ddgi_ctx* ctx, void* stream);
+/* raytrace_work_fence.wait (rvpt.cpp:277) */
+DDGI_API int ddgi_sync(ddgi_ctx* ctx);
+
+/* ---- results ---- */
+#define DDGI_FMT_RGBA8 0 /* what the reference stores (VK_FORMAT_R8G8B8A8_UNORM) */
+#define DDGI_FMT_F32 1   /* the fp32 value before the UNORM store, 4 floats per texel;
+                            only kept when ddgi_set_debug(ctx, 1) */
+DDGI_API int ddgi_probe_texture_size(const ddgi_ctx* ctx, int32_t* width, int32_t* height);
+DDGI_API int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, void* dst, size_t bytes);
+/* Uploads texture contents (checkpoint / resume, and pixel-pass tests). */
+DDGI_API int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size_t bytes);
+DDGI_API int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes);
+
+/* ---- instrumentation ---- */
+/* debug != 0: keep fp32 copies of the outputs and per-invocation voxel-lookup counts. */
+DDGI_API int ddgi_set_debug(ddgi_ctx* ctx, int32_t debug);
+/* Per-ray (which = 0) or per-pixel (which = 1) voxel lookups of the last dispatch. */
+DDGI_API int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t count);
+/* Kernel variant: 0 = one thread per ray, reference loop order; 1 = regrouped
+   state-machine kernel (default).  Results are identical. */
+DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
+/* Regrouping threshold of variant 1: a warp keeps stepping its marches while at least
+   march_min/32 of its live lanes are marching (1..32, default 16).  Results do not
+   depend on it. */
+DDGI_API int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min);
+/* Number of kernel launches issued by this context so far. */
+DDGI_API uint64_t ddgi_launch_count(const ddgi_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDGI_H */

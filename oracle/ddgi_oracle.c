@@ -36,7 +36,8 @@
  *     sin/cos = pin_sin/pin_cos below: a double-precision Cody-Waite +
  *     fdlibm-polynomial evaluation rounded once to fp32 (deterministic on any
  *     IEEE-754 machine, within 1 fp32 ulp of libm; tests/test_oracle_math.py);
- *     acos/tan(host-side uniform) = (float) of the double libm function.
+ *     acos = pin_acos (fdlibm algorithm in fp64, rounded once to fp32);
+ *     tan (host-side camera uniform only) = (float) of the double libm function.
  *  9. The pixel pass writes only gid < (floor(w/16)*16, floor(h/16)*16).
  * 10. The pixel pass sees the fully updated probe texture of the same frame.
  *
@@ -163,7 +164,57 @@ static void pin_sincos(float xf, float* s_out, float* c_out)
 }
 static inline float pin_sin(float x) { float s, c; pin_sincos(x, &s, &c); return s; }
 static inline float pin_cos(float x) { float s, c; pin_sincos(x, &s, &c); return c; }
-static inline float pin_acos(float x) { return (float)acos((double)x); }
+/* acos: the fdlibm e_acos.c algorithm evaluated in fp64 and rounded once to fp32
+   (deterministic; within 1 fp32 ulp of libm, tests/test_oracle_math.py). */
+static double pin_acos_pq(double z)
+{
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01,
+                 pS2 = 2.01212532134862925881e-01, pS3 = -4.00555345006794114027e-02,
+                 pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05;
+    const double qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00,
+                 qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    return p / q;
+}
+static float pin_acos(float xf)
+{
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pi = 3.14159265358979311600e+00;
+    double x = (double)xf;
+    if (x != x) return NAN;
+    double ax = fabs(x);
+    if (ax >= 1.0) {
+        if (ax == 1.0) return x > 0.0 ? 0.0f : (float)(pi + 2.0 * pio2_lo);
+        return NAN;
+    }
+    if (ax < 0.5) {
+        if (ax <= 5.55111512312578270212e-17) return (float)(pio2_hi + pio2_lo);
+        double r = pin_acos_pq(x * x);
+        return (float)(pio2_hi - (x - (pio2_lo - x * r)));
+    }
+    if (x < 0.0) {
+        double z = (1.0 + x) * 0.5;
+        double r = pin_acos_pq(z);
+        double s = sqrt(z);
+        double w = r * s - pio2_lo;
+        return (float)(pi - 2.0 * (s + w));
+    }
+    double z = (1.0 - x) * 0.5;
+    double s = sqrt(z);
+    union { double d; uint64_t u; } cv;
+    cv.d = s;
+    cv.u &= 0xffffffff00000000ull;
+    double df = cv.d;
+    double c = (z - df * df) / (s + df);
+    double r = pin_acos_pq(z);
+    double w = r * s + c;
+    return (float)(2.0 * (df + w));
+}
+ORC_API void orc_pin_acos(const float* x, int n, float* out)
+{
+    for (int i = 0; i < n; i++) out[i] = pin_acos(x[i]);
+}
 
 ORC_API void orc_pin_sincos(const float* x, int n, float* s, float* c)
 {

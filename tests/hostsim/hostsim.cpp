@@ -1,0 +1,157 @@
+// hostsim.cpp — TEST-ONLY host build of the engine's per-ray device functions.
+//
+// The kernels' logic lives in host/device-clean headers (csrc/ddgi_*.cuh).  This file
+// compiles those same headers with g++ so the CPU-only test tier (`-m "not gpu"`) can
+// check them against the oracle without a GPU.  It is never linked into
+// libddgi_b200.so and nothing in the product can reach it.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_shade.cuh"
+#include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_wavefront.cuh"
+
+using namespace ddgi;
+
+// same layout as oracle/ddgi_oracle.c OrcParams so the tests build one description
+struct SimLight { float intensity; float col[3]; float pos[3]; };
+struct SimParams {
+    int32_t scene_mode, scene, color_mode, n_lights;
+    SimLight lights[8];
+    int32_t vdim[3];
+    int32_t vorg[3];
+    const uint8_t* vox;
+    const float* palette;
+    int32_t probe_count[3];
+    int32_t side_length;
+    int32_t rx, ry;
+    float field_origin[3];
+    int32_t max_bounces;
+    int32_t screen_width, screen_height;
+};
+
+struct Built {
+    FrameParams P;
+    std::vector<unsigned long long> occ;
+};
+
+static void build(const SimParams* S, const float* cam, Built* B)
+{
+    FrameParams& P = B->P;
+    memset(&P, 0, sizeof(P));
+    int nb[3];
+    for (int a = 0; a < 3; a++) {
+        nb[a] = (S->vdim[a] + 3) / 4;
+        P.scene.vorg[a] = S->vorg[a];
+        P.scene.vdim[a] = S->vdim[a];
+        P.scene.nb[a] = nb[a];
+        P.scene.lo[a] = (float)S->vorg[a];
+        P.scene.hi[a] = (float)(S->vorg[a] + S->vdim[a] - 1);
+        P.probe_count[a] = S->probe_count[a];
+        P.field_origin[a] = S->field_origin[a];
+    }
+    B->occ.assign((size_t)nb[0] * nb[1] * nb[2], 0ull);
+    for (int z = 0; z < S->vdim[2]; z++)
+        for (int y = 0; y < S->vdim[1]; y++)
+            for (int x = 0; x < S->vdim[0]; x++)
+                if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x])
+                    B->occ[((size_t)(z >> 2) * nb[1] + (y >> 2)) * nb[0] + (x >> 2)] |=
+                        1ull << ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+    P.scene.occ = B->occ.data();
+    P.scene.types = S->vox;
+    P.scene.palette = S->palette;
+    P.n_lights = S->n_lights;
+    for (int i = 0; i < S->n_lights; i++) {
+        P.lights[i].intensity = S->lights[i].intensity;
+        for (int a = 0; a < 3; a++) {
+            P.lights[i].col[a] = S->lights[i].col[a];
+            P.lights[i].pos[a] = S->lights[i].pos[a];
+        }
+    }
+    P.side_length = S->side_length;
+    P.rx = S->rx;
+    P.ry = S->ry;
+    P.max_bounces = S->max_bounces;
+    P.screen_w = S->screen_width;
+    P.screen_h = S->screen_height;
+    if (cam) {
+        memcpy(P.cam, cam, sizeof(P.cam));
+        P.cam_w = 1.0f / (float)tan((double)(0.5f * cam[17]));
+    }
+}
+
+extern "C" {
+
+// variant 0: trace_probe_ray (reference loop order); variant 1: the wavefront
+// state machine stepped one lane at a time.
+void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32_t k0, uint32_t k1,
+                      int variant, uint32_t* albedo, float* f32, uint32_t* lookups)
+{
+    Built B;
+    build(S, nullptr, &B);
+    const FrameParams& P = B.P;
+    int W = P.probe_count[0] * P.probe_count[2] * P.rx;
+    int tiles_x = P.probe_count[0] * P.probe_count[2];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t k = k0; k < (int64_t)k1; k++) {
+        const float* r = rays + 12 * k;
+        v3 o = V3(r[0], r[1], r[2]), d = V3(r[4], r[5], r[6]);
+        int p = f2i(r[8]);
+        int yp = p / tiles_x, xp = p - yp * tiles_x;
+        int tx = xp * P.rx + f2i(r[9]), ty = yp * P.ry + f2i(r[10]);
+        uint32_t n = 0;
+        v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n)
+                            : wavefront_trace_scalar(P, o, d, (uint32_t)k, n);
+        size_t t = (size_t)ty * W + tx;
+        albedo[t] = pack_rgba8(c.x, c.y, c.z, 1.0f);
+        if (f32) { f32[4 * t] = c.x; f32[4 * t + 1] = c.y; f32[4 * t + 2] = c.z; f32[4 * t + 3] = 1.0f; }
+        if (lookups) lookups[k] = n;
+    }
+}
+
+void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex, uint32_t* frame,
+                      float* f32, uint32_t* lookups)
+{
+    Built B;
+    build(S, cam, &B);
+    const FrameParams& P = B.P;
+    int W = P.probe_count[0] * P.probe_count[2] * P.rx;
+    int w = P.screen_w, h = P.screen_h;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int gy = 0; gy < (h / 16) * 16; gy++)
+        for (int gx = 0; gx < (w / 16) * 16; gx++) {
+            float cx = (float)gx / (float)w, cy = (float)gy / (float)h;
+            cy = 1.0f - cy;
+            v3 o, d;
+            pinhole_ray(P, cx, cy, &o, &d);
+            uint32_t n = 0;
+            v3 s = shade_ddgi(P, tex, W, o, d, n);
+            s = V3(0, 0, 0) + s;
+            size_t at = (size_t)gy * w + gx;
+            frame[at] = pack_rgba8(s.x, s.y, s.z, 1.0f);
+            if (f32) { f32[4 * at] = s.x; f32[4 * at + 1] = s.y; f32[4 * at + 2] = s.z; f32[4 * at + 3] = 1.0f; }
+            if (lookups) lookups[at] = n;
+        }
+}
+
+void sim_bake_scene(int scene, const int32_t* org, const int32_t* dim, uint8_t* out)
+{
+#pragma omp parallel for
+    for (int z = 0; z < dim[2]; z++)
+        for (int y = 0; y < dim[1]; y++)
+            for (int x = 0; x < dim[0]; x++)
+                out[((size_t)z * dim[1] + y) * dim[0] + x] =
+                    (uint8_t)block_procedural(V3((float)(x + org[0]), (float)(y + org[1]), (float)(z + org[2])), scene);
+}
+
+void sim_pin_sincos(const float* x, int n, float* s, float* c)
+{
+    for (int i = 0; i < n; i++) pin_sincos(x[i], &s[i], &c[i]);
+}
+void sim_pin_acos(const float* x, int n, float* out)
+{
+    for (int i = 0; i < n; i++) out[i] = pin_acos(x[i]);
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""GPU parity: the CUDA engine, called through the C-ABI, against the CPU oracle on the
+same inputs.  Bit-exact is the bar: RGBA8 bytes, the fp32 value before quantisation
+(compared as bit patterns) and the per-ray voxel-lookup counts.
+
+north_star's stated tolerance is 1e-3 relative L-inf on the fp32 texture / frame; the
+tests assert the stronger max |diff| == 0 and print the tolerance figure alongside.
+"""
+import numpy as np
+import pytest
+
+import ddgi_b200
+import util
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+CFG = util.configs.CONFIGS
+TOL_REL_LINF = 1e-3  # north_star tolerance; we require exact equality below
+
+
+def make_engine(cfg, *, debug=True, time=0.0):
+    r = ddgi_b200.RVPT(*cfg["screen"])
+    r.set_debug(debug)
+    util.configs.apply(r, cfg, time=time)
+    r.generate_probe_rays(reseed=True)
+    r.update(advance_time=False)
+    return r
+
+
+def oracle_rays(sc, cfg):
+    rx, ry = cfg["tile"]
+    return oracle.generate_probe_rays(sc, oracle.generate_samples(rx, ry, reseed=True))
+
+
+def rel_linf(a, b):
+    denom = max(float(np.abs(b).max()), 1e-30)
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / denom
+
+
+@pytest.mark.parametrize("name", ["cornell_2x2x2", "cornell_3x3x3", "cave_64", "field_8"])
+def test_bake_matches_oracle(name):
+    cfg = CFG[name]
+    with ddgi_b200.RVPT(64, 64) as r:
+        util.configs.apply(r, cfg)
+        got = r.read_voxels(cfg["voxels"][1])
+    want, _ = util.oracle_voxels(cfg)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["cornell_2x2x2", "cave_64", "field_8"])
+def test_generated_rays_match_reference_generator(name):
+    cfg = CFG[name]
+    sc = util.oracle_scene(cfg)
+    want = oracle_rays(sc, cfg)
+    with make_engine(cfg) as r:
+        got = r.probe_rays
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("ray_mode", ["generated", "ssbo"])
+@pytest.mark.parametrize("name", ["cornell_2x2x2", "cornell_3x3x3", "cave_64", "field_8"])
+def test_probe_texture_parity(name, ray_mode, variant):
+    cfg = CFG[name]
+    sc = util.oracle_scene(cfg)
+    rays = oracle_rays(sc, cfg)
+    alb, dist, f32, steps, _ = oracle.probe_update(sc, rays)
+    with make_engine(cfg) as r:
+        if ray_mode == "ssbo":
+            r.set_probe_rays(rays)
+        r.set_kernel_variant(variant)
+        r.probe_update()
+        r.sync()
+        got = r.read_probe_texture(0)
+        got_dist = r.read_probe_texture(1)
+        got_f32 = r.read_probe_texture(0, ddgi_b200.capi.FMT_F32)
+        got_steps = r.read_lookup_counts(0)
+    print(f"{name}: rel Linf fp32 = {rel_linf(got_f32[..., :3], f32[..., :3]):.3e} (tolerance {TOL_REL_LINF})")
+    assert np.array_equal(got_steps, steps), "voxel lookup counts differ: a ray took another discrete path"
+    assert np.array_equal(got_f32.view(np.uint32), f32.view(np.uint32))
+    assert np.array_equal(got, alb)
+    assert np.array_equal(got_dist, dist)
+    assert (got_dist == 0).all()
+
+
+@pytest.mark.parametrize("name", ["cornell_2x2x2", "cornell_3x3x3", "field_8"])
+def test_frame_parity(name):
+    cfg = CFG[name]
+    sc = util.oracle_scene(cfg)
+    rays = oracle_rays(sc, cfg)
+    alb, *_ = oracle.probe_update(sc, rays)
+    cam = util.camera_block(cfg)
+    frame, f32, steps = oracle.render_frame(sc, cam, alb)
+    with make_engine(cfg) as r:
+        r.draw()
+        r.sync()
+        got = r.read_frame()
+        got_f32 = r.read_frame(ddgi_b200.capi.FMT_F32)
+        got_steps = r.read_lookup_counts(1).reshape(got.shape)
+    w, h = cfg["screen"]
+    wx, hy = (w // 16) * 16, (h // 16) * 16
+    print(f"{name}: frame rel Linf fp32 = {rel_linf(got_f32[:hy, :wx, :3], f32[:hy, :wx, :3]):.3e}")
+    assert np.array_equal(got_steps[:hy, :wx], steps[:hy, :wx])
+    assert np.array_equal(got_f32[:hy, :wx].view(np.uint32), f32[:hy, :wx].view(np.uint32))
+    assert np.array_equal(got[:hy, :wx], frame[:hy, :wx])
+    # pixels outside the reference's truncated dispatch are never written
+    assert (got[hy:, :] == 0).all() and (got[:, wx:] == 0).all()
+
+
+def test_cave_1080p_frame_rows_sample():
+    """cfg 2 at its full 1920x1080: oracle on a 64-row band (the full frame takes too long on CPU)."""
+    cfg = CFG["cave_64"]
+    sc = util.oracle_scene(cfg)
+    rays = oracle_rays(sc, cfg)
+    alb, *_ = oracle.probe_update(sc, rays)
+    with make_engine(cfg, debug=False) as r:
+        r.draw()
+        r.sync()
+        got = r.read_frame()
+    # oracle renders a 1920 x 64 window whose rows are rows [512, 576) of the full frame:
+    # the pixel's y coordinate only enters through gy / h, so render full-height rows on
+    # a band by asking for the full frame lazily is not possible; instead compare a
+    # reduced-height render of identical per-pixel maths: same w, h but only check rows
+    frame, _, _ = oracle.render_frame(sc, util.camera_block(cfg), alb)
+    hy = (1080 // 16) * 16
+    assert np.array_equal(got[:hy], frame[:hy])
+    assert (got[hy:] == 0).all()
+
+
+def test_dynamic_lights_change_the_texture_and_stay_in_parity():
+    cfg = CFG["field_8"]
+    tex = []
+    for time in (0.0, 40.0):
+        sc = util.oracle_scene(cfg, time=time)
+        rays = oracle_rays(sc, cfg)
+        alb, *_ = oracle.probe_update(sc, rays)
+        with make_engine(cfg, time=time) as r:
+            r.probe_update()
+            r.sync()
+            got = r.read_probe_texture(0)
+        assert np.array_equal(got, alb)
+        tex.append(got)
+    assert not np.array_equal(tex[0], tex[1])
+
+
+def test_probe_row_shards_compose_to_the_full_texture():
+    """Two contexts each update half the probe rows; the halves tile the full result."""
+    cfg = CFG["field_8"]
+    with make_engine(cfg, debug=False) as r:
+        r.probe_update()
+        r.sync()
+        full = r.read_probe_texture(0)
+    rows = cfg["probe_count"][1]
+    ry = cfg["tile"][1]
+    parts = []
+    for rank in range(2):
+        y0, y1 = ddgi_b200.probe_row_shard(rows, rank, 2)
+        with make_engine(cfg, debug=False) as r:
+            r.set_probe_rows(y0, y1)
+            r.probe_update()
+            r.sync()
+            t = r.read_probe_texture(0)
+            assert (t[: y0 * ry] == 0).all() and (t[y1 * ry :] == 0).all()
+            parts.append(t[y0 * ry : y1 * ry])
+    assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+def test_idempotent_and_tuning_independent():
+    cfg = CFG["field_8"]
+    with make_engine(cfg, debug=False) as r:
+        r.probe_update()
+        r.sync()
+        a = r.read_probe_texture(0)
+        for m in (1, 8, 24, 32):
+            r.set_tuning(m)
+            r.probe_update()
+            r.sync()
+            assert np.array_equal(r.read_probe_texture(0), a)
+        n0 = r.launch_count
+        r.probe_update()
+        assert r.launch_count == n0 + 1
+
+
+def test_errors_are_reported_not_thrown():
+    with ddgi_b200.RVPT(64, 64) as r:
+        with pytest.raises(ddgi_b200.DDGIError) as e:
+            r.probe_update()
+        assert e.value.code == ddgi_b200.capi.E_STATE
+        r.render_settings.render_mode = 3
+        with pytest.raises(ddgi_b200.DDGIError) as e:
+            r.update()
+        assert e.value.code == ddgi_b200.capi.E_INVALID
+
+
+def test_empty_screen_and_zero_bounces():
+    cfg = util.small(CFG["cornell_2x2x2"], screen=(8, 8), max_bounces=0)
+    sc = util.oracle_scene(cfg)
+    rays = oracle_rays(sc, cfg)
+    alb, *_ = oracle.probe_update(sc, rays)
+    with make_engine(cfg) as r:
+        r.draw()  # 8x8 screen: floor(8/16) = 0 workgroups -> nothing is written
+        r.sync()
+        assert (r.read_frame() == 0).all()
+        assert np.array_equal(r.read_probe_texture(0), alb)
