@@ -33,7 +33,7 @@ struct ddgi_ctx {
     Light lights[kMaxLights];
 
     // voxel field
-    int vdim[3] = {0, 0, 0}, vorg[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
+    int vdim[3] = {0, 0, 0}, vorg[3] = {0, 0, 0}, borg[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
     uint8_t* d_types = nullptr;
     unsigned long long* d_occ = nullptr;
     float* d_palette = nullptr;
@@ -167,6 +167,7 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
         P->scene.vorg[a] = c->vorg[a];
         P->scene.vdim[a] = c->vdim[a];
         P->scene.nb[a] = c->nb[a];
+        P->scene.borg[a] = c->borg[a];
         P->scene.lo[a] = (float)c->vorg[a];
         P->scene.hi[a] = (float)(c->vorg[a] + c->vdim[a] - 1);
         P->probe_count[a] = c->field.probe_count[a];
@@ -211,7 +212,8 @@ static int alloc_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t orig
     for (int a = 0; a < 3; a++) {
         ctx->vdim[a] = dims[a];
         ctx->vorg[a] = origin[a];
-        ctx->nb[a] = (dims[a] + 3) / 4;
+        ctx->borg[a] = origin[a] & ~3;  // two's complement: rounds toward -inf to a multiple of 4
+        ctx->nb[a] = (origin[a] + dims[a] - ctx->borg[a] + 3) / 4;
     }
     size_t n = (size_t)dims[0] * dims[1] * dims[2];
     size_t nbk = (size_t)ctx->nb[0] * ctx->nb[1] * ctx->nb[2];
@@ -228,7 +230,8 @@ static int alloc_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t orig
 static int finish_voxels(ddgi_ctx* ctx)
 {
     int l = 0;
-    CU(launch_build_occupancy(ctx->vdim, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
+    int shift[3] = {ctx->vorg[0] - ctx->borg[0], ctx->vorg[1] - ctx->borg[1], ctx->vorg[2] - ctx->borg[2]};
+    CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
     ctx->launches += l;
     CU(cudaDeviceSynchronize());
     return DDGI_OK;

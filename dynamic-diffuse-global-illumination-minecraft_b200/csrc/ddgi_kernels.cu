@@ -212,7 +212,7 @@ __global__ void bake_synthetic_kernel(int dx, int dy, int dz, int permille, uint
 }
 
 // One thread per 4x4x4 brick: gathers 64 type bytes into the occupancy word.
-__global__ void build_occupancy_kernel(int dx, int dy, int dz, int nbx, int nby, int nbz,
+__global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, int sz, int nbx, int nby, int nbz,
                                        const uint8_t* types, unsigned long long* occ)
 {
     size_t nb = (size_t)nbx * nby * nbz;
@@ -224,8 +224,9 @@ __global__ void build_occupancy_kernel(int dx, int dy, int dz, int nbx, int nby,
         for (int z = 0; z < 4; z++)
             for (int y = 0; y < 4; y++)
                 for (int x = 0; x < 4; x++) {
-                    int gx = bx * 4 + x, gy = by * 4 + y, gz = bz * 4 + z;
-                    if (gx < dx && gy < dy && gz < dz &&
+                    // grid cell of this brick cell: bricks start (sx,sy,sz) cells before the grid
+                    int gx = bx * 4 + x - sx, gy = by * 4 + y - sy, gz = bz * 4 + z - sz;
+                    if (gx >= 0 && gy >= 0 && gz >= 0 && gx < dx && gy < dy && gz < dz &&
                         types[((size_t)gz * dy + gy) * dx + gx] != 0)
                         w |= 1ull << (x | (y << 2) | (z << 4));
                 }
@@ -299,11 +300,12 @@ cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permi
     return cudaGetLastError();
 }
 
-cudaError_t launch_build_occupancy(const int dims[3], const int nb[3], const uint8_t* types,
+cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const uint8_t* types,
                                    unsigned long long* occ, cudaStream_t s, int* launches)
 {
     size_t n = (size_t)nb[0] * nb[1] * nb[2];
-    build_occupancy_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], nb[0], nb[1], nb[2], types, occ);
+    build_occupancy_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], shift[0], shift[1], shift[2], nb[0], nb[1], nb[2],
+                                                        types, occ);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -3,9 +3,11 @@
 // scene bakers that evaluate that procedural function once per voxel.
 //
 // HBM layout (DESIGN.md "Data layout"):
-//   occ   : one uint64 per 4x4x4 voxel brick, bit (x&3)|(y&3)<<2|(z&3)<<4 set = solid.
-//           Brick index ((bz*nby)+by)*nbx+bx.  512^3 voxels -> 16 MiB: L2-resident, and
-//           a marching ray re-uses one 8-byte word for every step it spends in a brick.
+//   occ   : one uint64 per 4x4x4 voxel brick, bit (x&3)|(y&3)<<2|(z&3)<<4 set = solid,
+//           x/y/z = voxel id mod 4 (bricks are aligned to voxel ids that are multiples
+//           of 4).  Brick index ((bz*nby)+by)*nbx+bx.  512^3 voxels -> 16 MiB:
+//           L2-resident, and a marching ray re-uses one 8-byte word (kept in registers)
+//           for every step it spends in a brick.
 //   types : one uint8 block type per voxel, linear x-fastest; read only on a hit.
 //   palette: 256 x rgb fp32 albedo by block type (flat-colour variant, README.md:266).
 // Voxel id c (an integer-valued float, c = ceil(position)) covers (c-1, c] per axis;
@@ -21,23 +23,59 @@ struct SceneView {
     const float* palette;
     int vorg[3];
     int vdim[3];
-    int nb[3];
+    int borg[3];  // voxel id of brick (0,0,0)'s first cell: vorg rounded down to a multiple of 4
+    int nb[3];    // bricks per axis
     float lo[3];  // (float)vorg
     float hi[3];  // (float)(vorg + vdim - 1)
 };
 
+DDGI_HD int float_bits(float x)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_int(x);
+#else
+    union {
+        float f;
+        int i;
+    } u;
+    u.f = x;
+    return u.i;
+#endif
+}
+
+// Integer-valued float c -> kCellBias + (int)c, exact for |c| < 2^22 (one FADD instead
+// of a conversion).  Anything else (NaN, Inf, |c| >= 2^22) maps to a value whose brick
+// falls outside every grid the engine accepts (|voxel id| < 2^22), i.e. reads as empty.
+constexpr int kCellBias = 0x4B400000;
+DDGI_HD int cell_bits(float c) { return float_bits(c + 12582912.0f); }
+
+// Occupancy word of the brick containing the cell with biased integer coordinates
+// (kx,ky,kz) = cell_bits(c) per axis; 0 for bricks outside the grid.
+DDGI_HD unsigned long long brick_word(const SceneView& S, int kx, int ky, int kz)
+{
+    int bx = (kx - (kCellBias + S.borg[0])) >> 2;
+    int by = (ky - (kCellBias + S.borg[1])) >> 2;
+    int bz = (kz - (kCellBias + S.borg[2])) >> 2;
+    if ((unsigned)bx >= (unsigned)S.nb[0] || (unsigned)by >= (unsigned)S.nb[1] || (unsigned)bz >= (unsigned)S.nb[2])
+        return 0ull;
+    return S.occ[((size_t)bz * S.nb[1] + by) * S.nb[0] + bx];
+}
+DDGI_HD int brick_bit(int kx, int ky, int kz) { return (kx & 3) | ((ky & 3) << 2) | ((kz & 3) << 4); }
+
+// Block type of an occupied cell (only called after its occupancy bit tested set).
+DDGI_HD int scene_type_at(const SceneView& S, v3 c)
+{
+    int gx = (int)c.x - S.vorg[0], gy = (int)c.y - S.vorg[1], gz = (int)c.z - S.vorg[2];
+    return S.types[((size_t)gz * S.vdim[1] + gy) * S.vdim[0] + gx];
+}
+
 // Returns the block type (0 = empty) of voxel id c.
 DDGI_HD int scene_lookup(const SceneView& S, v3 c)
 {
-    if (!(c.x >= S.lo[0] && c.x <= S.hi[0] && c.y >= S.lo[1] && c.y <= S.hi[1] && c.z >= S.lo[2] &&
-          c.z <= S.hi[2]))
-        return 0;
-    int gx = (int)c.x - S.vorg[0], gy = (int)c.y - S.vorg[1], gz = (int)c.z - S.vorg[2];
-    size_t b = ((size_t)(gz >> 2) * S.nb[1] + (gy >> 2)) * S.nb[0] + (gx >> 2);
-    unsigned long long w = S.occ[b];
-    int bit = (gx & 3) | ((gy & 3) << 2) | ((gz & 3) << 4);
-    if (!((w >> bit) & 1ull)) return 0;
-    return S.types[((size_t)gz * S.vdim[1] + gy) * S.vdim[0] + gx];
+    int kx = cell_bits(c.x), ky = cell_bits(c.y), kz = cell_bits(c.z);
+    unsigned long long w = brick_word(S, kx, ky, kz);
+    if (!((w >> brick_bit(kx, ky, kz)) & 1ull)) return 0;
+    return scene_type_at(S, c);
 }
 
 DDGI_HD v3 scene_albedo(const SceneView& S, int type)

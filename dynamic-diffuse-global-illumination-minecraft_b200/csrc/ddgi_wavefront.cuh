@@ -5,16 +5,26 @@
 // A probe ray is a chain of nearest-hit queries: per bounce one query along the ray and
 // then one shadow feeler per light (assets/shaders/probe_pass.comp:283-295, :180-215).
 // Each query is a light-sphere pre-test plus a voxel march of up to 125 steps
-// (assets/shaders/intersection.glsl:1244-1301, :1051-1100).  March lengths are
-// geometrically distributed, so in the reference's nested-loop form a warp idles on its
-// longest march ~40 times per ray.  Here every lane is either MARCHING (wf_step: one
-// DDA advance + voxel test) or PENDING (wf_transition: resolve the query, shade, start
-// the next query); the kernel runs wf_step while enough lanes march and batches the
-// transitions (ddgi_kernels.cu: probe_update_wavefront).
+// (assets/shaders/intersection.glsl:1244-1301, :1051-1100).  Here every lane is either
+// MARCHING (wf_step: one DDA advance + voxel test) or PENDING (wf_transition: resolve
+// the query, shade, start the next query); the kernel runs wf_step while enough lanes
+// march and batches the transitions (ddgi_kernels.cu: probe_update_wavefront).
 //
-// Every floating-point operation, and its order, is the same as in ddgi_trace.cuh, so
-// both kernel variants (and the oracle) produce identical bits.
+// The arithmetic is the reference's, operation for operation, so results are
+// bit-identical to ddgi_trace.cuh and to the oracle.  What differs is only how each
+// correctly-rounded result is obtained:
+//   * max((-f)/d, (1-f)/d) needs one division: for d > 0 the first quotient is <= 0 <=
+//     the second, for d < 0 the other way round (f in [0,1]); zero / NaN / tiny
+//     components take the literal two-division form (WfRay::slow).
+//   * that division and x/0.1f use the FMA-corrected reciprocal of ddgi_fastmath.cuh.
+//   * floor(p) is ceil(p)-1 unless p is an integer; ceil(p) is needed anyway for the
+//     voxel id, so a step costs three FRND instead of six (integers take the literal form).
+//   * the voxel test reads the 4x4x4-brick occupancy word, kept in registers while the
+//     ray stays inside the brick; the block type is fetched only on a hit.
+//   * a light sphere whose discriminant is not positive yields t = INF in the reference
+//     (intersection.glsl:100-113), so the two root divisions are skipped for it.
 #pragma once
+#include "ddgi_fastmath.cuh"
 #include "ddgi_trace.cuh"
 
 namespace ddgi {
@@ -23,29 +33,64 @@ enum : int { WF_MARCH = 0, WF_PENDING = 1, WF_DONE = 2 };
 
 struct WfRay {
     // current march
-    v3 mo;       // query origin
-    v3 md;       // normalize(query direction)
-    v3 p;        // position after the last advance
-    v3 cell;     // ceil(p)
+    v3 mo;    // query origin
+    v3 md;    // normalize(query direction)
+    v3 inv;   // 1 / md (valid when !slow)
+    v3 p;     // position after the last advance
+    v3 c;     // ceil(p)
     float t;
     int steps;
     int mode;
-    int block;   // block type the march ended on (0: 125 steps without a hit)
+    bool slow;  // a direction component is zero, NaN or tiny: literal step arithmetic
+    // brick cache: biased cell coordinates of a cell inside the cached brick + its word
+    int kx, ky, kz;
+    unsigned long long word;
     // current query
-    v3 qd;       // query direction as given (positions are origin + qd * t)
+    v3 qd;  // query direction as given (positions are origin + qd * t)
     float light_t;
-    int light_i; // nearest light sphere so far, -1 none
-    v3 light_n;
+    int light_i;  // nearest light sphere, -1 none
     // path
     int bounce;
-    int phase;   // 0: the bounce ray itself; i >= 1: shadow feeler to light i-1
-    v3 hpos, hnormal, hbase;
+    int phase;  // 0: the bounce ray itself; i >= 1: shadow feeler to light i-1
+    bool blocked;  // the march ended on a solid cell (else: 125 steps, no hit)
+    v3 hpos, hnormal;
+    int hblock;  // block type of the bounce hit, -1 for a light sphere (albedo 0)
     v3 direct;
     int visible;
     v3 color;
     uint32_t rng;
     uint32_t lookups;
 };
+
+// Light-sphere pre-test of a query: nearest t over all lights and which light, exactly
+// as the loop of intersect_scene (intersection.glsl:1262-1279) evaluates it.  `normal`
+// (optional) receives the un-normalised sphere normal of the winning light.
+DDGI_HD float light_pretest(const FrameParams& P, v3 origin, v3 direction, int* which, v3* normal)
+{
+    float closest = inf_f();
+    *which = -1;
+    v3 d = div_tenth(direction);
+    float A = dot(d, d);
+    for (int i = 0; i < P.n_lights; i++) {
+        v3 o = div_tenth(origin - lpos(P.lights[i]));
+        float B = -dot(d, o);
+        float C = dot(o, o) - 1.0f;
+        float D = B * B - A * C;
+        if (!(D > 0)) continue;  // D -> INF: both roots fail the (0, maxt) window, t = INF
+        D = sqrtf(D);
+        float t1 = (B - D) / A;
+        float t2 = (B + D) / A;
+        t1 = (0.0f < t1 && t1 < closest) ? t1 : inf_f();
+        t2 = (0.0f < t2 && t2 < closest) ? t2 : inf_f();
+        float t = gmin(t1, t2);
+        if (t < closest) {
+            *which = i;
+            if (normal) *normal = o + d * t;
+        }
+        closest = gmin(t, closest);
+    }
+    return closest;
+}
 
 // Starts a nearest-hit query: light spheres first (they do not depend on the march),
 // then arm the march.
@@ -54,23 +99,14 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R, v3 origin, v3 direct
     R.mo = origin;
     R.qd = direction;
     R.md = normalize(direction);
+    R.slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z));
+    R.inv = R.slow ? V3(0, 0, 0) : V3(1.0f / R.md.x, 1.0f / R.md.y, 1.0f / R.md.z);
     R.p = origin;
+    R.c = V3(ceilf(origin.x), ceilf(origin.y), ceilf(origin.z));
     R.t = 0.0f;
     R.steps = 0;
-    R.block = 0;
-    float closest = inf_f();
-    R.light_i = -1;
-    R.light_n = V3(0, 0, 0);
-    for (int i = 0; i < P.n_lights; i++) {
-        v3 n;
-        float t = light_sphere(origin, direction, P.lights[i], closest, &n);
-        if (t < closest) {
-            R.light_i = i;
-            R.light_n = n;
-        }
-        closest = gmin(t, closest);
-    }
-    R.light_t = closest;
+    R.blocked = false;
+    R.light_t = light_pretest(P, origin, direction, &R.light_i, nullptr);
     R.mode = WF_MARCH;
 }
 
@@ -89,8 +125,11 @@ DDGI_HD void wf_init(const FrameParams& P, WfRay& R, v3 origin, v3 direction, ui
     R.bounce = 0;
     R.phase = 0;
     R.lookups = 0;
-    R.hpos = R.hnormal = R.hbase = V3(0, 0, 0);
-    R.cell = V3(0, 0, 0);
+    R.hpos = R.hnormal = V3(0, 0, 0);
+    R.hblock = -1;
+    // empty brick cache: a key no cell can have (kCellBias-relative coordinates are < 2^23)
+    R.kx = R.ky = R.kz = (int)0x80000000;
+    R.word = 0ull;
     if (P.max_bounces <= 0) {
         wf_finish_ray(P, R);
         return;
@@ -101,16 +140,40 @@ DDGI_HD void wf_init(const FrameParams& P, WfRay& R, v3 origin, v3 direction, ui
 // One DDA advance and voxel test (the body of the reference's 125-iteration loop).
 DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
 {
-    march_advance(R.mo, R.md, R.t, R.p);
-    R.cell = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
+    // ---- advance: t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 ----
+    v3 fl = V3(R.c.x - 1.0f, R.c.y - 1.0f, R.c.z - 1.0f);  // floor(p) unless p is an integer
+    v3 f = R.p - fl;
+    // numerator of the larger quotient: 1-f for d > 0, -f for d < 0
+    float nx = (R.md.x > 0 ? 1.0f : 0.0f) - f.x;
+    float ny = (R.md.y > 0 ? 1.0f : 0.0f) - f.y;
+    float nz = (R.md.z > 0 ? 1.0f : 0.0f) - f.z;
+    bool rare = R.slow || R.p.x == R.c.x || R.p.y == R.c.y || R.p.z == R.c.z ||
+                !(gmin(gmin(fabsf(nx), fabsf(ny)), fabsf(nz)) >= 7.888609e-31f);
+    if (!rare) {
+        float tx = div_markstein(nx, R.md.x, R.inv.x);
+        float ty = div_markstein(ny, R.md.y, R.inv.y);
+        float tz = div_markstein(nz, R.md.z, R.inv.z);
+        float step = gmin(gmin(tx, ty), tz) + 0.0001f;
+        R.t += step;
+        R.p = R.mo + R.md * R.t;
+    } else {
+        march_advance(R.mo, R.md, R.t, R.p);
+    }
+    R.c = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
     R.lookups++;
     R.steps++;
-    int type = scene_lookup(P.scene, R.cell);
-    if (type > 0) {
-        R.block = type;
+    // ---- voxel test through the register-cached brick word ----
+    int kx = cell_bits(R.c.x), ky = cell_bits(R.c.y), kz = cell_bits(R.c.z);
+    if ((unsigned)(((kx ^ R.kx) | (ky ^ R.ky)) | (kz ^ R.kz)) > 3u) {
+        R.word = brick_word(P.scene, kx, ky, kz);
+        R.kx = kx;
+        R.ky = ky;
+        R.kz = kz;
+    }
+    if ((R.word >> brick_bit(kx, ky, kz)) & 1ull) {
+        R.blocked = true;
         R.mode = WF_PENDING;
     } else if (R.steps >= kMarchSteps) {
-        R.block = 0;
         R.mode = WF_PENDING;
     }
 }
@@ -121,20 +184,12 @@ DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
 {
     float closest = R.light_t;
     int type = R.light_i >= 0 ? 2 : 0;
-    float t = closest;
-    v3 n = R.light_n;
-    v3 base = V3(0, 0, 0);
-    if (R.block > 0 && R.t < closest) {
-        t = R.t;
-        n = normalize(face_normal(R.p, R.cell));
-        base = scene_albedo(P.scene, R.block);
+    bool block_hit = R.blocked && R.t < closest;
+    if (block_hit) {
         closest = R.t;
         type = 3;
     }
     bool hit = closest < inf_f();
-    v3 normal = hit ? normalize(n) : V3(0, 0, 0);
-    v3 pos = hit ? R.mo + R.qd * t : V3(0, 0, 0);
-    pos = pos + normal * 0.001f;
 
     bool end_bounce = false;
     v3 result = V3(0, 0, 0);
@@ -144,9 +199,19 @@ DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
             wf_finish_ray(P, R);
             return;
         }
-        R.hpos = pos;
+        v3 n;
+        if (block_hit) {
+            n = normalize(face_normal(R.p, R.c));
+            R.hblock = scene_type_at(P.scene, R.c);
+        } else {
+            // a light sphere is the nearest hit (rare): redo the pre-test for its normal
+            int which;
+            light_pretest(P, R.mo, R.qd, &which, &n);
+            R.hblock = -1;
+        }
+        v3 normal = normalize(n);
+        R.hpos = (R.mo + R.qd * closest) + normal * 0.001f;
         R.hnormal = normal;
-        R.hbase = base;
         R.direct = V3(0, 0, 0);
         R.visible = 0;
         if (P.n_lights == 0) end_bounce = true;
@@ -161,15 +226,19 @@ DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
                 R.direct = R.direct + ((lcol(l) * lambert) * l.intensity) / dist;
                 R.visible++;
             } else {
+                v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
                 end_bounce = true;
-                result = (R.hbase * 0.2f) * lambert;
+                result = (base * 0.2f) * lambert;
             }
         }
         if (!end_bounce) {
             R.phase++;
             if (R.phase > P.n_lights) {
                 end_bounce = true;
-                if (R.visible != 0) result = (R.hbase * R.direct) / (float)R.visible;
+                if (R.visible != 0) {
+                    v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
+                    result = (base * R.direct) / (float)R.visible;
+                }
             }
         }
     }

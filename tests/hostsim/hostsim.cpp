@@ -40,11 +40,14 @@ static void build(const SimParams* S, const float* cam, Built* B)
 {
     FrameParams& P = B->P;
     memset(&P, 0, sizeof(P));
-    int nb[3];
+    int nb[3], sh[3];
     for (int a = 0; a < 3; a++) {
-        nb[a] = (S->vdim[a] + 3) / 4;
+        int borg = S->vorg[a] & ~3;
+        sh[a] = S->vorg[a] - borg;
+        nb[a] = (S->vorg[a] + S->vdim[a] - borg + 3) / 4;
         P.scene.vorg[a] = S->vorg[a];
         P.scene.vdim[a] = S->vdim[a];
+        P.scene.borg[a] = borg;
         P.scene.nb[a] = nb[a];
         P.scene.lo[a] = (float)S->vorg[a];
         P.scene.hi[a] = (float)(S->vorg[a] + S->vdim[a] - 1);
@@ -55,9 +58,11 @@ static void build(const SimParams* S, const float* cam, Built* B)
     for (int z = 0; z < S->vdim[2]; z++)
         for (int y = 0; y < S->vdim[1]; y++)
             for (int x = 0; x < S->vdim[0]; x++)
-                if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x])
-                    B->occ[((size_t)(z >> 2) * nb[1] + (y >> 2)) * nb[0] + (x >> 2)] |=
-                        1ull << ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+                if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x]) {
+                    int bx = x + sh[0], by = y + sh[1], bz = z + sh[2];
+                    B->occ[((size_t)(bz >> 2) * nb[1] + (by >> 2)) * nb[0] + (bx >> 2)] |=
+                        1ull << ((bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4));
+                }
     P.scene.occ = B->occ.data();
     P.scene.types = S->vox;
     P.scene.palette = S->palette;
