@@ -57,6 +57,7 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
     uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);
     J.albedo[t] = rgba;
     J.distance[t] = 0u;  // probe_pass.comp:276,302: distances = vec2(0)
+#pragma unroll 1
     for (int g = 0; g < J.n_peers; g++) {
         J.peer_albedo[g][t] = rgba;
         J.peer_distance[g][t] = 0u;
@@ -78,11 +79,16 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 }
 
 // ------------------------------------------------------------------ variant 1
-// Persistent warps over a global ray counter.  Each lane owns one probe ray as a WfRay
-// state machine.  The warp spins in the DDA step loop while at least `march_min/32` of
-// its live lanes are still marching, then runs the transition code once for every lane
-// whose march ended, retires finished rays (one texel store each) and refills the free
-// lanes with the next rays from the counter.
+// Persistent warps over a global ray counter; each lane owns one probe ray as a WfRay
+// state machine (ddgi_wavefront.cuh).  The warp alternates between
+//   march phase      : wf_step for every marching lane, repeated while at least
+//                      march_min/32 of the lanes that hold a ray are still marching;
+//   transition phase : every lane whose march ended resolves its query; a lane whose ray
+//                      is finished stores its texel and takes the next ray index (the
+//                      warp draws indices from the global counter 32 at a time); then all
+//                      of them start their next query through one wf_begin_query site.
+// Lanes therefore never wait for a refill, and the heavy divergent code (light-sphere
+// tests, normalisations, reciprocals) runs once per phase for all lanes that need it.
 constexpr int kWfThreads = 128;
 
 __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __grid_constant__ FrameParams P,
@@ -92,51 +98,78 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const uint32_t n_rays = J.ray_end - J.ray_begin;
     WfRay R;
-    R.mode = WF_DONE;
-    bool has_ray = false;
-    bool exhausted = false;
+    R.mode = WF_IDLE;
     uint32_t k = 0;
     int tx = 0, ty = 0;
+    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: ray indices already reserved
+    bool exhausted = false;
 
     for (;;) {
-        // ---- retire + refill ----
-        if (has_ray && R.mode == WF_DONE) {
-            store_texel(J, tx, ty, R.color, k, R.lookups);
-            has_ray = false;
-        }
-        unsigned want = __ballot_sync(full, !has_ray);
-        if (want && !exhausted) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(next_ray, (uint32_t)__popc(want));
-            base = __shfl_sync(full, base, 0);
-            if (base >= J.ray_end - J.ray_begin) exhausted = true;
-            if (!has_ray) {
-                uint32_t idx = base + (uint32_t)__popc(want & ((1u << lane) - 1u));
-                if (idx < J.ray_end - J.ray_begin) {
-                    k = J.ray_begin + idx;
-                    RayIn r = fetch_ray(P, J, k);
-                    tx = r.tx;
-                    ty = r.ty;
-                    wf_init(P, R, r.origin, r.direction, k);
-                    has_ray = true;
-                }
+        // ---- transition phase ----
+        v3 o, d;
+        bool start = false;
+        bool need = R.mode == WF_IDLE && !exhausted;
+        if (R.mode == WF_PENDING) {
+            if (wf_resolve(P, R, o, d)) {
+                store_texel(J, tx, ty, R.color, k, R.lookups);
+                R.mode = WF_IDLE;
+                need = true;
+            } else {
+                start = true;
             }
         }
-        unsigned live = __ballot_sync(full, has_ray);
-        if (live == 0) break;
-        const int n_live = __popc(live);
+        unsigned want = __ballot_sync(full, need);
+        if (want) {
+            uint32_t cnt = (uint32_t)__popc(want);
+            uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
+            uint32_t avail = chunk_end - chunk_next;
+            uint32_t idx;
+            if (cnt <= avail) {
+                idx = chunk_next + rank;
+                chunk_next += cnt;
+            } else {
+                uint32_t base = 0;
+                if (!exhausted) {
+                    if (lane == 0) base = atomicAdd(next_ray, 32u);
+                    base = __shfl_sync(full, base, 0);
+                } else {
+                    base = n_rays;
+                }
+                uint32_t nend = base + 32u < n_rays ? base + 32u : n_rays;
+                if (base >= n_rays) {
+                    exhausted = true;
+                    base = nend = n_rays;
+                }
+                idx = rank < avail ? chunk_next + rank : base + (rank - avail);
+                chunk_next = base + (cnt - avail);
+                chunk_end = nend;
+                if (chunk_next > chunk_end) chunk_next = chunk_end;
+            }
+            if (need && idx < n_rays) {
+                k = J.ray_begin + idx;
+                RayIn r = fetch_ray(P, J, k);
+                tx = r.tx;
+                ty = r.ty;
+                o = r.origin;
+                d = r.direction;
+                wf_init(R, k);
+                start = true;
+            }
+        }
+        if (start) wf_begin_query(P, R, o, d);
+
+        const int n_live = __popc(__ballot_sync(full, R.mode != WF_IDLE));
+        if (n_live == 0) break;
 
         // ---- march phase ----
         for (;;) {
-            bool marching = has_ray && R.mode == WF_MARCH;
+            bool marching = R.mode == WF_MARCH;
             int n_march = __popc(__ballot_sync(full, marching));
-            if (n_march == 0 || n_march * 32 < n_live * march_min) break;
+            if (n_march * 32 < n_live * march_min || n_march == 0) break;
             if (marching) wf_step(P, R);
         }
-
-        // ---- transition phase ----
-        if (has_ray && R.mode == WF_PENDING) wf_transition(P, R);
     }
 }
 
@@ -240,7 +273,7 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
 {
     uint32_t n = J.ray_end - J.ray_begin;
     if (n == 0) return cudaSuccess;
-    if (variant == 0) {
+    if (variant == 0 || P.max_bounces <= 0) {
         dim3 block(256), grid((n + 255) / 256);
         probe_update_direct<<<grid, block, 0, s>>>(P, J);
         (*launches)++;

@@ -19,8 +19,8 @@
 //   * that division and x/0.1f use the FMA-corrected reciprocal of ddgi_fastmath.cuh.
 //   * floor(p) is ceil(p)-1 unless p is an integer; ceil(p) is needed anyway for the
 //     voxel id, so a step costs three FRND instead of six (integers take the literal form).
-//   * the voxel test reads the 4x4x4-brick occupancy word, kept in registers while the
-//     ray stays inside the brick; the block type is fetched only on a hit.
+//   * the voxel test reads one bit of the 4x4x4-brick occupancy word (16 MiB for 512^3
+//     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
 //     (intersection.glsl:100-113), so the two root divisions are skipped for it.
 #pragma once
@@ -29,7 +29,7 @@
 
 namespace ddgi {
 
-enum : int { WF_MARCH = 0, WF_PENDING = 1, WF_DONE = 2 };
+enum : int { WF_MARCH = 0, WF_PENDING = 1, WF_DONE = 2, WF_IDLE = 3 };
 
 struct WfRay {
     // current march
@@ -42,9 +42,6 @@ struct WfRay {
     int steps;
     int mode;
     bool slow;  // a direction component is zero, NaN or tiny: literal step arithmetic
-    // brick cache: biased cell coordinates of a cell inside the cached brick + its word
-    int kx, ky, kz;
-    unsigned long long word;
     // current query
     v3 qd;  // query direction as given (positions are origin + qd * t)
     float light_t;
@@ -99,7 +96,10 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R, v3 origin, v3 direct
     R.mo = origin;
     R.qd = direction;
     R.md = normalize(direction);
-    R.slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z));
+    // fast-step preconditions (ddgi_fastmath.cuh): regular direction components, and no
+    // origin component in (0, 2^-70) so that a position is either 0 or >= 2^-98 in magnitude
+    R.slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) ||
+             tiny_nonzero(origin.x) || tiny_nonzero(origin.y) || tiny_nonzero(origin.z);
     R.inv = R.slow ? V3(0, 0, 0) : V3(1.0f / R.md.x, 1.0f / R.md.y, 1.0f / R.md.z);
     R.p = origin;
     R.c = V3(ceilf(origin.x), ceilf(origin.y), ceilf(origin.z));
@@ -116,7 +116,8 @@ DDGI_HD void wf_finish_ray(const FrameParams& P, WfRay& R)
     R.mode = WF_DONE;
 }
 
-DDGI_HD void wf_init(const FrameParams& P, WfRay& R, v3 origin, v3 direction, uint32_t ray_index)
+// Path state of a fresh ray (the caller starts its first query with wf_begin_query).
+DDGI_HD void wf_init(WfRay& R, uint32_t ray_index)
 {
     R.rng = wang_hash(ray_index);
     R.color = V3(0, 0, 0);
@@ -127,29 +128,22 @@ DDGI_HD void wf_init(const FrameParams& P, WfRay& R, v3 origin, v3 direction, ui
     R.lookups = 0;
     R.hpos = R.hnormal = V3(0, 0, 0);
     R.hblock = -1;
-    // empty brick cache: a key no cell can have (kCellBias-relative coordinates are < 2^23)
-    R.kx = R.ky = R.kz = (int)0x80000000;
-    R.word = 0ull;
-    if (P.max_bounces <= 0) {
-        wf_finish_ray(P, R);
-        return;
-    }
-    wf_begin_query(P, R, origin, direction);
 }
 
 // One DDA advance and voxel test (the body of the reference's 125-iteration loop).
 DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
 {
     // ---- advance: t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 ----
-    v3 fl = V3(R.c.x - 1.0f, R.c.y - 1.0f, R.c.z - 1.0f);  // floor(p) unless p is an integer
-    v3 f = R.p - fl;
-    // numerator of the larger quotient: 1-f for d > 0, -f for d < 0
-    float nx = (R.md.x > 0 ? 1.0f : 0.0f) - f.x;
-    float ny = (R.md.y > 0 ? 1.0f : 0.0f) - f.y;
-    float nz = (R.md.z > 0 ? 1.0f : 0.0f) - f.z;
-    bool rare = R.slow || R.p.x == R.c.x || R.p.y == R.c.y || R.p.z == R.c.z ||
-                !(gmin(gmin(fabsf(nx), fabsf(ny)), fabsf(nz)) >= 7.888609e-31f);
-    if (!rare) {
+    if (!R.slow) {
+        v3 fl = V3(R.c.x - 1.0f, R.c.y - 1.0f, R.c.z - 1.0f);  // floor(p) unless p is an integer
+        if (R.p.x == R.c.x || R.p.y == R.c.y || R.p.z == R.c.z)
+            fl = V3(floorf(R.p.x), floorf(R.p.y), floorf(R.p.z));
+        v3 f = R.p - fl;
+        // numerator of the larger quotient: 1-f for d > 0, -f for d < 0 (a zero numerator
+        // may come out as +0 where the reference has -0: min(..)+1e-4 is the same)
+        float nx = (R.md.x > 0 ? 1.0f : 0.0f) - f.x;
+        float ny = (R.md.y > 0 ? 1.0f : 0.0f) - f.y;
+        float nz = (R.md.z > 0 ? 1.0f : 0.0f) - f.z;
         float tx = div_markstein(nx, R.md.x, R.inv.x);
         float ty = div_markstein(ny, R.md.y, R.inv.y);
         float tz = div_markstein(nz, R.md.z, R.inv.z);
@@ -162,15 +156,10 @@ DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
     R.c = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
     R.lookups++;
     R.steps++;
-    // ---- voxel test through the register-cached brick word ----
+    // ---- voxel test: one bit of the brick occupancy word ----
     int kx = cell_bits(R.c.x), ky = cell_bits(R.c.y), kz = cell_bits(R.c.z);
-    if ((unsigned)(((kx ^ R.kx) | (ky ^ R.ky)) | (kz ^ R.kz)) > 3u) {
-        R.word = brick_word(P.scene, kx, ky, kz);
-        R.kx = kx;
-        R.ky = ky;
-        R.kz = kz;
-    }
-    if ((R.word >> brick_bit(kx, ky, kz)) & 1ull) {
+    unsigned long long word = brick_word(P.scene, kx, ky, kz);
+    if ((word >> brick_bit(kx, ky, kz)) & 1ull) {
         R.blocked = true;
         R.mode = WF_PENDING;
     } else if (R.steps >= kMarchSteps) {
@@ -178,9 +167,10 @@ DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
     }
 }
 
-// A march ended: resolve the query (nearest of light sphere / block), advance the
-// bounce / feeler bookkeeping and arm the next query (single wf_begin_query site).
-DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
+// A march ended: resolve the query (nearest of light sphere / block) and advance the
+// bounce / feeler bookkeeping.  Returns true when the ray is finished (R.color final),
+// otherwise the next query's origin / direction.
+DDGI_HD bool wf_resolve(const FrameParams& P, WfRay& R, v3& o, v3& d)
 {
     float closest = R.light_t;
     int type = R.light_i >= 0 ? 2 : 0;
@@ -197,7 +187,7 @@ DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
         // the bounce ray itself
         if (!hit) {
             wf_finish_ray(P, R);
-            return;
+            return true;
         }
         v3 n;
         if (block_hit) {
@@ -242,7 +232,6 @@ DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
             }
         }
     }
-    v3 o, d;
     if (end_bounce) {
         // probe_pass.comp:286-292: accumulate, pick the next bounce direction
         R.color = R.color + result;
@@ -251,14 +240,14 @@ DDGI_HD void wf_transition(const FrameParams& P, WfRay& R)
         R.bounce++;
         if (R.bounce >= P.max_bounces) {
             wf_finish_ray(P, R);
-            return;
+            return true;
         }
         R.phase = 0;
     } else {
         o = R.hpos;
         d = normalize(lpos(P.lights[R.phase - 1]) - R.hpos);
     }
-    wf_begin_query(P, R, o, d);
+    return false;
 }
 
 // Scalar driver (tests/hostsim): the state machine stepped for a single ray.
@@ -266,10 +255,20 @@ DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction,
                                   uint32_t& lookups)
 {
     WfRay R;
-    wf_init(P, R, origin, direction, ray_index);
-    while (R.mode != WF_DONE) {
-        if (R.mode == WF_MARCH) wf_step(P, R);
-        else wf_transition(P, R);
+    wf_init(R, ray_index);
+    if (P.max_bounces <= 0) {
+        wf_finish_ray(P, R);
+        return R.color;
+    }
+    wf_begin_query(P, R, origin, direction);
+    for (;;) {
+        if (R.mode == WF_MARCH) {
+            wf_step(P, R);
+            continue;
+        }
+        v3 o, d;
+        if (wf_resolve(P, R, o, d)) break;
+        wf_begin_query(P, R, o, d);
     }
     lookups += R.lookups;
     return R.color;
