@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
         v3 o, d;
         bool start = false;
         bool need = R.mode == WF_IDLE && !exhausted;
-        if (R.mode == WF_PENDING) {
+        if (R.mode == WF_HIT || R.mode == WF_MISS) {
             if (wf_resolve(P, R, o, d)) {
                 store_texel(J, tx, ty, R.color, k, R.lookups);
                 R.mode = WF_IDLE;
@@ -164,11 +164,9 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
         if (n_live == 0) break;
 
         // ---- march phase ----
-        for (;;) {
-            bool marching = R.mode == WF_MARCH;
-            int n_march = __popc(__ballot_sync(full, marching));
-            if (n_march * 32 < n_live * march_min || n_march == 0) break;
-            if (marching) wf_step(P, R);
+        const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // in 1/32 lanes, >= 1 lane
+        while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) * 32 >= enough) {
+            if (R.mode == WF_MARCH) wf_step(P, R);
         }
     }
 }

@@ -20,6 +20,12 @@
 #define DDGI_D inline
 #endif
 
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define DDGI_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define DDGI_UNLIKELY(x) (x)
+#endif
+
 namespace ddgi {
 
 struct v3 {

@@ -49,18 +49,25 @@ DDGI_HD int float_bits(float x)
 constexpr int kCellBias = 0x4B400000;
 DDGI_HD int cell_bits(float c) { return float_bits(c + 12582912.0f); }
 
-// Occupancy word of the brick containing the cell with biased integer coordinates
-// (kx,ky,kz) = cell_bits(c) per axis; 0 for bricks outside the grid.
-DDGI_HD unsigned long long brick_word(const SceneView& S, int kx, int ky, int kz)
+// Occupancy test of the cell with biased integer coordinates (kx,ky,kz) = cell_bits(c)
+// per axis: the 32-bit half (z&2 selects it) of the brick word, 0 for bricks outside the
+// grid, and the bit inside that half.
+DDGI_HD uint32_t brick_half(const SceneView& S, int kx, int ky, int kz)
 {
     int bx = (kx - (kCellBias + S.borg[0])) >> 2;
     int by = (ky - (kCellBias + S.borg[1])) >> 2;
     int bz = (kz - (kCellBias + S.borg[2])) >> 2;
     if ((unsigned)bx >= (unsigned)S.nb[0] || (unsigned)by >= (unsigned)S.nb[1] || (unsigned)bz >= (unsigned)S.nb[2])
-        return 0ull;
-    return S.occ[((size_t)bz * S.nb[1] + by) * S.nb[0] + bx];
+        return 0u;
+    unsigned idx = ((unsigned)bz * (unsigned)S.nb[1] + (unsigned)by) * (unsigned)S.nb[0] + (unsigned)bx;
+    return reinterpret_cast<const uint32_t*>(S.occ)[2u * idx + (((unsigned)kz >> 1) & 1u)];
 }
-DDGI_HD int brick_bit(int kx, int ky, int kz) { return (kx & 3) | ((ky & 3) << 2) | ((kz & 3) << 4); }
+DDGI_HD bool cell_solid(const SceneView& S, int kx, int ky, int kz)
+{
+    uint32_t half = brick_half(S, kx, ky, kz);
+    int bit = (kx & 3) | ((ky & 3) << 2) | ((kz & 1) << 4);
+    return (half >> bit) & 1u;
+}
 
 // Block type of an occupied cell (only called after its occupancy bit tested set).
 DDGI_HD int scene_type_at(const SceneView& S, v3 c)
@@ -72,9 +79,7 @@ DDGI_HD int scene_type_at(const SceneView& S, v3 c)
 // Returns the block type (0 = empty) of voxel id c.
 DDGI_HD int scene_lookup(const SceneView& S, v3 c)
 {
-    int kx = cell_bits(c.x), ky = cell_bits(c.y), kz = cell_bits(c.z);
-    unsigned long long w = brick_word(S, kx, ky, kz);
-    if (!((w >> brick_bit(kx, ky, kz)) & 1ull)) return 0;
+    if (!cell_solid(S, cell_bits(c.x), cell_bits(c.y), cell_bits(c.z))) return 0;
     return scene_type_at(S, c);
 }
 

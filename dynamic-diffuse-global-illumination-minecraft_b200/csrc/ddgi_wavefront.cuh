@@ -29,7 +29,8 @@
 
 namespace ddgi {
 
-enum : int { WF_MARCH = 0, WF_PENDING = 1, WF_DONE = 2, WF_IDLE = 3 };
+// WF_HIT / WF_MISS: the march ended on a solid cell / after 125 empty cells
+enum : int { WF_MARCH = 0, WF_HIT = 1, WF_MISS = 2, WF_DONE = 3, WF_IDLE = 4 };
 
 struct WfRay {
     // current march
@@ -41,7 +42,7 @@ struct WfRay {
     float t;
     int steps;
     int mode;
-    bool slow;  // a direction component is zero, NaN or tiny: literal step arithmetic
+    int slow;  // a direction component is zero, NaN or tiny: literal step arithmetic
     // current query
     v3 qd;  // query direction as given (positions are origin + qd * t)
     float light_t;
@@ -49,7 +50,6 @@ struct WfRay {
     // path
     int bounce;
     int phase;  // 0: the bounce ray itself; i >= 1: shadow feeler to light i-1
-    bool blocked;  // the march ended on a solid cell (else: 125 steps, no hit)
     v3 hpos, hnormal;
     int hblock;  // block type of the bounce hit, -1 for a light sphere (albedo 0)
     v3 direct;
@@ -98,14 +98,13 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R, v3 origin, v3 direct
     R.md = normalize(direction);
     // fast-step preconditions (ddgi_fastmath.cuh): regular direction components, and no
     // origin component in (0, 2^-70) so that a position is either 0 or >= 2^-98 in magnitude
-    R.slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) ||
-             tiny_nonzero(origin.x) || tiny_nonzero(origin.y) || tiny_nonzero(origin.z);
+    R.slow = (int)!(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) |
+             (int)(tiny_nonzero(origin.x) || tiny_nonzero(origin.y) || tiny_nonzero(origin.z));
     R.inv = R.slow ? V3(0, 0, 0) : V3(1.0f / R.md.x, 1.0f / R.md.y, 1.0f / R.md.z);
     R.p = origin;
     R.c = V3(ceilf(origin.x), ceilf(origin.y), ceilf(origin.z));
     R.t = 0.0f;
     R.steps = 0;
-    R.blocked = false;
     R.light_t = light_pretest(P, origin, direction, &R.light_i, nullptr);
     R.mode = WF_MARCH;
 }
@@ -136,7 +135,7 @@ DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
     // ---- advance: t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 ----
     if (!R.slow) {
         v3 fl = V3(R.c.x - 1.0f, R.c.y - 1.0f, R.c.z - 1.0f);  // floor(p) unless p is an integer
-        if (R.p.x == R.c.x || R.p.y == R.c.y || R.p.z == R.c.z)
+        if (DDGI_UNLIKELY(R.p.x == R.c.x || R.p.y == R.c.y || R.p.z == R.c.z))
             fl = V3(floorf(R.p.x), floorf(R.p.y), floorf(R.p.z));
         v3 f = R.p - fl;
         // numerator of the larger quotient: 1-f for d > 0, -f for d < 0 (a zero numerator
@@ -154,17 +153,10 @@ DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
         march_advance(R.mo, R.md, R.t, R.p);
     }
     R.c = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
-    R.lookups++;
     R.steps++;
     // ---- voxel test: one bit of the brick occupancy word ----
-    int kx = cell_bits(R.c.x), ky = cell_bits(R.c.y), kz = cell_bits(R.c.z);
-    unsigned long long word = brick_word(P.scene, kx, ky, kz);
-    if ((word >> brick_bit(kx, ky, kz)) & 1ull) {
-        R.blocked = true;
-        R.mode = WF_PENDING;
-    } else if (R.steps >= kMarchSteps) {
-        R.mode = WF_PENDING;
-    }
+    if (cell_solid(P.scene, cell_bits(R.c.x), cell_bits(R.c.y), cell_bits(R.c.z))) R.mode = WF_HIT;
+    else if (R.steps >= kMarchSteps) R.mode = WF_MISS;
 }
 
 // A march ended: resolve the query (nearest of light sphere / block) and advance the
@@ -174,7 +166,8 @@ DDGI_HD bool wf_resolve(const FrameParams& P, WfRay& R, v3& o, v3& d)
 {
     float closest = R.light_t;
     int type = R.light_i >= 0 ? 2 : 0;
-    bool block_hit = R.blocked && R.t < closest;
+    bool block_hit = R.mode == WF_HIT && R.t < closest;
+    R.lookups += (uint32_t)R.steps;
     if (block_hit) {
         closest = R.t;
         type = 3;
