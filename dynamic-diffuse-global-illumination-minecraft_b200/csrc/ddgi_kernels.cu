@@ -80,15 +80,13 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 
 // ------------------------------------------------------------------ variant 1
 // Persistent warps over a global ray counter; each lane owns one probe ray as a WfRay
-// state machine (ddgi_wavefront.cuh).  The warp alternates between
-//   march phase      : wf_step for every marching lane, repeated while at least
-//                      march_min/32 of the lanes that hold a ray are still marching;
-//   transition phase : every lane whose march ended resolves its query; a lane whose ray
-//                      is finished stores its texel and takes the next ray index (the
-//                      warp draws indices from the global counter 32 at a time); then all
-//                      of them start their next query through one wf_begin_query site.
-// Lanes therefore never wait for a refill, and the heavy divergent code (light-sphere
-// tests, normalisations, reciprocals) runs once per phase for all lanes that need it.
+// state machine (ddgi_wavefront.cuh).  The warp steps the DDA march while at least
+// march_min/32 of its rays are marching; below that it counts its lanes per remaining
+// state (ballots), picks the fullest one and runs that state's code for exactly those
+// lanes.  The other lanes wait and accumulate, so each code block executes with many
+// lanes active instead of once per divergent lane group.
+// Finished rays store their texel in WF_FETCH and take the next ray index there (the
+// warp draws indices from the global counter 32 at a time).
 constexpr int kWfThreads = 128;
 
 __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __grid_constant__ FrameParams P,
@@ -100,28 +98,50 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
     const int lane = threadIdx.x & 31;
     const uint32_t n_rays = J.ray_end - J.ray_begin;
     WfRay R;
-    R.mode = WF_IDLE;
-    uint32_t k = 0;
+    R.mode = WF_FETCH;
+    uint32_t k = 0xffffffffu;  // no ray yet
     int tx = 0, ty = 0;
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: ray indices already reserved
     bool exhausted = false;
 
     for (;;) {
-        // ---- transition phase ----
-        v3 o, d;
-        bool start = false;
-        bool need = R.mode == WF_IDLE && !exhausted;
-        if (R.mode == WF_HIT || R.mode == WF_MISS) {
-            if (wf_resolve(P, R, o, d)) {
-                store_texel(J, tx, ty, R.color, k, R.lookups);
-                R.mode = WF_IDLE;
-                need = true;
-            } else {
-                start = true;
+        // ---- march while at least march_min/32 of the lanes holding a ray are marching ----
+        const int n_live = __popc(__ballot_sync(full, R.mode != WF_IDLE));
+        if (n_live == 0) break;
+        const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // in 1/32 lanes, >= 1 lane
+        while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) * 32 >= enough) {
+            if (R.mode == WF_MARCH) wf_step(P, R);
+        }
+        // ---- otherwise run the fullest of the other states (ties: the later stage) ----
+        int best = -1, best_n = 0;
+        const int same = __shfl_sync(full, R.mode, 0);
+        if (__all_sync(full, R.mode == same)) {
+            best = same;  // coherent warp (e.g. every probe ray of a probe buried in rock)
+        } else {
+#pragma unroll
+            for (int s = WF_QUERY; s < WF_NUM_STATES; s++) {
+                int n = __popc(__ballot_sync(full, R.mode == s));
+                if (n >= best_n && n > 0) {
+                    best_n = n;
+                    best = s;
+                }
             }
         }
-        unsigned want = __ballot_sync(full, need);
-        if (want) {
+        if (best <= WF_MARCH) continue;  // only marching lanes are left: lower the bar next pass
+
+        if (best == WF_QUERY) {
+            if (R.mode == WF_QUERY) wf_begin_query(P, R);
+        } else if (best == WF_BOUNCE_HIT) {
+            if (R.mode == WF_BOUNCE_HIT) wf_resolve_bounce(P, R);
+        } else if (best == WF_FEELER_HIT) {
+            if (R.mode == WF_FEELER_HIT) wf_resolve_feeler(P, R);
+        } else if (best == WF_SCATTER) {
+            if (R.mode == WF_SCATTER) wf_scatter(P, R);
+        } else {
+            // WF_FETCH: store the finished ray, take the next one
+            bool need = R.mode == WF_FETCH;
+            if (need && k != 0xffffffffu) store_texel(J, tx, ty, R.color, k, R.lookups);
+            unsigned want = __ballot_sync(full, need);
             uint32_t cnt = (uint32_t)__popc(want);
             uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
             uint32_t avail = chunk_end - chunk_next;
@@ -130,12 +150,10 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
                 idx = chunk_next + rank;
                 chunk_next += cnt;
             } else {
-                uint32_t base = 0;
+                uint32_t base = n_rays;
                 if (!exhausted) {
                     if (lane == 0) base = atomicAdd(next_ray, 32u);
                     base = __shfl_sync(full, base, 0);
-                } else {
-                    base = n_rays;
                 }
                 uint32_t nend = base + 32u < n_rays ? base + 32u : n_rays;
                 if (base >= n_rays) {
@@ -147,26 +165,17 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
                 chunk_end = nend;
                 if (chunk_next > chunk_end) chunk_next = chunk_end;
             }
-            if (need && idx < n_rays) {
-                k = J.ray_begin + idx;
-                RayIn r = fetch_ray(P, J, k);
-                tx = r.tx;
-                ty = r.ty;
-                o = r.origin;
-                d = r.direction;
-                wf_init(R, k);
-                start = true;
+            if (need) {
+                if (idx < n_rays) {
+                    k = J.ray_begin + idx;
+                    RayIn r = fetch_ray(P, J, k);
+                    tx = r.tx;
+                    ty = r.ty;
+                    wf_init(R, r.origin, r.direction, k);
+                } else {
+                    R.mode = WF_IDLE;
+                }
             }
-        }
-        if (start) wf_begin_query(P, R, o, d);
-
-        const int n_live = __popc(__ballot_sync(full, R.mode != WF_IDLE));
-        if (n_live == 0) break;
-
-        // ---- march phase ----
-        const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // in 1/32 lanes, >= 1 lane
-        while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) * 32 >= enough) {
-            if (R.mode == WF_MARCH) wf_step(P, R);
         }
     }
 }

@@ -1,14 +1,24 @@
 // ddgi_wavefront.cuh — the probe-ray path of ddgi_trace.cuh re-expressed as a per-lane
-// state machine, so a warp can keep all lanes inside the DDA step loop and regroup the
-// expensive, divergent "a march just ended" work.
+// state machine whose states a warp executes one at a time, most-populated first.
 //
 // A probe ray is a chain of nearest-hit queries: per bounce one query along the ray and
 // then one shadow feeler per light (assets/shaders/probe_pass.comp:283-295, :180-215).
 // Each query is a light-sphere pre-test plus a voxel march of up to 125 steps
-// (assets/shaders/intersection.glsl:1244-1301, :1051-1100).  Here every lane is either
-// MARCHING (wf_step: one DDA advance + voxel test) or PENDING (wf_transition: resolve
-// the query, shade, start the next query); the kernel runs wf_step while enough lanes
-// march and batches the transitions (ddgi_kernels.cu: probe_update_wavefront).
+// (assets/shaders/intersection.glsl:1244-1301, :1051-1100).  In the reference's nested
+// loops a warp serialises every divergent branch of that chain.  Here each lane carries
+// its ray as a WfRay and is always in exactly one state:
+//
+//   WF_QUERY       wf_begin_query     normalise direction, reciprocals, light-sphere pre-test
+//   WF_MARCH       wf_step            one DDA advance + voxel test (repeated)
+//   WF_BOUNCE_HIT  wf_resolve_bounce  the bounce ray's march ended: hit record, first feeler
+//   WF_FEELER_HIT  wf_resolve_feeler  a shadow feeler's march ended: direct term / next feeler
+//   WF_SCATTER     wf_scatter         bounce finished: cosine-weighted direction for the next
+//   WF_FETCH       (kernel)           ray finished: store its texel, take the next ray
+//
+// and the kernel (ddgi_kernels.cu: probe_update_wavefront) repeatedly counts the lanes
+// per state with ballots and runs the code of the fullest state for exactly those lanes.
+// Every block of code therefore executes with many lanes active instead of once per
+// divergent lane group.
 //
 // The arithmetic is the reference's, operation for operation, so results are
 // bit-identical to ddgi_trace.cuh and to the oracle.  What differs is only how each
@@ -18,28 +28,37 @@
 //     components take the literal two-division form (WfRay::slow).
 //   * that division and x/0.1f use the FMA-corrected reciprocal of ddgi_fastmath.cuh.
 //   * floor(p) is ceil(p)-1 unless p is an integer; ceil(p) is needed anyway for the
-//     voxel id, so a step costs three FRND instead of six (integers take the literal form).
+//     voxel id, so a step costs three FRND instead of six.
 //   * the voxel test reads one bit of the 4x4x4-brick occupancy word (16 MiB for 512^3
 //     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
 //     (intersection.glsl:100-113), so the two root divisions are skipped for it.
+//   * normalize() of an axis-aligned unit vector is the identity (1/sqrt(1) = 1).
 #pragma once
 #include "ddgi_fastmath.cuh"
 #include "ddgi_trace.cuh"
 
 namespace ddgi {
 
-// WF_HIT / WF_MISS: the march ended on a solid cell / after 125 empty cells
-enum : int { WF_MARCH = 0, WF_HIT = 1, WF_MISS = 2, WF_DONE = 3, WF_IDLE = 4 };
+enum : int {
+    WF_MARCH = 0,
+    WF_QUERY = 1,
+    WF_BOUNCE_HIT = 2,
+    WF_FEELER_HIT = 3,
+    WF_SCATTER = 4,
+    WF_FETCH = 5,
+    WF_IDLE = 6,
+    WF_NUM_STATES = 6  // schedulable states (IDLE excluded)
+};
 
 struct WfRay {
     // current march
-    v3 mo;    // query origin
-    v3 md;    // normalize(query direction)
-    v3 inv;   // 1 / md (valid when !slow)
-    v3 p;     // position after the last advance
-    v3 c;     // ceil(p)
-    float t;
+    v3 mo;   // query origin
+    v3 md;   // normalize(query direction)
+    v3 inv;  // 1 / md (valid when !slow)
+    v3 p;    // position after the last advance
+    v3 c;    // ceil(p)
+    float t; // march parameter; +INF once the march has ended without a hit
     int steps;
     int mode;
     int slow;  // a direction component is zero, NaN or tiny: literal step arithmetic
@@ -58,6 +77,14 @@ struct WfRay {
     uint32_t rng;
     uint32_t lookups;
 };
+
+// normalize(v) with the exact shortcut for axis-aligned unit vectors: dot = 1,
+// sqrt(1) = 1, 1/1 = 1, v * 1 = v.
+DDGI_HD v3 normalize_axis_aware(v3 v)
+{
+    if ((fabsf(v.x) + fabsf(v.y)) + fabsf(v.z) == 1.0f && (v.x == 0.0f) + (v.y == 0.0f) + (v.z == 0.0f) == 2) return v;
+    return normalize(v);
+}
 
 // Light-sphere pre-test of a query: nearest t over all lights and which light, exactly
 // as the loop of intersect_scene (intersection.glsl:1262-1279) evaluates it.  `normal`
@@ -89,13 +116,12 @@ DDGI_HD float light_pretest(const FrameParams& P, v3 origin, v3 direction, int* 
     return closest;
 }
 
-// Starts a nearest-hit query: light spheres first (they do not depend on the march),
-// then arm the march.
-DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R, v3 origin, v3 direction)
+// WF_QUERY: starts the nearest-hit query (R.mo, R.qd): light spheres first (they do not
+// depend on the march), then arm the march.
+DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R)
 {
-    R.mo = origin;
-    R.qd = direction;
-    R.md = normalize(direction);
+    v3 origin = R.mo;
+    R.md = normalize(R.qd);
     // fast-step preconditions (ddgi_fastmath.cuh): regular direction components, and no
     // origin component in (0, 2^-70) so that a position is either 0 or >= 2^-98 in magnitude
     R.slow = (int)!(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) |
@@ -105,18 +131,19 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R, v3 origin, v3 direct
     R.c = V3(ceilf(origin.x), ceilf(origin.y), ceilf(origin.z));
     R.t = 0.0f;
     R.steps = 0;
-    R.light_t = light_pretest(P, origin, direction, &R.light_i, nullptr);
+    R.light_t = light_pretest(P, origin, R.qd, &R.light_i, nullptr);
     R.mode = WF_MARCH;
 }
 
+// The ray is complete: final colour, then WF_FETCH stores it.
 DDGI_HD void wf_finish_ray(const FrameParams& P, WfRay& R)
 {
     R.color = R.color / (float)P.max_bounces;
-    R.mode = WF_DONE;
+    R.mode = WF_FETCH;
 }
 
-// Path state of a fresh ray (the caller starts its first query with wf_begin_query).
-DDGI_HD void wf_init(WfRay& R, uint32_t ray_index)
+// Path state of a fresh ray with first query (origin, direction).
+DDGI_HD void wf_init(WfRay& R, v3 origin, v3 direction, uint32_t ray_index)
 {
     R.rng = wang_hash(ray_index);
     R.color = V3(0, 0, 0);
@@ -127,9 +154,12 @@ DDGI_HD void wf_init(WfRay& R, uint32_t ray_index)
     R.lookups = 0;
     R.hpos = R.hnormal = V3(0, 0, 0);
     R.hblock = -1;
+    R.mo = origin;
+    R.qd = direction;
+    R.mode = WF_QUERY;
 }
 
-// One DDA advance and voxel test (the body of the reference's 125-iteration loop).
+// WF_MARCH: one DDA advance and voxel test (the body of the reference's 125-iteration loop).
 DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
 {
     // ---- advance: t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 ----
@@ -155,92 +185,111 @@ DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
     R.c = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
     R.steps++;
     // ---- voxel test: one bit of the brick occupancy word ----
-    if (cell_solid(P.scene, cell_bits(R.c.x), cell_bits(R.c.y), cell_bits(R.c.z))) R.mode = WF_HIT;
-    else if (R.steps >= kMarchSteps) R.mode = WF_MISS;
+    if (cell_solid(P.scene, cell_bits(R.c.x), cell_bits(R.c.y), cell_bits(R.c.z))) {
+        R.mode = R.phase == 0 ? WF_BOUNCE_HIT : WF_FEELER_HIT;
+    } else if (R.steps >= kMarchSteps) {
+        R.t = inf_f();  // no block within 125 cells
+        R.mode = R.phase == 0 ? WF_BOUNCE_HIT : WF_FEELER_HIT;
+    }
 }
 
-// A march ended: resolve the query (nearest of light sphere / block) and advance the
-// bounce / feeler bookkeeping.  Returns true when the ray is finished (R.color final),
-// otherwise the next query's origin / direction.
-DDGI_HD bool wf_resolve(const FrameParams& P, WfRay& R, v3& o, v3& d)
+// Arms the shadow feeler to light R.phase-1 from the current bounce hit.
+DDGI_HD void wf_aim_feeler(const FrameParams& P, WfRay& R)
 {
-    float closest = R.light_t;
-    int type = R.light_i >= 0 ? 2 : 0;
-    bool block_hit = R.mode == WF_HIT && R.t < closest;
-    R.lookups += (uint32_t)R.steps;
-    if (block_hit) {
-        closest = R.t;
-        type = 3;
-    }
-    bool hit = closest < inf_f();
+    R.mo = R.hpos;
+    R.qd = normalize(lpos(P.lights[R.phase - 1]) - R.hpos);
+    R.mode = WF_QUERY;
+}
 
-    bool end_bounce = false;
-    v3 result = V3(0, 0, 0);
-    if (R.phase == 0) {
-        // the bounce ray itself
-        if (!hit) {
-            wf_finish_ray(P, R);
-            return true;
-        }
+// WF_BOUNCE_HIT: the bounce ray's march ended.  Nearest of light sphere / block; on a
+// miss the ray is complete, else record the hit and aim the first feeler.
+DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
+{
+    R.lookups += (uint32_t)R.steps;
+    float closest = R.light_t;
+    bool block_hit = R.t < closest;
+    if (block_hit) closest = R.t;
+    if (!(closest < inf_f())) {
+        wf_finish_ray(P, R);
+        return;
+    }
+    v3 normal;
+    if (block_hit) {
+        // face_normal is axis-aligned (or zero for a NaN position): both normalize() calls
+        // of the reference (grid_march :1088, intersect_scene :1294) are identities on it
+        normal = normalize_axis_aware(normalize_axis_aware(face_normal(R.p, R.c)));
+        R.hblock = scene_type_at(P.scene, R.c);
+    } else {
+        // a light sphere is the nearest hit (rare): redo the pre-test for its normal
+        int which;
         v3 n;
-        if (block_hit) {
-            n = normalize(face_normal(R.p, R.c));
-            R.hblock = scene_type_at(P.scene, R.c);
+        light_pretest(P, R.mo, R.qd, &which, &n);
+        normal = normalize(n);
+        R.hblock = -1;
+    }
+    R.hpos = (R.mo + R.qd * closest) + normal * 0.001f;
+    R.hnormal = normal;
+    R.direct = V3(0, 0, 0);
+    R.visible = 0;
+    if (P.n_lights == 0) {
+        R.mode = WF_SCATTER;  // direct term 0
+        return;
+    }
+    R.phase = 1;
+    wf_aim_feeler(P, R);
+}
+
+// WF_FEELER_HIT: the feeler to light R.phase-1 ended (probe_pass.comp:186-212).
+DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
+{
+    R.lookups += (uint32_t)R.steps;
+    float closest = R.light_t;
+    bool block_hit = R.t < closest;
+    if (block_hit) closest = R.t;
+    const Light& l = P.lights[R.phase - 1];
+    if (closest < inf_f()) {
+        float lambert = gclamp(dot(normalize_axis_aware(R.hnormal), R.qd), 0.0f, 1.0f);
+        if (!block_hit) {
+            float dist = length(lpos(l) - R.hpos);
+            R.direct = R.direct + ((lcol(l) * lambert) * l.intensity) / dist;
+            R.visible++;
         } else {
-            // a light sphere is the nearest hit (rare): redo the pre-test for its normal
-            int which;
-            light_pretest(P, R.mo, R.qd, &which, &n);
-            R.hblock = -1;
-        }
-        v3 normal = normalize(n);
-        R.hpos = (R.mo + R.qd * closest) + normal * 0.001f;
-        R.hnormal = normal;
-        R.direct = V3(0, 0, 0);
-        R.visible = 0;
-        if (P.n_lights == 0) end_bounce = true;
-        else R.phase = 1;
-    } else {
-        // shadow feeler to light phase-1 (probe_pass.comp:186-207)
-        const Light& l = P.lights[R.phase - 1];
-        if (hit) {
-            float lambert = gclamp(dot(normalize(R.hnormal), R.qd), 0.0f, 1.0f);
-            if (type == 2) {
-                float dist = length(lpos(l) - R.hpos);
-                R.direct = R.direct + ((lcol(l) * lambert) * l.intensity) / dist;
-                R.visible++;
-            } else {
-                v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
-                end_bounce = true;
-                result = (base * 0.2f) * lambert;
-            }
-        }
-        if (!end_bounce) {
-            R.phase++;
-            if (R.phase > P.n_lights) {
-                end_bounce = true;
-                if (R.visible != 0) {
-                    v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
-                    result = (base * R.direct) / (float)R.visible;
-                }
-            }
+            // blocked by a voxel: ambient term, remaining lights are skipped
+            v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
+            R.color = R.color + (base * 0.2f) * lambert;
+            R.mode = WF_SCATTER;
+            return;
         }
     }
-    if (end_bounce) {
-        // probe_pass.comp:286-292: accumulate, pick the next bounce direction
+    R.phase++;
+    if (R.phase > P.n_lights) {
+        v3 result = V3(0, 0, 0);
+        if (R.visible != 0) {
+            v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
+            result = (base * R.direct) / (float)R.visible;
+        }
         R.color = R.color + result;
-        o = R.hpos + R.hnormal * 0.0001f;
-        d = hemisphere_dir(R.hnormal, R.rng);
-        R.bounce++;
-        if (R.bounce >= P.max_bounces) {
-            wf_finish_ray(P, R);
-            return true;
-        }
-        R.phase = 0;
-    } else {
-        o = R.hpos;
-        d = normalize(lpos(P.lights[R.phase - 1]) - R.hpos);
+        R.mode = WF_SCATTER;
+        return;
     }
-    return false;
+    wf_aim_feeler(P, R);
+}
+
+// WF_SCATTER: the bounce's direct term is in; pick the next bounce direction
+// (probe_pass.comp:292) or finish after max_bounces.
+DDGI_HD void wf_scatter(const FrameParams& P, WfRay& R)
+{
+    v3 o = R.hpos + R.hnormal * 0.0001f;
+    v3 d = hemisphere_dir(R.hnormal, R.rng);
+    R.bounce++;
+    if (R.bounce >= P.max_bounces) {
+        wf_finish_ray(P, R);
+        return;
+    }
+    R.phase = 0;
+    R.mo = o;
+    R.qd = d;
+    R.mode = WF_QUERY;
 }
 
 // Scalar driver (tests/hostsim): the state machine stepped for a single ray.
@@ -248,20 +297,16 @@ DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction,
                                   uint32_t& lookups)
 {
     WfRay R;
-    wf_init(R, ray_index);
-    if (P.max_bounces <= 0) {
-        wf_finish_ray(P, R);
-        return R.color;
-    }
-    wf_begin_query(P, R, origin, direction);
-    for (;;) {
-        if (R.mode == WF_MARCH) {
-            wf_step(P, R);
-            continue;
+    wf_init(R, origin, direction, ray_index);
+    if (P.max_bounces <= 0) wf_finish_ray(P, R);
+    while (R.mode != WF_FETCH) {
+        switch (R.mode) {
+            case WF_MARCH: wf_step(P, R); break;
+            case WF_QUERY: wf_begin_query(P, R); break;
+            case WF_BOUNCE_HIT: wf_resolve_bounce(P, R); break;
+            case WF_FEELER_HIT: wf_resolve_feeler(P, R); break;
+            default: wf_scatter(P, R); break;
         }
-        v3 o, d;
-        if (wf_resolve(P, R, o, d)) break;
-        wf_begin_query(P, R, o, d);
     }
     lookups += R.lookups;
     return R.color;

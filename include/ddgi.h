@@ -187,9 +187,9 @@ DDGI_API int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst
 /* Kernel variant: 0 = one thread per ray, reference loop order; 1 = regrouped
    state-machine kernel (default).  Results are identical. */
 DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
-/* Regrouping threshold of variant 1: a warp keeps stepping its marches while at least
-   march_min/32 of its live lanes are marching (1..32, default 16).  Results do not
-   depend on it. */
+/* Scheduling knob of variant 1: a warp keeps stepping its marches while at least
+   march_min/32 of the lanes that hold a ray are marching (1..32, default 14).  Results do
+   not depend on it. */
 DDGI_API int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min);
 /* Number of kernel launches issued by this context so far. */
 DDGI_API uint64_t ddgi_launch_count(const ddgi_ctx* ctx);
