@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddgi_b200.so")
+# DDGI_LIB overrides the library path (A/B builds while tuning); the default is the in-tree build
+LIB_PATH = os.environ.get("DDGI_LIB") or os.path.join(_HERE, "libddgi_b200.so")
 
 OK, E_INVALID, E_CUDA, E_STATE = 0, -1, -2, -3
 FMT_RGBA8, FMT_F32 = 0, 1

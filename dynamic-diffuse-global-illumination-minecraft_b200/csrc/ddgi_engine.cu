@@ -35,7 +35,7 @@ struct ddgi_ctx {
     // voxel field
     int vdim[3] = {0, 0, 0}, vorg[3] = {0, 0, 0}, borg[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
     uint8_t* d_types = nullptr;
-    unsigned long long* d_occ = nullptr;
+    uint32_t* d_occ = nullptr;  // one word per 4x4x2 brick
     float* d_palette = nullptr;
 
     // rays
@@ -213,12 +213,13 @@ static int alloc_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t orig
         ctx->vdim[a] = dims[a];
         ctx->vorg[a] = origin[a];
         ctx->borg[a] = origin[a] & ~3;  // two's complement: rounds toward -inf to a multiple of 4
-        ctx->nb[a] = (origin[a] + dims[a] - ctx->borg[a] + 3) / 4;
+        int cells = a == 2 ? 2 : 4;  // bricks are 4x4x2 cells
+        ctx->nb[a] = (origin[a] + dims[a] - ctx->borg[a] + cells - 1) / cells;
     }
     size_t n = (size_t)dims[0] * dims[1] * dims[2];
     size_t nbk = (size_t)ctx->nb[0] * ctx->nb[1] * ctx->nb[2];
     CU(cudaMalloc(&ctx->d_types, n));
-    CU(cudaMalloc(&ctx->d_occ, nbk * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_occ, nbk * sizeof(uint32_t)));
     if (!ctx->d_palette) CU(cudaMalloc(&ctx->d_palette, 256 * 3 * sizeof(float)));
     float pal[256 * 3];
     if (palette) memcpy(pal, palette, sizeof(pal));

@@ -41,6 +41,6 @@ cudaError_t launch_bake_scene(int scene, const int dims[3], const int org[3], ui
 cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permille, uint32_t seed,
                                   uint8_t* types, cudaStream_t s, int* launches);
 cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const uint8_t* types,
-                                   unsigned long long* occ, cudaStream_t s, int* launches);
+                                   uint32_t* occ, cudaStream_t s, int* launches);
 
 }  // namespace ddgi

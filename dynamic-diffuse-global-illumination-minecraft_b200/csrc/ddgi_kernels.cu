@@ -88,8 +88,11 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
 constexpr int kWfThreads = 128;
+#ifndef DDGI_WF_MIN_BLOCKS
+#define DDGI_WF_MIN_BLOCKS 8  // 64 registers / thread: 32 resident warps per SM
+#endif
 
-__global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __grid_constant__ FrameParams P,
+__global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_wavefront(const __grid_constant__ FrameParams P,
                                                                      const __grid_constant__ ProbeJob J,
                                                                      uint32_t* __restrict__ next_ray,
                                                                      int march_min)
@@ -112,22 +115,12 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
         while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) * 32 >= enough) {
             if (R.mode == WF_MARCH) wf_step(P, R);
         }
-        // ---- otherwise run the fullest of the other states (ties: the later stage) ----
-        int best = -1, best_n = 0;
-        const int same = __shfl_sync(full, R.mode, 0);
-        if (__all_sync(full, R.mode == same)) {
-            best = same;  // coherent warp (e.g. every probe ray of a probe buried in rock)
-        } else {
-#pragma unroll
-            for (int s = WF_QUERY; s < WF_NUM_STATES; s++) {
-                int n = __popc(__ballot_sync(full, R.mode == s));
-                if (n >= best_n && n > 0) {
-                    best_n = n;
-                    best = s;
-                }
-            }
-        }
-        if (best <= WF_MARCH) continue;  // only marching lanes are left: lower the bar next pass
+        // ---- otherwise run the fullest of the other states (ties: the later stage):
+        //      one MATCH gives every lane the size of its own group, one REDUX the winner ----
+        const unsigned peers = __match_any_sync(full, R.mode);
+        const unsigned key = (R.mode != WF_MARCH && R.mode != WF_IDLE) ? ((unsigned)__popc(peers) << 3) | (unsigned)R.mode : 0u;
+        const int best = (int)(__reduce_max_sync(full, key) & 7u);
+        if (best == WF_MARCH) continue;  // only marching lanes are left: lower the bar next pass
 
         if (best == WF_QUERY) {
             if (R.mode == WF_QUERY) wf_begin_query(P, R);
@@ -137,6 +130,8 @@ __global__ void __launch_bounds__(kWfThreads) probe_update_wavefront(const __gri
             if (R.mode == WF_FEELER_HIT) wf_resolve_feeler(P, R);
         } else if (best == WF_SCATTER) {
             if (R.mode == WF_SCATTER) wf_scatter(P, R);
+        } else if (best == WF_MARCH_SLOW) {
+            if (R.mode == WF_MARCH_SLOW) wf_step_literal(P, R);
         } else {
             // WF_FETCH: store the finished ray, take the next one
             bool need = R.mode == WF_FETCH;
@@ -251,24 +246,24 @@ __global__ void bake_synthetic_kernel(int dx, int dy, int dz, int permille, uint
     }
 }
 
-// One thread per 4x4x4 brick: gathers 64 type bytes into the occupancy word.
+// One thread per 4x4x2 brick: gathers 32 type bytes into the occupancy word.
 __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, int sz, int nbx, int nby, int nbz,
-                                       const uint8_t* types, unsigned long long* occ)
+                                       const uint8_t* types, uint32_t* occ)
 {
     size_t nb = (size_t)nbx * nby * nbz;
     for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
         int bx = (int)(b % nbx);
         int by = (int)((b / nbx) % nby);
         int bz = (int)(b / ((size_t)nbx * nby));
-        unsigned long long w = 0ull;
-        for (int z = 0; z < 4; z++)
+        uint32_t w = 0u;
+        for (int z = 0; z < 2; z++)
             for (int y = 0; y < 4; y++)
                 for (int x = 0; x < 4; x++) {
                     // grid cell of this brick cell: bricks start (sx,sy,sz) cells before the grid
-                    int gx = bx * 4 + x - sx, gy = by * 4 + y - sy, gz = bz * 4 + z - sz;
+                    int gx = bx * 4 + x - sx, gy = by * 4 + y - sy, gz = bz * 2 + z - sz;
                     if (gx >= 0 && gy >= 0 && gz >= 0 && gx < dx && gy < dy && gz < dz &&
                         types[((size_t)gz * dy + gy) * dx + gx] != 0)
-                        w |= 1ull << (x | (y << 2) | (z << 4));
+                        w |= 1u << (x | (y << 2) | (z << 4));
                 }
         occ[b] = w;
     }
@@ -341,7 +336,7 @@ cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permi
 }
 
 cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const uint8_t* types,
-                                   unsigned long long* occ, cudaStream_t s, int* launches)
+                                   uint32_t* occ, cudaStream_t s, int* launches)
 {
     size_t n = (size_t)nb[0] * nb[1] * nb[2];
     build_occupancy_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], shift[0], shift[1], shift[2], nb[0], nb[1], nb[2],

@@ -3,11 +3,10 @@
 // scene bakers that evaluate that procedural function once per voxel.
 //
 // HBM layout (DESIGN.md "Data layout"):
-//   occ   : one uint64 per 4x4x4 voxel brick, bit (x&3)|(y&3)<<2|(z&3)<<4 set = solid,
-//           x/y/z = voxel id mod 4 (bricks are aligned to voxel ids that are multiples
-//           of 4).  Brick index ((bz*nby)+by)*nbx+bx.  512^3 voxels -> 16 MiB:
-//           L2-resident, and a marching ray re-uses one 8-byte word (kept in registers)
-//           for every step it spends in a brick.
+//   occ   : one uint32 per 4x4x2 voxel brick, bit (x&3)|(y&3)<<2|(z&1)<<4 set = solid,
+//           x/y/z = voxel id relative to `borg` (a multiple of 4 per axis).  Brick index
+//           ((bz*nby)+by)*nbx+bx, x fastest: a 32-byte sector holds 32x4x2 voxels.
+//           512^3 voxels -> 16 MiB, L1/L2 resident.
 //   types : one uint8 block type per voxel, linear x-fastest; read only on a hit.
 //   palette: 256 x rgb fp32 albedo by block type (flat-colour variant, README.md:266).
 // Voxel id c (an integer-valued float, c = ceil(position)) covers (c-1, c] per axis;
@@ -18,13 +17,13 @@
 namespace ddgi {
 
 struct SceneView {
-    const unsigned long long* occ;
+    const uint32_t* occ;
     const uint8_t* types;
     const float* palette;
     int vorg[3];
     int vdim[3];
     int borg[3];  // voxel id of brick (0,0,0)'s first cell: vorg rounded down to a multiple of 4
-    int nb[3];    // bricks per axis
+    int nb[3];    // bricks per axis (4 cells in x and y, 2 in z)
     float lo[3];  // (float)vorg
     float hi[3];  // (float)(vorg + vdim - 1)
 };
@@ -49,24 +48,28 @@ DDGI_HD int float_bits(float x)
 constexpr int kCellBias = 0x4B400000;
 DDGI_HD int cell_bits(float c) { return float_bits(c + 12582912.0f); }
 
-// Occupancy test of the cell with biased integer coordinates (kx,ky,kz) = cell_bits(c)
-// per axis: the 32-bit half (z&2 selects it) of the brick word, 0 for bricks outside the
-// grid, and the bit inside that half.
-DDGI_HD uint32_t brick_half(const SceneView& S, int kx, int ky, int kz)
+// word >> (s mod 32): SHF.R.W on the device, so callers need not mask the shift count
+DDGI_HD uint32_t shr_wrap(uint32_t w, int s)
 {
-    int bx = (kx - (kCellBias + S.borg[0])) >> 2;
-    int by = (ky - (kCellBias + S.borg[1])) >> 2;
-    int bz = (kz - (kCellBias + S.borg[2])) >> 2;
-    if ((unsigned)bx >= (unsigned)S.nb[0] || (unsigned)by >= (unsigned)S.nb[1] || (unsigned)bz >= (unsigned)S.nb[2])
-        return 0u;
-    unsigned idx = ((unsigned)bz * (unsigned)S.nb[1] + (unsigned)by) * (unsigned)S.nb[0] + (unsigned)bx;
-    return reinterpret_cast<const uint32_t*>(S.occ)[2u * idx + (((unsigned)kz >> 1) & 1u)];
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(w, 0u, (unsigned)s);
+#else
+    return w >> ((unsigned)s & 31u);
+#endif
 }
+
+// Occupancy test of the cell with biased integer coordinates (kx,ky,kz) = cell_bits(c)
+// per axis; bricks outside the grid read as empty.
 DDGI_HD bool cell_solid(const SceneView& S, int kx, int ky, int kz)
 {
-    uint32_t half = brick_half(S, kx, ky, kz);
-    int bit = (kx & 3) | ((ky & 3) << 2) | ((kz & 1) << 4);
-    return (half >> bit) & 1u;
+    int gx = kx - (kCellBias + S.borg[0]);
+    int gy = ky - (kCellBias + S.borg[1]);
+    int gz = kz - (kCellBias + S.borg[2]);
+    unsigned bx = (unsigned)(gx >> 2), by = (unsigned)(gy >> 2), bz = (unsigned)(gz >> 1);
+    if (bx >= (unsigned)S.nb[0] || by >= (unsigned)S.nb[1] || bz >= (unsigned)S.nb[2]) return false;
+    uint32_t word = S.occ[(bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx];
+    // bit (gx&3) | (gy&3)<<2 | (gz&1)<<4; the higher bits of gz fall off the 5-bit shift count
+    return shr_wrap(word, (gx & 3) + ((gy & 3) << 2) + (gz << 4)) & 1u;
 }
 
 // Block type of an occupied cell (only called after its occupancy bit tested set).

@@ -10,6 +10,7 @@
 //
 //   WF_QUERY       wf_begin_query     normalise direction, reciprocals, light-sphere pre-test
 //   WF_MARCH       wf_step            one DDA advance + voxel test (repeated)
+//   WF_MARCH_SLOW  wf_step_literal    the same for irregular directions, literal arithmetic
 //   WF_BOUNCE_HIT  wf_resolve_bounce  the bounce ray's march ended: hit record, first feeler
 //   WF_FEELER_HIT  wf_resolve_feeler  a shadow feeler's march ended: direct term / next feeler
 //   WF_SCATTER     wf_scatter         bounce finished: cosine-weighted direction for the next
@@ -27,8 +28,6 @@
 //     the second, for d < 0 the other way round (f in [0,1]); zero / NaN / tiny
 //     components take the literal two-division form (WfRay::slow).
 //   * that division and x/0.1f use the FMA-corrected reciprocal of ddgi_fastmath.cuh.
-//   * floor(p) is ceil(p)-1 unless p is an integer; ceil(p) is needed anyway for the
-//     voxel id, so a step costs three FRND instead of six.
 //   * the voxel test reads one bit of the 4x4x4-brick occupancy word (16 MiB for 512^3
 //     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
@@ -47,21 +46,22 @@ enum : int {
     WF_FEELER_HIT = 3,
     WF_SCATTER = 4,
     WF_FETCH = 5,
-    WF_IDLE = 6,
-    WF_NUM_STATES = 6  // schedulable states (IDLE excluded)
+    WF_MARCH_SLOW = 6,  // march with a zero / NaN / tiny direction component: literal arithmetic
+    WF_IDLE = 7,
+    WF_NUM_STATES = 7  // schedulable states (IDLE excluded)
 };
 
 struct WfRay {
     // current march
     v3 mo;   // query origin
     v3 md;   // normalize(query direction)
-    v3 inv;  // 1 / md (valid when !slow)
+    v3 inv;  // 1 / md (WF_MARCH only)
+    v3 sel;  // 1 where md > 0 else 0: numerator of the larger quotient is sel - fract(p)
     v3 p;    // position after the last advance
-    v3 c;    // ceil(p)
     float t; // march parameter; +INF once the march has ended without a hit
     int steps;
     int mode;
-    int slow;  // a direction component is zero, NaN or tiny: literal step arithmetic
+    int hit_mode;  // state a finished march hands over to: WF_BOUNCE_HIT or WF_FEELER_HIT
     // current query
     v3 qd;  // query direction as given (positions are origin + qd * t)
     float light_t;
@@ -124,15 +124,17 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R)
     R.md = normalize(R.qd);
     // fast-step preconditions (ddgi_fastmath.cuh): regular direction components, and no
     // origin component in (0, 2^-70) so that a position is either 0 or >= 2^-98 in magnitude
-    R.slow = (int)!(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) |
-             (int)(tiny_nonzero(origin.x) || tiny_nonzero(origin.y) || tiny_nonzero(origin.z));
-    R.inv = R.slow ? V3(0, 0, 0) : V3(1.0f / R.md.x, 1.0f / R.md.y, 1.0f / R.md.z);
+    // and |origin| < 2^20 so that |p| stays below 2^22 over 125 cells (floor_small / add_round_up)
+    bool slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) ||
+                !(regular_origin(origin.x) && regular_origin(origin.y) && regular_origin(origin.z));
+    R.inv = slow ? V3(0, 0, 0) : V3(1.0f / R.md.x, 1.0f / R.md.y, 1.0f / R.md.z);
+    R.sel = V3(R.md.x > 0 ? 1.0f : 0.0f, R.md.y > 0 ? 1.0f : 0.0f, R.md.z > 0 ? 1.0f : 0.0f);
     R.p = origin;
-    R.c = V3(ceilf(origin.x), ceilf(origin.y), ceilf(origin.z));
     R.t = 0.0f;
     R.steps = 0;
     R.light_t = light_pretest(P, origin, R.qd, &R.light_i, nullptr);
-    R.mode = WF_MARCH;
+    R.hit_mode = R.phase == 0 ? WF_BOUNCE_HIT : WF_FEELER_HIT;
+    R.mode = slow ? WF_MARCH_SLOW : WF_MARCH;
 }
 
 // The ray is complete: final colour, then WF_FETCH stores it.
@@ -159,38 +161,49 @@ DDGI_HD void wf_init(WfRay& R, v3 origin, v3 direction, uint32_t ray_index)
     R.mode = WF_QUERY;
 }
 
-// WF_MARCH: one DDA advance and voxel test (the body of the reference's 125-iteration loop).
-DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
+// Voxel test at the new position, shared by both march flavours.
+DDGI_HD void wf_test_cell(const FrameParams& P, WfRay& R, bool small_coords)
 {
-    // ---- advance: t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 ----
-    if (!R.slow) {
-        v3 fl = V3(R.c.x - 1.0f, R.c.y - 1.0f, R.c.z - 1.0f);  // floor(p) unless p is an integer
-        if (DDGI_UNLIKELY(R.p.x == R.c.x || R.p.y == R.c.y || R.p.z == R.c.z))
-            fl = V3(floorf(R.p.x), floorf(R.p.y), floorf(R.p.z));
-        v3 f = R.p - fl;
-        // numerator of the larger quotient: 1-f for d > 0, -f for d < 0 (a zero numerator
-        // may come out as +0 where the reference has -0: min(..)+1e-4 is the same)
-        float nx = (R.md.x > 0 ? 1.0f : 0.0f) - f.x;
-        float ny = (R.md.y > 0 ? 1.0f : 0.0f) - f.y;
-        float nz = (R.md.z > 0 ? 1.0f : 0.0f) - f.z;
-        float tx = div_markstein(nx, R.md.x, R.inv.x);
-        float ty = div_markstein(ny, R.md.y, R.inv.y);
-        float tz = div_markstein(nz, R.md.z, R.inv.z);
-        float step = gmin(gmin(tx, ty), tz) + 0.0001f;
-        R.t += step;
-        R.p = R.mo + R.md * R.t;
-    } else {
-        march_advance(R.mo, R.md, R.t, R.p);
-    }
-    R.c = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
     R.steps++;
-    // ---- voxel test: one bit of the brick occupancy word ----
-    if (cell_solid(P.scene, cell_bits(R.c.x), cell_bits(R.c.y), cell_bits(R.c.z))) {
-        R.mode = R.phase == 0 ? WF_BOUNCE_HIT : WF_FEELER_HIT;
+    int kx, ky, kz;
+    if (small_coords) {
+        // |p| < 2^22: p + 1.5*2^23 rounded up IS ceil(p) + 1.5*2^23 (one directed-rounding add)
+        kx = float_bits(add_round_up(R.p.x, kCellMagic));
+        ky = float_bits(add_round_up(R.p.y, kCellMagic));
+        kz = float_bits(add_round_up(R.p.z, kCellMagic));
+    } else {
+        kx = cell_bits(ceilf(R.p.x));
+        ky = cell_bits(ceilf(R.p.y));
+        kz = cell_bits(ceilf(R.p.z));
+    }
+    if (cell_solid(P.scene, kx, ky, kz)) {
+        R.mode = R.hit_mode;
     } else if (R.steps >= kMarchSteps) {
         R.t = inf_f();  // no block within 125 cells
-        R.mode = R.phase == 0 ? WF_BOUNCE_HIT : WF_FEELER_HIT;
+        R.mode = R.hit_mode;
     }
+}
+
+// WF_MARCH: one DDA advance and voxel test (the body of the reference's 125-iteration
+// loop): t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 with f = fract(p).  The larger
+// quotient has numerator 1-f for d > 0 and -f for d < 0 (a zero numerator may come out as
+// +0 where the reference has -0: min(..)+1e-4 is the same).
+// floor(p) for |p| < 2^22 comes from two full-rate adds (no conversion-pipe FRND).
+DDGI_HD void wf_step(const FrameParams& P, WfRay& R)
+{
+    float tx = div_markstein(R.sel.x - (R.p.x - floor_small(R.p.x)), R.md.x, R.inv.x);
+    float ty = div_markstein(R.sel.y - (R.p.y - floor_small(R.p.y)), R.md.y, R.inv.y);
+    float tz = div_markstein(R.sel.z - (R.p.z - floor_small(R.p.z)), R.md.z, R.inv.z);
+    R.t += gmin(gmin(tx, ty), tz) + 0.0001f;
+    R.p = R.mo + R.md * R.t;
+    wf_test_cell(P, R, true);
+}
+
+// WF_MARCH_SLOW: the literal two-division form.
+DDGI_HD void wf_step_literal(const FrameParams& P, WfRay& R)
+{
+    march_advance(R.mo, R.md, R.t, R.p);
+    wf_test_cell(P, R, false);
 }
 
 // Arms the shadow feeler to light R.phase-1 from the current bounce hit.
@@ -217,8 +230,9 @@ DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
     if (block_hit) {
         // face_normal is axis-aligned (or zero for a NaN position): both normalize() calls
         // of the reference (grid_march :1088, intersect_scene :1294) are identities on it
-        normal = normalize_axis_aware(normalize_axis_aware(face_normal(R.p, R.c)));
-        R.hblock = scene_type_at(P.scene, R.c);
+        v3 cell = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
+        normal = normalize_axis_aware(normalize_axis_aware(face_normal(R.p, cell)));
+        R.hblock = scene_type_at(P.scene, cell);
     } else {
         // a light sphere is the nearest hit (rare): redo the pre-test for its normal
         int which;
@@ -302,6 +316,7 @@ DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction,
     while (R.mode != WF_FETCH) {
         switch (R.mode) {
             case WF_MARCH: wf_step(P, R); break;
+            case WF_MARCH_SLOW: wf_step_literal(P, R); break;
             case WF_QUERY: wf_begin_query(P, R); break;
             case WF_BOUNCE_HIT: wf_resolve_bounce(P, R); break;
             case WF_FEELER_HIT: wf_resolve_feeler(P, R); break;

@@ -33,7 +33,7 @@ struct SimParams {
 
 struct Built {
     FrameParams P;
-    std::vector<unsigned long long> occ;
+    std::vector<uint32_t> occ;  // one word per 4x4x2 brick
 };
 
 static void build(const SimParams* S, const float* cam, Built* B)
@@ -44,7 +44,8 @@ static void build(const SimParams* S, const float* cam, Built* B)
     for (int a = 0; a < 3; a++) {
         int borg = S->vorg[a] & ~3;
         sh[a] = S->vorg[a] - borg;
-        nb[a] = (S->vorg[a] + S->vdim[a] - borg + 3) / 4;
+        int cells = a == 2 ? 2 : 4;
+        nb[a] = (S->vorg[a] + S->vdim[a] - borg + cells - 1) / cells;
         P.scene.vorg[a] = S->vorg[a];
         P.scene.vdim[a] = S->vdim[a];
         P.scene.borg[a] = borg;
@@ -54,14 +55,14 @@ static void build(const SimParams* S, const float* cam, Built* B)
         P.probe_count[a] = S->probe_count[a];
         P.field_origin[a] = S->field_origin[a];
     }
-    B->occ.assign((size_t)nb[0] * nb[1] * nb[2], 0ull);
+    B->occ.assign((size_t)nb[0] * nb[1] * nb[2], 0u);
     for (int z = 0; z < S->vdim[2]; z++)
         for (int y = 0; y < S->vdim[1]; y++)
             for (int x = 0; x < S->vdim[0]; x++)
                 if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x]) {
                     int bx = x + sh[0], by = y + sh[1], bz = z + sh[2];
-                    B->occ[((size_t)(bz >> 2) * nb[1] + (by >> 2)) * nb[0] + (bx >> 2)] |=
-                        1ull << ((bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4));
+                    B->occ[((size_t)(bz >> 1) * nb[1] + (by >> 2)) * nb[0] + (bx >> 2)] |=
+                        1u << ((bx & 3) | ((by & 3) << 2) | ((bz & 1) << 4));
                 }
     P.scene.occ = B->occ.data();
     P.scene.types = S->vox;

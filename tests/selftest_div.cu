@@ -51,6 +51,12 @@ __global__ void markstein_random(uint64_t per_thread, unsigned long long* bad, f
     unsigned long long local = 0;
     for (uint64_t n = 0; n < per_thread; n++) {
         uint32_t r1 = mix(s), r2 = mix(s), r3 = mix(s);
+        // every 4th pair: adversarial significands (all ones / one / near one) for both
+        if ((n & 3) == 3) {
+            uint32_t pat[4] = {0x7fffffu, 0x000000u, 0x000001u, 0x7ffffeu};
+            r1 = (r1 & 0xff800000u) | (pat[(r3 >> 22) & 3] ^ ((r3 >> 26) & 3));
+            r2 = (r2 & 0xff800000u) | (pat[(r3 >> 24) & 3] ^ ((r3 >> 28) & 3));
+        }
         // a: sign | exponent in [27, 127] (2^-100 .. 1) biased towards [2^-24, 1] | mantissa
         uint32_t ea = (r3 & 7) ? 103 + (r3 >> 3) % 25 : 27 + (r3 >> 3) % 101;
         uint32_t abits = (r1 & 0x807fffffu) | (ea << 23);
@@ -62,7 +68,8 @@ __global__ void markstein_random(uint64_t per_thread, unsigned long long* bad, f
         float inv = 1.0f / d;
         float want = a / d;
         float got = div_markstein(a, d, inv);
-        if (!same(want, got)) {
+        float got2 = div_markstein2(a, d, inv);
+        if (!same(want, got) || !same(want, got2)) {
             if (!local) { ex[0] = a; ex[1] = d; }
             local++;
         }
