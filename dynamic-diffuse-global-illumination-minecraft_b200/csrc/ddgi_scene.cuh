@@ -66,10 +66,12 @@ DDGI_HD bool cell_solid(const SceneView& S, int kx, int ky, int kz)
     int gy = ky - (kCellBias + S.borg[1]);
     int gz = kz - (kCellBias + S.borg[2]);
     unsigned bx = (unsigned)(gx >> 2), by = (unsigned)(gy >> 2), bz = (unsigned)(gz >> 1);
-    if (bx >= (unsigned)S.nb[0] || by >= (unsigned)S.nb[1] || bz >= (unsigned)S.nb[2]) return false;
-    uint32_t word = S.occ[(bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx];
+    // out-of-grid bricks read word 0 and are masked off: no branch, no divergence
+    bool inside = (bx < (unsigned)S.nb[0]) & (by < (unsigned)S.nb[1]) & (bz < (unsigned)S.nb[2]);
+    unsigned idx = inside ? (bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx : 0u;
+    uint32_t word = S.occ[idx];
     // bit (gx&3) | (gy&3)<<2 | (gz&1)<<4; the higher bits of gz fall off the 5-bit shift count
-    return shr_wrap(word, (gx & 3) + ((gy & 3) << 2) + (gz << 4)) & 1u;
+    return inside & (bool)(shr_wrap(word, (gx & 3) + ((gy & 3) << 2) + (gz << 4)) & 1u);
 }
 
 // Block type of an occupied cell (only called after its occupancy bit tested set).

@@ -8,7 +8,7 @@
 // loops a warp serialises every divergent branch of that chain.  Here each lane carries
 // its ray as a WfRay and is always in exactly one state:
 //
-//   WF_QUERY       wf_begin_query     normalise direction, reciprocals, light-sphere pre-test
+//   WF_QUERY       wf_begin_query     normalise direction, reciprocals
 //   WF_MARCH       wf_step            one DDA advance + voxel test (repeated)
 //   WF_MARCH_SLOW  wf_step_literal    the same for irregular directions, literal arithmetic
 //   WF_BOUNCE_HIT  wf_resolve_bounce  the bounce ray's march ended: hit record, first feeler
@@ -31,7 +31,8 @@
 //   * the voxel test reads one bit of the 4x4x4-brick occupancy word (16 MiB for 512^3
 //     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
-//     (intersection.glsl:100-113), so the two root divisions are skipped for it.
+//     (intersection.glsl:100-113), so the two root divisions are skipped for it; and the
+//     light spheres are tested after the march, only those that could beat the block hit.
 //   * normalize() of an axis-aligned unit vector is the identity (1/sqrt(1) = 1).
 #pragma once
 #include "ddgi_fastmath.cuh"
@@ -64,8 +65,6 @@ struct WfRay {
     int hit_mode;  // state a finished march hands over to: WF_BOUNCE_HIT or WF_FEELER_HIT
     // current query
     v3 qd;  // query direction as given (positions are origin + qd * t)
-    float light_t;
-    int light_i;  // nearest light sphere, -1 none
     // path
     int bounce;
     int phase;  // 0: the bounce ray itself; i >= 1: shadow feeler to light i-1
@@ -86,17 +85,37 @@ DDGI_HD v3 normalize_axis_aware(v3 v)
     return normalize(v);
 }
 
-// Light-sphere pre-test of a query: nearest t over all lights and which light, exactly
-// as the loop of intersect_scene (intersection.glsl:1262-1279) evaluates it.  `normal`
-// (optional) receives the un-normalised sphere normal of the winning light.
-DDGI_HD float light_pretest(const FrameParams& P, v3 origin, v3 direction, int* which, v3* normal)
+// Light-sphere test of a query: nearest t over all lights, exactly as the loop of
+// intersect_scene (intersection.glsl:1262-1279) evaluates it, except that it runs AFTER
+// the march and skips lights that cannot beat the block hit at t_block:
+// a root of |w + dir*t| = 0.1 (w = origin - light) has t*|dir| >= |w| - 0.1, and the
+// reference's fp32 evaluation of it is within 1e-5 of that for |w| >= 0.101 (no
+// cancellation: B^2/(A*C) <= 50), so with |w| > 1.01*t_block*|dir| + 0.101 every root it
+// could report is > t_block: the block wins whatever the light's t is.  Skipping a light
+// only widens the (0, closest) window of later ones by values > t_block, which lose
+// to the block as well; with no block hit (t_block = INF) nothing is skipped.
+// `normal` (optional) receives the un-normalised sphere normal of the winning light.
+DDGI_HD float light_test(const FrameParams& P, v3 origin, v3 direction, float t_block, int* which, v3* normal)
 {
     float closest = inf_f();
     *which = -1;
-    v3 d = div_tenth(direction);
-    float A = dot(d, d);
+    float reach2 = inf_f();
+    if (t_block < inf_f()) {
+        float reach = (t_block * sqrtf(dot(direction, direction))) * 1.01f + 0.101f;
+        reach2 = reach * reach;
+    }
+    bool scaled = false;
+    v3 d = V3(0, 0, 0);
+    float A = 0.0f;
     for (int i = 0; i < P.n_lights; i++) {
-        v3 o = div_tenth(origin - lpos(P.lights[i]));
+        v3 w = origin - lpos(P.lights[i]);
+        if (dot(w, w) > reach2) continue;
+        if (!scaled) {
+            d = div_tenth(direction);
+            A = dot(d, d);
+            scaled = true;
+        }
+        v3 o = div_tenth(w);
         float B = -dot(d, o);
         float C = dot(o, o) - 1.0f;
         float D = B * B - A * C;
@@ -116,8 +135,8 @@ DDGI_HD float light_pretest(const FrameParams& P, v3 origin, v3 direction, int* 
     return closest;
 }
 
-// WF_QUERY: starts the nearest-hit query (R.mo, R.qd): light spheres first (they do not
-// depend on the march), then arm the march.
+// WF_QUERY: starts the nearest-hit query (R.mo, R.qd): arms the march.  The light spheres
+// are tested when the march has ended (light_test).
 DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R)
 {
     v3 origin = R.mo;
@@ -127,12 +146,11 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R)
     // and |origin| < 2^20 so that |p| stays below 2^22 over 125 cells (floor_small / add_round_up)
     bool slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) ||
                 !(regular_origin(origin.x) && regular_origin(origin.y) && regular_origin(origin.z));
-    R.inv = slow ? V3(0, 0, 0) : V3(1.0f / R.md.x, 1.0f / R.md.y, 1.0f / R.md.z);
+    R.inv = slow ? V3(0, 0, 0) : V3(rcp_exact(R.md.x), rcp_exact(R.md.y), rcp_exact(R.md.z));
     R.sel = V3(R.md.x > 0 ? 1.0f : 0.0f, R.md.y > 0 ? 1.0f : 0.0f, R.md.z > 0 ? 1.0f : 0.0f);
     R.p = origin;
     R.t = 0.0f;
     R.steps = 0;
-    R.light_t = light_pretest(P, origin, R.qd, &R.light_i, nullptr);
     R.hit_mode = R.phase == 0 ? WF_BOUNCE_HIT : WF_FEELER_HIT;
     R.mode = slow ? WF_MARCH_SLOW : WF_MARCH;
 }
@@ -219,7 +237,8 @@ DDGI_HD void wf_aim_feeler(const FrameParams& P, WfRay& R)
 DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
 {
     R.lookups += (uint32_t)R.steps;
-    float closest = R.light_t;
+    int which;
+    float closest = light_test(P, R.mo, R.qd, R.t, &which, nullptr);
     bool block_hit = R.t < closest;
     if (block_hit) closest = R.t;
     if (!(closest < inf_f())) {
@@ -234,10 +253,9 @@ DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
         normal = normalize_axis_aware(normalize_axis_aware(face_normal(R.p, cell)));
         R.hblock = scene_type_at(P.scene, cell);
     } else {
-        // a light sphere is the nearest hit (rare): redo the pre-test for its normal
-        int which;
+        // a light sphere is the nearest hit (rare): redo the test for its normal
         v3 n;
-        light_pretest(P, R.mo, R.qd, &which, &n);
+        light_test(P, R.mo, R.qd, inf_f(), &which, &n);
         normal = normalize(n);
         R.hblock = -1;
     }
@@ -257,7 +275,8 @@ DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
 DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
 {
     R.lookups += (uint32_t)R.steps;
-    float closest = R.light_t;
+    int which;
+    float closest = light_test(P, R.mo, R.qd, R.t, &which, nullptr);
     bool block_hit = R.t < closest;
     if (block_hit) closest = R.t;
     const Light& l = P.lights[R.phase - 1];
