@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
 constexpr int kWfThreads = 128;
+#ifndef DDGI_WF_UNROLL
+#define DDGI_WF_UNROLL 1  // march steps per lane-count check
+#endif
 #ifndef DDGI_WF_MIN_BLOCKS
 #define DDGI_WF_MIN_BLOCKS 8  // 64 registers / thread: 32 resident warps per SM
 #endif
@@ -113,7 +116,9 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         if (n_live == 0) break;
         const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // in 1/32 lanes, >= 1 lane
         while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) * 32 >= enough) {
-            if (R.mode == WF_MARCH) wf_step(P, R);
+#pragma unroll
+            for (int u = 0; u < DDGI_WF_UNROLL; u++)
+                if (R.mode == WF_MARCH) wf_step(P, R);
         }
         // ---- otherwise run the fullest of the other states (ties: the later stage):
         //      one MATCH gives every lane the size of its own group, one REDUX the winner ----
