@@ -171,7 +171,6 @@ def main():
     ptr, nbytes = r.probe_texture_device_ptr(0)
     tex = torch.as_tensor(DevPtr(ptr, 2 * nbytes), device=f"cuda:{local}")
     planes = [tex[:nbytes], tex[nbytes:]]
-    even = Y % world == 0
     row_bytes = W * 4 * ry
 
     if world > 1 and args.exchange == "fused":
@@ -189,15 +188,7 @@ def main():
             dist.all_reduce(sync_flag)
             return
         for pl in planes:
-            if even:
-                chunk = (Y // world) * row_bytes
-                dist.all_gather_into_tensor(pl, pl[rank * chunk:(rank + 1) * chunk])
-            else:
-                outs = []
-                for g in range(world):
-                    a, b = ddgi_b200.probe_row_shard(Y, g, world)
-                    outs.append(pl[a * row_bytes:b * row_bytes])
-                dist.all_gather(outs, pl[y0 * row_bytes:y1 * row_bytes])
+            ddgi_b200.sharding.allgather_probe_rows(pl, Y, row_bytes, rank, world)
 
     frame_no = [0]
 

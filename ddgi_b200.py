@@ -9,6 +9,7 @@ if _root not in sys.path:
 _pkg = importlib.import_module("dynamic-diffuse-global-illumination-minecraft_b200")
 
 capi = _pkg.capi
+sharding = _pkg.sharding
 RVPT = _pkg.RVPT
 Camera = _pkg.Camera
 DDGIError = _pkg.DDGIError

@@ -6,7 +6,7 @@ The directory name is not a Python identifier; import it with
 ``importlib.import_module("dynamic-diffuse-global-illumination-minecraft_b200")`` or through
 the ``ddgi_b200`` alias module at the repository root.
 """
-from . import capi
+from . import capi, sharding
 from .rvpt import RVPT, Camera, DDGIError, probe_row_shard
 
-__all__ = ["capi", "RVPT", "Camera", "DDGIError", "probe_row_shard"]
+__all__ = ["capi", "sharding", "RVPT", "Camera", "DDGIError", "probe_row_shard"]

@@ -293,9 +293,4 @@ class RVPT:
         self._check(self._lib.ddgi_close_peers(self._ctx))
 
 
-def probe_row_shard(probe_rows: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous y-slab of probe rows owned by `rank`: rows split as
-    evenly as possible, the first `probe_rows % world` ranks take one extra."""
-    base, extra = divmod(probe_rows, world)
-    y0 = rank * base + min(rank, extra)
-    return y0, y0 + base + (1 if rank < extra else 0)
+from .sharding import probe_row_shard  # noqa: E402  (kept importable from here)
