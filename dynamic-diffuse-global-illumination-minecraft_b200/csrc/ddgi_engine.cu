@@ -175,6 +175,7 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
     }
     P->n_lights = c->n_lights;
     for (int i = 0; i < c->n_lights; i++) P->lights[i] = c->lights[i];
+    light_bounds(*P);
     P->side_length = c->field.side_length;
     P->rx = c->rx;
     P->ry = c->ry;

@@ -52,10 +52,20 @@ DDGI_HD v3 cross(v3 a, v3 b)
 {
     return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
+// RN(1/x): the IEEE reciprocal.  rcp.rn returns exactly what 1.0f / x does for every input
+// (zeros, denormals, Inf, NaN included) with a shorter sequence than the general division.
+DDGI_HD float rcp_exact(float x)
+{
+#ifdef __CUDA_ARCH__
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
 // normalize(v) = v * inversesqrt(dot(v,v)), inversesqrt(x) = 1/sqrt(x)  (glm 0.9.9.8 form)
 DDGI_HD v3 normalize(v3 a)
 {
-    float inv = 1.0f / sqrtf(dot(a, a));
+    float inv = rcp_exact(sqrtf(dot(a, a)));
     return a * inv;
 }
 

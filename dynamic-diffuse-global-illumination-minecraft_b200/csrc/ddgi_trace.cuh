@@ -36,6 +36,10 @@ struct FrameParams {
     // camera block (src/rvpt/camera.cpp:100-111) + host-evaluated 1/tan(hfov/2)
     float cam[20];
     float cam_w;
+    // bounding sphere of the light positions (light_bounds below): one test rejects all
+    // lights for a query that ends far from every one of them
+    float lights_centre[3];
+    float lights_radius;
 };
 
 struct Hit {
@@ -54,6 +58,26 @@ DDGI_HD float inf_f()
 #else
     return INFINITY;
 #endif
+}
+
+// Host-side: a sphere that contains every light position, radius rounded up generously
+// (1e-4 relative + 1e-4 absolute, far above the fp32 error of evaluating it).
+inline void light_bounds(FrameParams& P)
+{
+    double c[3] = {0, 0, 0};
+    for (int i = 0; i < P.n_lights; i++)
+        for (int a = 0; a < 3; a++) c[a] += (double)P.lights[i].pos[a] / (P.n_lights > 0 ? P.n_lights : 1);
+    double r = 0;
+    for (int i = 0; i < P.n_lights; i++) {
+        double d2 = 0;
+        for (int a = 0; a < 3; a++) {
+            double d = (double)P.lights[i].pos[a] - (double)(float)c[a];
+            d2 += d * d;
+        }
+        if (!(sqrt(d2) <= r)) r = sqrt(d2);  // a NaN / Inf position makes the radius NaN / Inf: never rejects
+    }
+    for (int a = 0; a < 3; a++) P.lights_centre[a] = (float)c[a];
+    P.lights_radius = (float)(r * 1.0001 + 1e-4);
 }
 
 DDGI_HD v3 lpos(const Light& l) { return V3(l.pos[0], l.pos[1], l.pos[2]); }
@@ -78,7 +102,10 @@ DDGI_HD float rng_next(uint32_t& st)
     return (float)st / 4294967296.0f;
 }
 
-DDGI_HD v3 hemisphere_dir(v3 normal, uint32_t& st)
+// `axis_normal`: the caller knows `normal` is an axis-aligned unit vector (or all-NaN).  Then
+// cross(normal, other) and cross(normal, p1) are axis-aligned unit vectors too (signed zeros
+// elsewhere) and normalize() returns them unchanged, so both calls are skipped.
+DDGI_HD v3 hemisphere_dir(v3 normal, uint32_t& st, bool axis_normal = false)
 {
     const float two_pi = 6.2831853071795864769252867665590057683943f;
     const float sqrt_third = 0.5773502691896257645091487805019574556476f;
@@ -89,8 +116,10 @@ DDGI_HD v3 hemisphere_dir(v3 normal, uint32_t& st)
     if (fabsf(normal.x) < sqrt_third) other = V3(1, 0, 0);
     else if (fabsf(normal.y) < sqrt_third) other = V3(0, 1, 0);
     else other = V3(0, 0, 1);
-    v3 p1 = normalize(cross(normal, other));
-    v3 p2 = normalize(cross(normal, p1));
+    v3 p1 = cross(normal, other);
+    if (!axis_normal) p1 = normalize(p1);
+    v3 p2 = cross(normal, p1);
+    if (!axis_normal) p2 = normalize(p2);
     float sn, cs;
     pin_sincos(around, &sn, &cs);
     return (normal * up + p1 * (cs * over)) + p2 * (sn * over);
@@ -137,6 +166,20 @@ DDGI_HD v3 face_normal(v3 p, v3 cell)
     if (fabsf(diff.z) > mx) {
         mx = fabsf(diff.z);
         n = V3(0, 0, gsign(diff.z));
+    }
+    return n;
+}
+
+// normalize(normalize(face_normal(p, cell))) — what grid_march (:1088) and intersect_scene
+// (:1294) make of it: an axis-aligned unit vector is a fixed point of normalize (dot = 1,
+// sqrt(1) = 1, 1/1 = 1, v * 1 = v) and the zero vector (no component of diff compares
+// > 0: all zero or NaN) becomes 0 * (1/sqrt(0)) = 0 * Inf = NaN in every component.
+DDGI_HD v3 face_normal_unit(v3 p, v3 cell)
+{
+    v3 n = face_normal(p, cell);
+    if (n.x == 0.0f && n.y == 0.0f && n.z == 0.0f) {
+        float q = 0.0f * inf_f();
+        return V3(q, q, q);
     }
     return n;
 }

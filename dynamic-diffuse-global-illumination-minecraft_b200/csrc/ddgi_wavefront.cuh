@@ -32,8 +32,10 @@
 //     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
 //     (intersection.glsl:100-113), so the two root divisions are skipped for it; and the
-//     light spheres are tested after the march, only those that could beat the block hit.
-//   * normalize() of an axis-aligned unit vector is the identity (1/sqrt(1) = 1).
+//     light spheres are tested after the march, only those that could beat the block hit
+//     (one bounding-sphere test rejects all of them for most queries).
+//   * normalize() of an axis-aligned unit vector is the identity (1/sqrt(1) = 1), which
+//     removes it from the block-hit normal, the feeler's lambert term and the scatter frame.
 #pragma once
 #include "ddgi_fastmath.cuh"
 #include "ddgi_trace.cuh"
@@ -77,14 +79,6 @@ struct WfRay {
     uint32_t lookups;
 };
 
-// normalize(v) with the exact shortcut for axis-aligned unit vectors: dot = 1,
-// sqrt(1) = 1, 1/1 = 1, v * 1 = v.
-DDGI_HD v3 normalize_axis_aware(v3 v)
-{
-    if ((fabsf(v.x) + fabsf(v.y)) + fabsf(v.z) == 1.0f && (v.x == 0.0f) + (v.y == 0.0f) + (v.z == 0.0f) == 2) return v;
-    return normalize(v);
-}
-
 // Light-sphere test of a query: nearest t over all lights, exactly as the loop of
 // intersect_scene (intersection.glsl:1262-1279) evaluates it, except that it runs AFTER
 // the march and skips lights that cannot beat the block hit at t_block:
@@ -103,6 +97,11 @@ DDGI_HD float light_test(const FrameParams& P, v3 origin, v3 direction, float t_
     if (t_block < inf_f()) {
         float reach = (t_block * sqrtf(dot(direction, direction))) * 1.01f + 0.101f;
         reach2 = reach * reach;
+        // all lights at once: they lie within lights_radius of lights_centre, so
+        // |w_i| >= |origin - centre| - radius for every i; 1.0001 covers the fp32 evaluation
+        v3 wc = origin - V3(P.lights_centre[0], P.lights_centre[1], P.lights_centre[2]);
+        float far = reach + P.lights_radius;
+        if (dot(wc, wc) > (far * far) * 1.0001f) return closest;
     }
     bool scaled = false;
     v3 d = V3(0, 0, 0);
@@ -250,7 +249,7 @@ DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
         // face_normal is axis-aligned (or zero for a NaN position): both normalize() calls
         // of the reference (grid_march :1088, intersect_scene :1294) are identities on it
         v3 cell = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
-        normal = normalize_axis_aware(normalize_axis_aware(face_normal(R.p, cell)));
+        normal = face_normal_unit(R.p, cell);
         R.hblock = scene_type_at(P.scene, cell);
     } else {
         // a light sphere is the nearest hit (rare): redo the test for its normal
@@ -281,7 +280,10 @@ DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
     if (block_hit) closest = R.t;
     const Light& l = P.lights[R.phase - 1];
     if (closest < inf_f()) {
-        float lambert = gclamp(dot(normalize_axis_aware(R.hnormal), R.qd), 0.0f, 1.0f);
+        // normalize(info.normal) (probe_pass.comp:194): a block-hit normal is an axis-aligned
+        // unit vector (or all-NaN), a fixed point of normalize
+        v3 n = R.hblock >= 0 ? R.hnormal : normalize(R.hnormal);
+        float lambert = gclamp(dot(n, R.qd), 0.0f, 1.0f);
         if (!block_hit) {
             float dist = length(lpos(l) - R.hpos);
             R.direct = R.direct + ((lcol(l) * lambert) * l.intensity) / dist;
@@ -313,7 +315,7 @@ DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
 DDGI_HD void wf_scatter(const FrameParams& P, WfRay& R)
 {
     v3 o = R.hpos + R.hnormal * 0.0001f;
-    v3 d = hemisphere_dir(R.hnormal, R.rng);
+    v3 d = hemisphere_dir(R.hnormal, R.rng, R.hblock >= 0);
     R.bounce++;
     if (R.bounce >= P.max_bounces) {
         wf_finish_ray(P, R);

@@ -75,6 +75,7 @@ static void build(const SimParams* S, const float* cam, Built* B)
             P.lights[i].pos[a] = S->lights[i].pos[a];
         }
     }
+    light_bounds(P);
     P.side_length = S->side_length;
     P.rx = S->rx;
     P.ry = S->ry;
