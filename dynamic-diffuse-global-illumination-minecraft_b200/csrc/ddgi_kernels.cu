@@ -131,8 +131,6 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
             if (R.mode == WF_BOUNCE_HIT) wf_resolve_bounce(P, R);
         } else if (best == WF_FEELER_HIT) {
             if (R.mode == WF_FEELER_HIT) wf_resolve_feeler(P, R);
-        } else if (best == WF_SCATTER) {
-            if (R.mode == WF_SCATTER) wf_scatter(P, R);
         } else if (best == WF_MARCH_SLOW) {
             if (R.mode == WF_MARCH_SLOW) wf_step_literal(P, R);
         } else {
@@ -175,8 +173,10 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                 }
             }
         }
-        // every state above hands over to WF_QUERY or ends the ray: arm the new queries
-        // right away instead of scheduling them as a state of their own
+        // a resolved bounce scatters at once, and every state above hands over to WF_QUERY or
+        // ends the ray: arm the new queries right away.  Neither is scheduled as a state of
+        // its own (one MATCH/REDUX round less per bounce and per query).
+        if (R.mode == WF_SCATTER) wf_scatter(P, R);
         if (R.mode == WF_QUERY) wf_begin_query(P, R);
     }
 }
