@@ -117,7 +117,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="field_32")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"])
+    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
+                    help="N > 1: fused = the kernel stores texels into every replica over NVLink; nccl = in-place all-gathers")
+    ap.add_argument("--sharding", default="cyclic", choices=["cyclic", "slab"],
+                    help="N > 1: block-cyclic probe rows (balanced) or one contiguous slab per rank")
     ap.add_argument("--variant", type=int, default=1)
     ap.add_argument("--march-min", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -164,8 +167,16 @@ def main():
     rx, ry = cfg["tile"]
     n_rays = X * Y * Z * rx * ry
     W, H = r.probe_texture_size
-    y0, y1 = ddgi_b200.probe_row_shard(Y, rank, world)
-    r.set_probe_rows(y0, y1)
+    sh = ddgi_b200.sharding
+    if args.sharding == "cyclic" and world > 1:
+        block = 1 if args.exchange == "fused" else sh.cyclic_block(Y, world)
+        owned = sh.probe_row_blocks(Y, rank, world, block)
+        r.set_probe_rows_cyclic(rank, world, block)
+    else:
+        block = 0
+        owned = [sh.probe_row_shard(Y, rank, world)]
+        r.set_probe_rows(*owned[0])
+    owned_rows = sum(b - a for a, b in owned)
 
     # the probe texture as a torch tensor (for the NCCL exchange)
     ptr, nbytes = r.probe_texture_device_ptr(0)
@@ -188,7 +199,10 @@ def main():
             dist.all_reduce(sync_flag)
             return
         for pl in planes:
-            ddgi_b200.sharding.allgather_probe_rows(pl, Y, row_bytes, rank, world)
+            if block:
+                sh.allgather_probe_rows_cyclic(pl, Y, row_bytes, rank, world, block)
+            else:
+                sh.allgather_probe_rows(pl, Y, row_bytes, rank, world)
 
     frame_no = [0]
 
@@ -274,15 +288,15 @@ def main():
     r.probe_update()
     r.sync()
     per_row = X * Z * rx * ry
-    lk = r.read_lookup_counts(0)[y0 * per_row:y1 * per_row]
-    lk_sum = torch.tensor([float(lk.sum(dtype=np.float64))], device=f"cuda:{local}", dtype=torch.float64)
+    lk_all = r.read_lookup_counts(0)
+    lk_sum = torch.tensor([float(sum(lk_all[a * per_row:b * per_row].sum(dtype=np.float64) for a, b in owned))], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(lk_sum)
     mean_lookups = float(lk_sum[0]) / n_rays
     r.set_debug(False)
     bytes_per_ray = 4.0 * mean_lookups + 8.0
     peak, peak_src = load_peaks()
-    rays_this_rank = (y1 - y0) * per_row
+    rays_this_rank = owned_rows * per_row
     achieved = rays_this_rank * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
 
     # ---- e2e through the C-ABI with host buffers (pinned), per step:
@@ -295,7 +309,7 @@ def main():
         host_tex = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         lib = ddgi_b200.capi.load()
         h2d = pinned_samples.numel() * 4 + 32 + 48 + 80 + 4 * 28
-        d2h = nbytes if world == 1 else (y1 - y0) * row_bytes
+        d2h = nbytes if world == 1 else owned_rows * row_bytes
 
         def e2e_step():
             frame_no[0] += 1
@@ -310,8 +324,12 @@ def main():
                 rc = lib.ddgi_read_probe_texture(r._ctx, 0, 0, host_tex.data_ptr(), nbytes)
                 assert rc == 0
             else:
+                at = 0
+                for a, b in owned:  # this rank's rows of the albedo plane
+                    n = (b - a) * row_bytes
+                    host_tex[at:at + n].copy_(planes[0][a * row_bytes:b * row_bytes], non_blocking=True)
+                    at += n
                 torch.cuda.current_stream().synchronize()
-                host_tex[: d2h].copy_(planes[0][y0 * row_bytes:y1 * row_bytes])
 
         for _ in range(3):
             e2e_step()
@@ -366,7 +384,7 @@ def main():
                        "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"]),
                        "l2": "flushed between timed steps (256 MiB write)" if flush_buf is not None else "not flushed",
                        "kernel_variant": args.variant, "exchange": args.exchange if world > 1 else "none",
-                       "sharding": f"probe rows {Y}/{world}"},
+                       "sharding": (f"probe rows {Y}/{world}, " + (f"block-cyclic (block {block})" if block else "contiguous slabs"))},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "ddgi_get_probe_rays": (C.c_int, [_P, _P, _SZ]),
     "ddgi_num_probe_rays": (_SZ, [_P]),
     "ddgi_set_probe_rows": (C.c_int, [_P, _I32, _I32]),
+    "ddgi_set_probe_rows_cyclic": (C.c_int, [_P, _I32, _I32, _I32]),
     "ddgi_probe_texture_device_ptr": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_SZ)]),
     "ddgi_export_texture_handle": (C.c_int, [_P, _P]),
     "ddgi_open_peers": (C.c_int, [_P, _I32, _P, _I32]),

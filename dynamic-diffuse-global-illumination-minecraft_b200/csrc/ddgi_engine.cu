@@ -50,7 +50,8 @@ struct ddgi_ctx {
     uint32_t* d_tex = nullptr;
     float4* d_tex_f32 = nullptr;
     uint32_t* d_ray_lookups = nullptr;
-    int row0 = 0, row1 = 0;  // probe rows owned by this context
+    int row0 = 0, row1 = 0;  // probe rows owned by this context (contiguous ownership)
+    int cyc_world = 0, cyc_rank = 0, cyc_block = 1;  // block-cyclic ownership when cyc_world > 0
 
     // frame
     int frame_w = 0, frame_h = 0;
@@ -580,6 +581,18 @@ int ddgi_set_probe_rows(ddgi_ctx* ctx, int32_t y0, int32_t y1)
     NEED(0 <= y0 && y0 <= y1 && y1 <= ctx->field.probe_count[1], "rows out of range");
     ctx->row0 = y0;
     ctx->row1 = y1;
+    ctx->cyc_world = 0;
+    return DDGI_OK;
+}
+
+int ddgi_set_probe_rows_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, int32_t block)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    NEED(world >= 1 && rank >= 0 && rank < world && block >= 1, "bad rank / world / block");
+    ctx->cyc_world = world;
+    ctx->cyc_rank = rank;
+    ctx->cyc_block = block;
     return DDGI_OK;
 }
 
@@ -657,6 +670,17 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     uint32_t per_row = (uint32_t)(ctx->field.probe_count[0] * ctx->field.probe_count[2] * ctx->rx * ctx->ry);
     J.ray_begin = (uint32_t)ctx->row0 * per_row;
     J.ray_end = (uint32_t)ctx->row1 * per_row;
+    if (ctx->cyc_world > 0) {
+        uint32_t owned = 0;
+        for (int y = 0; y < ctx->field.probe_count[1]; y++)
+            if ((y / ctx->cyc_block) % ctx->cyc_world == ctx->cyc_rank) owned++;
+        J.ray_begin = 0;
+        J.ray_end = owned * per_row;
+        J.rays_per_row = per_row;
+        J.row_block = ctx->cyc_block;
+        J.row_world = ctx->cyc_world;
+        J.row_rank = ctx->cyc_rank;
+    }
     J.tex_w = ctx->tex_w;
     J.tex_h = ctx->tex_h;
     J.albedo = ctx->d_tex;

@@ -14,7 +14,12 @@ struct ProbeJob {
     const float4* rays;   // literal 48-byte ProbeRay records (3 x float4) or nullptr
     const float* dirs;    // generated mode: rx*ry normalised directions (xyz)
     uint32_t ray_begin;   // first / one-past-last linear ray index of this shard
-    uint32_t ray_end;
+    uint32_t ray_end;     // (cyclic ownership: 0 / number of owned rays)
+    // block-cyclic ownership of probe rows (row_world > 0): this shard owns the rows y with
+    // (y / row_block) % row_world == row_rank; owned ray i is ray `i % rays_per_row` of the
+    // (i / rays_per_row)-th owned row
+    uint32_t rays_per_row;
+    int row_block, row_world, row_rank;
     int tex_w, tex_h;
     uint32_t* albedo;     // W*H RGBA8
     uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)

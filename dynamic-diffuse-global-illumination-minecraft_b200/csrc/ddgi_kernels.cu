@@ -50,6 +50,18 @@ __device__ __forceinline__ RayIn fetch_ray(const FrameParams& P, const ProbeJob&
     return r;
 }
 
+// Linear ray index of the idx-th ray of this shard.
+__device__ __forceinline__ uint32_t shard_ray(const ProbeJob& J, uint32_t idx)
+{
+    if (J.row_world == 0) return J.ray_begin + idx;
+    uint32_t lrow = idx / J.rays_per_row;
+    uint32_t rem = idx - lrow * J.rays_per_row;
+    uint32_t blk = lrow / (uint32_t)J.row_block;
+    uint32_t within = lrow - blk * (uint32_t)J.row_block;
+    uint32_t y = (blk * (uint32_t)J.row_world + (uint32_t)J.row_rank) * (uint32_t)J.row_block + within;
+    return y * J.rays_per_row + rem;
+}
+
 __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v3 color, uint32_t k,
                                             uint32_t lookups)
 {
@@ -70,8 +82,9 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
 __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant__ FrameParams P,
                                                            const __grid_constant__ ProbeJob J)
 {
-    uint32_t k = J.ray_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= J.ray_end) return;
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= J.ray_end - J.ray_begin) return;
+    uint32_t k = shard_ray(J, idx);
     RayIn r = fetch_ray(P, J, k);
     uint32_t lookups = 0;
     v3 color = trace_probe_ray(P, r.origin, r.direction, k, lookups);
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
             }
             if (need) {
                 if (idx < n_rays) {
-                    k = J.ray_begin + idx;
+                    k = shard_ray(J, idx);
                     RayIn r = fetch_ray(P, J, k);
                     tx = r.tx;
                     ty = r.ty;

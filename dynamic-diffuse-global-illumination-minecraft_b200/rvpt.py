@@ -275,6 +275,9 @@ class RVPT:
     def set_probe_rows(self, y0: int, y1: int):
         self._check(self._lib.ddgi_set_probe_rows(self._ctx, y0, y1))
 
+    def set_probe_rows_cyclic(self, rank: int, world: int, block: int = 1):
+        self._check(self._lib.ddgi_set_probe_rows_cyclic(self._ctx, rank, world, block))
+
     def probe_texture_device_ptr(self, which: int = 0):
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self._lib.ddgi_probe_texture_device_ptr(self._ctx, which, C.byref(p), C.byref(n)))

@@ -28,6 +28,53 @@ def shard_byte_ranges(probe_rows: int, world: int, row_bytes: int) -> list[tuple
     return out
 
 
+def cyclic_block(probe_rows: int, world: int, max_groups: int = 8) -> int:
+    """Block size for block-cyclic ownership: 1 row unless that needs more than `max_groups`
+    collectives per plane (one per group of world*block rows)."""
+    block = 1
+    while probe_rows > max_groups * world * block:
+        block *= 2
+    return block
+
+
+def probe_row_blocks(probe_rows: int, rank: int, world: int, block: int = 1) -> list[tuple[int, int]]:
+    """Block-cyclic ownership (ddgi_set_probe_rows_cyclic): the row ranges [y0, y1) with
+    (y // block) % world == rank, in increasing order.  Spreads expensive regions of the
+    field over all ranks, which contiguous slabs do not."""
+    if world < 1 or not 0 <= rank < world or block < 1:
+        raise ValueError(f"rank {rank} of world {world}, block {block}")
+    out = []
+    y = rank * block
+    while y < probe_rows:
+        out.append((y, min(y + block, probe_rows)))
+        y += world * block
+    return out
+
+
+def allgather_probe_rows_cyclic(plane, probe_rows: int, row_bytes: int, rank: int, world: int, block: int = 1, group=None):
+    """In-place exchange of one texture plane under block-cyclic ownership: every group of
+    world*block consecutive probe rows is one all_gather_into_tensor (rank r's block is the
+    r-th chunk of the group); a ragged last group is broadcast block by block."""
+    import torch.distributed as dist
+
+    if world == 1:
+        return
+    span = world * block
+    full_groups = probe_rows // span
+    for g in range(full_groups):
+        base = g * span * row_bytes
+        mine = base + rank * block * row_bytes
+        dist.all_gather_into_tensor(plane[base:base + span * row_bytes], plane[mine:mine + block * row_bytes], group=group)
+    y = full_groups * span
+    owner = 0
+    while y < probe_rows:
+        y1 = min(y + block, probe_rows)
+        src = dist.get_global_rank(group, owner) if group is not None else owner
+        dist.broadcast(plane[y * row_bytes:y1 * row_bytes], src=src, group=group)
+        y = y1
+        owner += 1
+
+
 def allgather_probe_rows(plane, probe_rows: int, row_bytes: int, rank: int, world: int, group=None):
     """In-place all-gather of one texture plane (a flat uint8 torch tensor over the whole
     plane, on any device the process group supports).  Even splits use ONE

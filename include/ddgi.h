@@ -152,6 +152,10 @@ DDGI_API size_t ddgi_num_probe_rays(const ddgi_ctx* ctx);
 /* ---- probe sharding across GPUs (no reference counterpart) ---- */
 /* This context updates only probe rows [y0, y1) (texture rows [y0*ry, y1*ry)). */
 DDGI_API int ddgi_set_probe_rows(ddgi_ctx* ctx, int32_t y0, int32_t y1);
+/* Block-cyclic ownership instead: this context updates the probe rows y with
+   (y / block) % world == rank.  Spreads the expensive (open-cavity) rows over all ranks;
+   each owned block is still a contiguous byte range of the texture. */
+DDGI_API int ddgi_set_probe_rows_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, int32_t block);
 /* Device address and size of probe texture `which` (0 albedo, 1 distance); both live in
    one allocation, albedo first, so one collective can move both. */
 DDGI_API int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** ptr, size_t* bytes);

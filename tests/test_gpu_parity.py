@@ -167,6 +167,35 @@ def test_probe_row_shards_compose_to_the_full_texture():
     assert np.array_equal(np.concatenate(parts, axis=0), full)
 
 
+def test_block_cyclic_shards_compose_to_the_full_texture():
+    """ddgi_set_probe_rows_cyclic: three ranks, block 1 and 2, ragged (8 rows / 3)."""
+    cfg = CFG["field_8"]
+    with make_engine(cfg, debug=False) as r:
+        r.probe_update()
+        r.sync()
+        full = r.read_probe_texture(0)
+    rows = cfg["probe_count"][1]
+    ry = cfg["tile"][1]
+    for block in (1, 2):
+        acc = np.zeros_like(full)
+        for rank in range(3):
+            owned = ddgi_b200.sharding.probe_row_blocks(rows, rank, 3, block)
+            for variant in (0, 1):
+                with make_engine(cfg, debug=False) as r:
+                    r.set_kernel_variant(variant)
+                    r.set_probe_rows_cyclic(rank, 3, block)
+                    r.probe_update()
+                    r.sync()
+                    t = r.read_probe_texture(0)
+                mask = np.zeros(t.shape[0], dtype=bool)
+                for a, b in owned:
+                    mask[a * ry:b * ry] = True
+                assert (t[~mask] == 0).all()
+                assert np.array_equal(t[mask], full[mask])
+            acc[mask] = t[mask]
+        assert np.array_equal(acc, full)
+
+
 def test_idempotent_and_tuning_independent():
     cfg = CFG["field_8"]
     with make_engine(cfg, debug=False) as r:
