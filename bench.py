@@ -120,7 +120,8 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
                     help="N > 1: fused = the kernel stores texels into every replica over NVLink; nccl = in-place all-gathers")
     ap.add_argument("--sharding", default="cyclic", choices=["cyclic", "slab"],
-                    help="N > 1: block-cyclic probe rows (balanced) or one contiguous slab per rank")
+                    help="N > 1: cyclic ownership (single probes with the fused exchange, blocks of probe rows with nccl) "
+                         "or one contiguous slab of probe rows per rank")
     ap.add_argument("--variant", type=int, default=1)
     ap.add_argument("--march-min", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -168,15 +169,26 @@ def main():
     n_rays = X * Y * Z * rx * ry
     W, H = r.probe_texture_size
     sh = ddgi_b200.sharding
-    if args.sharding == "cyclic" and world > 1:
-        block = 1 if args.exchange == "fused" else sh.cyclic_block(Y, world)
-        owned = sh.probe_row_blocks(Y, rank, world, block)
+    n_probes = X * Y * Z
+    probe_owner = np.zeros(n_probes, dtype=np.int32)   # rank that updates each probe
+    block = 0
+    slab = sh.probe_row_shard(Y, rank, world)           # the rows a rank reads back (e2e) in any mode
+    if world > 1 and args.sharding == "cyclic" and args.exchange == "fused":
+        r.set_probes_cyclic(rank, world, 1)
+        probe_owner = (np.arange(n_probes) % world).astype(np.int32)
+        shard_desc = f"{n_probes} probes dealt round-robin to {world} ranks"
+    elif world > 1 and args.sharding == "cyclic":
+        block = sh.cyclic_block(Y, world)
         r.set_probe_rows_cyclic(rank, world, block)
+        probe_owner = np.repeat((np.arange(Y) // block) % world, X * Z).astype(np.int32)
+        shard_desc = f"probe rows {Y}/{world}, block-cyclic (block {block})"
     else:
-        block = 0
-        owned = [sh.probe_row_shard(Y, rank, world)]
-        r.set_probe_rows(*owned[0])
-    owned_rows = sum(b - a for a, b in owned)
+        r.set_probe_rows(*slab)
+        for g in range(world):
+            a, b = sh.probe_row_shard(Y, g, world)
+            probe_owner[a * X * Z:b * X * Z] = g
+        shard_desc = f"probe rows {Y}/{world}, contiguous slabs"
+    owned_probes = probe_owner == rank
 
     # the probe texture as a torch tensor (for the NCCL exchange)
     ptr, nbytes = r.probe_texture_device_ptr(0)
@@ -288,15 +300,15 @@ def main():
     r.probe_update()
     r.sync()
     per_row = X * Z * rx * ry
-    lk_all = r.read_lookup_counts(0)
-    lk_sum = torch.tensor([float(sum(lk_all[a * per_row:b * per_row].sum(dtype=np.float64) for a, b in owned))], device=f"cuda:{local}", dtype=torch.float64)
+    lk_all = r.read_lookup_counts(0).reshape(n_probes, rx * ry)
+    lk_sum = torch.tensor([float(lk_all[owned_probes].sum(dtype=np.float64))], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(lk_sum)
     mean_lookups = float(lk_sum[0]) / n_rays
     r.set_debug(False)
     bytes_per_ray = 4.0 * mean_lookups + 8.0
     peak, peak_src = load_peaks()
-    rays_this_rank = owned_rows * per_row
+    rays_this_rank = int(owned_probes.sum()) * rx * ry
     achieved = rays_this_rank * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
 
     # ---- e2e through the C-ABI with host buffers (pinned), per step:
@@ -309,7 +321,7 @@ def main():
         host_tex = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         lib = ddgi_b200.capi.load()
         h2d = pinned_samples.numel() * 4 + 32 + 48 + 80 + 4 * 28
-        d2h = nbytes if world == 1 else owned_rows * row_bytes
+        d2h = nbytes if world == 1 else (slab[1] - slab[0]) * row_bytes
 
         def e2e_step():
             frame_no[0] += 1
@@ -324,11 +336,8 @@ def main():
                 rc = lib.ddgi_read_probe_texture(r._ctx, 0, 0, host_tex.data_ptr(), nbytes)
                 assert rc == 0
             else:
-                at = 0
-                for a, b in owned:  # this rank's rows of the albedo plane
-                    n = (b - a) * row_bytes
-                    host_tex[at:at + n].copy_(planes[0][a * row_bytes:b * row_bytes], non_blocking=True)
-                    at += n
+                # every replica is complete after the exchange: each rank reads back 1/N of the albedo plane
+                host_tex[:d2h].copy_(planes[0][slab[0] * row_bytes:slab[1] * row_bytes], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
         for _ in range(3):
@@ -384,7 +393,7 @@ def main():
                        "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"]),
                        "l2": "flushed between timed steps (256 MiB write)" if flush_buf is not None else "not flushed",
                        "kernel_variant": args.variant, "exchange": args.exchange if world > 1 else "none",
-                       "sharding": (f"probe rows {Y}/{world}, " + (f"block-cyclic (block {block})" if block else "contiguous slabs"))},
+                       "sharding": shard_desc if world > 1 else "none"},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "ddgi_num_probe_rays": (_SZ, [_P]),
     "ddgi_set_probe_rows": (C.c_int, [_P, _I32, _I32]),
     "ddgi_set_probe_rows_cyclic": (C.c_int, [_P, _I32, _I32, _I32]),
+    "ddgi_set_probes_cyclic": (C.c_int, [_P, _I32, _I32, _I32]),
     "ddgi_probe_texture_device_ptr": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_SZ)]),
     "ddgi_export_texture_handle": (C.c_int, [_P, _P]),
     "ddgi_open_peers": (C.c_int, [_P, _I32, _P, _I32]),
@@ -116,6 +117,7 @@ PROTOTYPES = {
     "ddgi_read_lookup_counts": (C.c_int, [_P, _I32, _P, _SZ]),
     "ddgi_set_kernel_variant": (C.c_int, [_P, _I32]),
     "ddgi_set_tuning": (C.c_int, [_P, _I32]),
+    "ddgi_set_auto_schedule": (C.c_int, [_P, _I32]),
     "ddgi_launch_count": (C.c_uint64, [_P]),
 }
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/ddgi.h"
@@ -52,6 +53,17 @@ struct ddgi_ctx {
     uint32_t* d_ray_lookups = nullptr;
     int row0 = 0, row1 = 0;  // probe rows owned by this context (contiguous ownership)
     int cyc_world = 0, cyc_rank = 0, cyc_block = 1;  // block-cyclic ownership when cyc_world > 0
+    int cyc_unit = 0;                                // 0: blocks of probe rows, 1: blocks of probes
+
+    // schedule: the owned probes, most expensive first once calibrated
+    std::vector<uint32_t> order;
+    uint32_t* d_order = nullptr;
+    uint32_t* d_probe_cost = nullptr;
+    size_t order_cap = 0;
+    bool order_dirty = true;   // ownership / field changed: rebuild the list
+    bool calibrated = false;   // per-probe costs of the current scene + rays are in `cost`
+    int auto_schedule = 1;
+    std::vector<uint32_t> cost;
 
     // frame
     int frame_w = 0, frame_h = 0;
@@ -98,6 +110,51 @@ static size_t num_rays(const ddgi_ctx* c)
 {
     if (!c->have_field) return 0;
     return (size_t)c->field.probe_count[0] * c->field.probe_count[1] * c->field.probe_count[2] * c->rx * c->ry;
+}
+
+static size_t num_probes(const ddgi_ctx* c)
+{
+    return (size_t)c->field.probe_count[0] * c->field.probe_count[1] * c->field.probe_count[2];
+}
+
+static bool owns_probe(const ddgi_ctx* c, int p)
+{
+    int per_row = c->field.probe_count[0] * c->field.probe_count[2];
+    int y = p / per_row;
+    if (c->cyc_world == 0) return y >= c->row0 && y < c->row1;
+    int unit = c->cyc_unit ? p : y;
+    return (unit / c->cyc_block) % c->cyc_world == c->cyc_rank;
+}
+
+// Builds the list of owned probes (by the ownership mode: a slab of probe rows, block-cyclic
+// rows or block-cyclic probes) and uploads it.  With measured costs the list is sorted most
+// expensive first (ties by probe index): a probe ray's bounces and marches are one long
+// dependent chain, so the longest rays must start early or they ARE the kernel's tail.
+static int schedule(ddgi_ctx* ctx)
+{
+    if (!ctx->order_dirty && ctx->d_order) return DDGI_OK;
+    size_t np = num_probes(ctx);
+    ctx->order.clear();
+    for (size_t p = 0; p < np; p++)
+        if (owns_probe(ctx, (int)p)) ctx->order.push_back((uint32_t)p);
+    if (ctx->auto_schedule && ctx->calibrated && ctx->cost.size() == np) {
+        const std::vector<uint32_t>& c = ctx->cost;
+        bool measured = true;
+        for (uint32_t p : ctx->order) measured = measured && c[p] != 0xffffffffu;
+        if (measured)
+            std::stable_sort(ctx->order.begin(), ctx->order.end(), [&c](uint32_t a, uint32_t b) { return c[a] > c[b]; });
+    }
+    if (np > ctx->order_cap) {
+        dfree(ctx->d_order);
+        dfree(ctx->d_probe_cost);
+        CU(cudaMalloc(&ctx->d_order, np * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->d_probe_cost, np * sizeof(uint32_t)));
+        ctx->order_cap = np;
+    }
+    if (!ctx->order.empty())
+        CU(cudaMemcpy(ctx->d_order, ctx->order.data(), ctx->order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->order_dirty = false;
+    return DDGI_OK;
 }
 
 // (Re)creates the probe textures for the current field, as recreate_probe_textures
@@ -237,6 +294,7 @@ static int finish_voxels(ddgi_ctx* ctx)
     CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
     ctx->launches += l;
     CU(cudaDeviceSynchronize());
+    ctx->calibrated = false;  // a new scene: measure the per-probe costs again
     return DDGI_OK;
 }
 
@@ -323,6 +381,8 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_frame);
     dfree(ctx->d_frame_f32);
     dfree(ctx->d_px_lookups);
+    dfree(ctx->d_order);
+    dfree(ctx->d_probe_cost);
     delete ctx;
 }
 
@@ -364,6 +424,8 @@ int ddgi_set_irradiance_field(ddgi_ctx* ctx, const ddgi_irradiance_field* f)
         ctx->ray_mode = 0;
         ctx->row0 = 0;
         ctx->row1 = f->probe_count[1];
+        ctx->order_dirty = true;
+        ctx->calibrated = false;
         return resize_textures(ctx);
     }
     return DDGI_OK;
@@ -379,6 +441,7 @@ int ddgi_set_ray_tile(ddgi_ctx* ctx, int32_t rx, int32_t ry)
         ctx->rx = rx;
         ctx->ry = ry;
         ctx->ray_mode = 0;
+        ctx->calibrated = false;
         return resize_textures(ctx);
     }
     return DDGI_OK;
@@ -582,6 +645,8 @@ int ddgi_set_probe_rows(ddgi_ctx* ctx, int32_t y0, int32_t y1)
     ctx->row0 = y0;
     ctx->row1 = y1;
     ctx->cyc_world = 0;
+    ctx->order_dirty = true;
+    ctx->calibrated = false;
     return DDGI_OK;
 }
 
@@ -593,7 +658,17 @@ int ddgi_set_probe_rows_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, int32
     ctx->cyc_world = world;
     ctx->cyc_rank = rank;
     ctx->cyc_block = block;
+    ctx->cyc_unit = 0;
+    ctx->order_dirty = true;
+    ctx->calibrated = false;
     return DDGI_OK;
+}
+
+int ddgi_set_probes_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, int32_t block)
+{
+    int rc = ddgi_set_probe_rows_cyclic(ctx, rank, world, block);
+    if (rc == DDGI_OK) ctx->cyc_unit = 1;  // order_dirty already set
+    return rc;
 }
 
 int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** ptr, size_t* bytes)
@@ -667,19 +742,15 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     memset(&J, 0, sizeof(J));
     J.rays = ctx->ray_mode == 2 ? ctx->d_rays : nullptr;
     J.dirs = ctx->d_dirs;
-    uint32_t per_row = (uint32_t)(ctx->field.probe_count[0] * ctx->field.probe_count[2] * ctx->rx * ctx->ry);
-    J.ray_begin = (uint32_t)ctx->row0 * per_row;
-    J.ray_end = (uint32_t)ctx->row1 * per_row;
-    if (ctx->cyc_world > 0) {
-        uint32_t owned = 0;
-        for (int y = 0; y < ctx->field.probe_count[1]; y++)
-            if ((y / ctx->cyc_block) % ctx->cyc_world == ctx->cyc_rank) owned++;
-        J.ray_begin = 0;
-        J.ray_end = owned * per_row;
-        J.rays_per_row = per_row;
-        J.row_block = ctx->cyc_block;
-        J.row_world = ctx->cyc_world;
-        J.row_rank = ctx->cyc_rank;
+    rc = schedule(ctx);
+    if (rc) return rc;
+    bool calibrate = ctx->auto_schedule && !ctx->calibrated;
+    J.order = ctx->d_order;
+    J.n_owned = (uint32_t)ctx->order.size();
+    J.rays_per_probe = (uint32_t)(ctx->rx * ctx->ry);
+    if (calibrate) {
+        CU(cudaMemsetAsync(ctx->d_probe_cost, 0, num_probes(ctx) * sizeof(uint32_t), (cudaStream_t)stream));
+        J.probe_cost = ctx->d_probe_cost;
     }
     J.tex_w = ctx->tex_w;
     J.tex_h = ctx->tex_h;
@@ -696,6 +767,19 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     int l = 0;
     CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, (cudaStream_t)stream, &l));
     ctx->launches += l;
+    if (calibrate) {
+        // First update after the scene / rays / field changed: this launch also summed the voxel
+        // lookups per probe.  Read them once (the only synchronising probe update) and list the
+        // owned probes most expensive first from now on.
+        size_t np = num_probes(ctx);
+        std::vector<uint32_t> c(np);
+        CU(cudaMemcpyAsync(c.data(), ctx->d_probe_cost, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        if (ctx->cost.size() != np) ctx->cost.assign(np, 0xffffffffu);
+        for (uint32_t p : ctx->order) ctx->cost[p] = c[p];  // only the owned probes were measured
+        ctx->calibrated = true;
+        ctx->order_dirty = true;
+    }
     return DDGI_OK;
 }
 
@@ -826,6 +910,15 @@ int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min)
     if (!ctx) return DDGI_E_INVALID;
     NEED(march_min >= 1 && march_min <= 32, "march_min in [1,32]");
     ctx->march_min = march_min;
+    return DDGI_OK;
+}
+
+int ddgi_set_auto_schedule(ddgi_ctx* ctx, int32_t on)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    ctx->auto_schedule = on ? 1 : 0;
+    ctx->order_dirty = true;
+    ctx->calibrated = false;
     return DDGI_OK;
 }
 

@@ -13,13 +13,14 @@ constexpr int kMaxPeers = 8;
 struct ProbeJob {
     const float4* rays;   // literal 48-byte ProbeRay records (3 x float4) or nullptr
     const float* dirs;    // generated mode: rx*ry normalised directions (xyz)
-    uint32_t ray_begin;   // first / one-past-last linear ray index of this shard
-    uint32_t ray_end;     // (cyclic ownership: 0 / number of owned rays)
-    // block-cyclic ownership of probe rows (row_world > 0): this shard owns the rows y with
-    // (y / row_block) % row_world == row_rank; owned ray i is ray `i % rays_per_row` of the
-    // (i / rays_per_row)-th owned row
-    uint32_t rays_per_row;
-    int row_block, row_world, row_rank;
+    // This shard updates the probes order[0 .. n_owned): the idx-th ray of the shard is ray
+    // idx % rays_per_probe of probe order[idx / rays_per_probe].  The host lists the owned
+    // probes most expensive first (ddgi_engine.cu: schedule), so the long rays start early and
+    // the persistent kernel's tail is short.  The order never changes a result.
+    const uint32_t* order;
+    uint32_t n_owned;
+    uint32_t rays_per_probe;
+    uint32_t* probe_cost;  // calibration launch: per-probe sum of voxel lookups, else nullptr
     int tex_w, tex_h;
     uint32_t* albedo;     // W*H RGBA8
     uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)

@@ -50,16 +50,12 @@ __device__ __forceinline__ RayIn fetch_ray(const FrameParams& P, const ProbeJob&
     return r;
 }
 
-// Linear ray index of the idx-th ray of this shard.
+// Linear ray index (the reference's position in the ProbeRay list) of the idx-th ray of this shard.
 __device__ __forceinline__ uint32_t shard_ray(const ProbeJob& J, uint32_t idx)
 {
-    if (J.row_world == 0) return J.ray_begin + idx;
-    uint32_t lrow = idx / J.rays_per_row;
-    uint32_t rem = idx - lrow * J.rays_per_row;
-    uint32_t blk = lrow / (uint32_t)J.row_block;
-    uint32_t within = lrow - blk * (uint32_t)J.row_block;
-    uint32_t y = (blk * (uint32_t)J.row_world + (uint32_t)J.row_rank) * (uint32_t)J.row_block + within;
-    return y * J.rays_per_row + rem;
+    uint32_t slot = idx / J.rays_per_probe;
+    uint32_t i = idx - slot * J.rays_per_probe;
+    return __ldg(J.order + slot) * J.rays_per_probe + i;
 }
 
 __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v3 color, uint32_t k,
@@ -76,6 +72,7 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
     }
     if (J.albedo_f32) J.albedo_f32[t] = make_float4(color.x, color.y, color.z, 1.0f);
     if (J.lookups) J.lookups[k] = lookups;
+    if (J.probe_cost) atomicAdd(J.probe_cost + k / J.rays_per_probe, lookups);
 }
 
 // ------------------------------------------------------------------ variant 0
@@ -83,7 +80,7 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
                                                            const __grid_constant__ ProbeJob J)
 {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= J.ray_end - J.ray_begin) return;
+    if (idx >= J.n_owned * J.rays_per_probe) return;
     uint32_t k = shard_ray(J, idx);
     RayIn r = fetch_ray(P, J, k);
     uint32_t lookups = 0;
@@ -115,7 +112,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const uint32_t n_rays = J.ray_end - J.ray_begin;
+    const uint32_t n_rays = J.n_owned * J.rays_per_probe;
     WfRay R;
     R.mode = WF_FETCH;
     uint32_t k = 0xffffffffu;  // no ray yet
@@ -292,7 +289,7 @@ __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, i
 cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
                                 int march_min, cudaStream_t s, int* launches)
 {
-    uint32_t n = J.ray_end - J.ray_begin;
+    uint32_t n = J.n_owned * J.rays_per_probe;
     if (n == 0) return cudaSuccess;
     if (variant == 0 || P.max_bounces <= 0) {
         dim3 block(256), grid((n + 255) / 256);

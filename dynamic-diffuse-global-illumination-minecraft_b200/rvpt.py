@@ -260,6 +260,9 @@ class RVPT:
     def set_tuning(self, march_min: int):
         self._check(self._lib.ddgi_set_tuning(self._ctx, march_min))
 
+    def set_auto_schedule(self, on: bool):
+        self._check(self._lib.ddgi_set_auto_schedule(self._ctx, 1 if on else 0))
+
     def read_lookup_counts(self, which: int = 0) -> np.ndarray:
         if which == 0:
             out = np.empty(self.num_probe_rays, dtype=np.uint32)
@@ -277,6 +280,9 @@ class RVPT:
 
     def set_probe_rows_cyclic(self, rank: int, world: int, block: int = 1):
         self._check(self._lib.ddgi_set_probe_rows_cyclic(self._ctx, rank, world, block))
+
+    def set_probes_cyclic(self, rank: int, world: int, block: int = 1):
+        self._check(self._lib.ddgi_set_probes_cyclic(self._ctx, rank, world, block))
 
     def probe_texture_device_ptr(self, which: int = 0):
         p, n = C.c_void_p(), C.c_size_t()

@@ -156,6 +156,10 @@ DDGI_API int ddgi_set_probe_rows(ddgi_ctx* ctx, int32_t y0, int32_t y1);
    (y / block) % world == rank.  Spreads the expensive (open-cavity) rows over all ranks;
    each owned block is still a contiguous byte range of the texture. */
 DDGI_API int ddgi_set_probe_rows_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, int32_t block);
+/* The same at probe granularity: this context updates the probes p with
+   (p / block) % world == rank.  Finest balance; a rank's texels are then scattered tiles,
+   so pair it with the fused exchange (ddgi_open_peers), not an all-gather. */
+DDGI_API int ddgi_set_probes_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, int32_t block);
 /* Device address and size of probe texture `which` (0 albedo, 1 distance); both live in
    one allocation, albedo first, so one collective can move both. */
 DDGI_API int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** ptr, size_t* bytes);
@@ -195,6 +199,12 @@ DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
    march_min/32 of the lanes that hold a ray are marching (1..32, default 14).  Results do
    not depend on it. */
 DDGI_API int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min);
+/* Cost-ordered scheduling (default on): the first ddgi_probe_update after the voxels, the
+   field shape or the probe ownership changed also sums the voxel lookups per probe and
+   synchronises once to read them; later updates trace the owned probes most expensive
+   first, which shortens the tail of the persistent kernel.  Results do not depend on it.
+   0 = natural probe order, never synchronises. */
+DDGI_API int ddgi_set_auto_schedule(ddgi_ctx* ctx, int32_t on);
 /* Number of kernel launches issued by this context so far. */
 DDGI_API uint64_t ddgi_launch_count(const ddgi_ctx* ctx);
 

@@ -196,6 +196,48 @@ def test_block_cyclic_shards_compose_to_the_full_texture():
         assert np.array_equal(acc, full)
 
 
+def test_probe_cyclic_shards_compose_to_the_full_texture():
+    """ddgi_set_probes_cyclic: 3 ranks over 512 probes (ragged), blocks of 1 and 5 probes."""
+    cfg = CFG["field_8"]
+    with make_engine(cfg, debug=False) as r:
+        r.probe_update()
+        r.sync()
+        full = r.read_probe_texture(0)
+    X, Y, Z = cfg["probe_count"]
+    rx, ry = cfg["tile"]
+    tiles = full.reshape(Y, ry, X * Z, rx).transpose(0, 2, 1, 3).reshape(X * Y * Z, ry, rx)  # [probe, ty, tx]
+    for block in (1, 5):
+        owner = (np.arange(X * Y * Z) // block) % 3
+        for rank in range(3):
+            with make_engine(cfg, debug=False) as r:
+                r.set_probes_cyclic(rank, 3, block)
+                r.probe_update()
+                r.sync()
+                t = r.read_probe_texture(0)
+            tt = t.reshape(Y, ry, X * Z, rx).transpose(0, 2, 1, 3).reshape(X * Y * Z, ry, rx)
+            assert np.array_equal(tt[owner == rank], tiles[owner == rank])
+            assert (tt[owner != rank] == 0).all()
+
+
+def test_cost_ordered_schedule_does_not_change_results():
+    """The first update measures per-probe costs, later ones trace expensive probes first:
+    same bytes, same per-ray lookup counts, with the schedule on or off, on both variants."""
+    cfg = CFG["field_8"]
+    sc = util.oracle_scene(cfg)
+    alb, _, _, steps, _ = oracle.probe_update(sc, oracle_rays(sc, cfg))
+    for variant in (0, 1):
+        for on in (True, False):
+            with make_engine(cfg) as r:
+                r.set_kernel_variant(variant)
+                r.set_auto_schedule(on)
+                for _ in range(3):  # calibrating update, then two scheduled ones
+                    r.write_probe_texture(np.zeros_like(alb))
+                    r.probe_update()
+                    r.sync()
+                    assert np.array_equal(r.read_probe_texture(0), alb)
+                    assert np.array_equal(r.read_lookup_counts(0), steps)
+
+
 def test_idempotent_and_tuning_independent():
     cfg = CFG["field_8"]
     with make_engine(cfg, debug=False) as r:
