@@ -1,0 +1,92 @@
+"""ctypes loader of oracle/_ref/libddgi_ref.so — the reference's own compute shaders
+(probe_pass.comp, compute_pass.comp + includes) transpiled to C++ by
+oracle/ref_glsl/build_ref.py and run on the CPU.
+
+TEST INFRASTRUCTURE ONLY (tests/, tests/golden/make_golden.py).  The reference's scene and
+lights are compiled into its shaders: only scenes 0 (cave), 1 (Cornell), 2 (house) with the
+reference's own light tables and procedural block / colour functions can run here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libddgi_ref.so")
+
+
+class RefSettings(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("screen_width", "screen_height", "max_bounces", "camera_mode", "render_mode", "scene")] + [
+        ("time", C.c_float), ("visualize_probes", C.c_int32)]
+
+
+class RefField(C.Structure):
+    _fields_ = [("probe_count", C.c_int32 * 3), ("side_length", C.c_int32), ("hysteresis", C.c_float),
+                ("sqrt_rays_per_probe", C.c_int32), ("field_origin", C.c_float * 3)]
+
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        from . import oracle
+
+        oracle.load()  # libddgi_ref.so resolves the pinned sin/cos/acos from the oracle library
+        lib = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        lib.ref_probe_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.ref_compute_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        _lib = lib
+    return _lib
+
+
+def _params(scene, probe_count, side_length, field_origin, s, screen=(0, 0), max_bounces=8, time=0.0):
+    rs = RefSettings(screen[0], screen[1], max_bounces, 0, 0, scene, time, 0)
+    f = RefField()
+    f.probe_count[:] = tuple(probe_count)
+    f.side_length = side_length
+    f.hysteresis = 0.9
+    f.sqrt_rays_per_probe = s
+    f.field_origin[:] = tuple(field_origin)
+    return rs, f
+
+
+def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bounces=8):
+    """Runs probe_pass.comp::main for every texel.  rays: float32 [R, 12] in the reference's
+    ProbeRay layout.  Returns (albedo RGBA8 [H,W], distances RGBA8 [H,W], fp32 [H,W,4], lookups [R])."""
+    rs, f = _params(scene, probe_count, side_length, field_origin, s, max_bounces=max_bounces)
+    W = probe_count[0] * probe_count[2] * s
+    H = probe_count[1] * s
+    r = np.ascontiguousarray(rays, dtype=np.float32)
+    alb = np.zeros((H, W), dtype=np.uint32)
+    dist = np.full((H, W), 0xdeadbeef, dtype=np.uint32)
+    f32 = np.zeros((H, W, 4), dtype=np.float32)
+    lk = np.zeros(r.shape[0], dtype=np.uint32)
+    load().ref_probe_pass(C.byref(rs), C.byref(f), r.ctypes.data, r.shape[0], W, H, alb.ctypes.data, dist.ctypes.data,
+                          f32.ctypes.data, lk.ctypes.data)
+    return alb, dist, f32, lk
+
+
+def compute_pass(*, scene, probe_count, side_length, field_origin, s, screen, cam, tex_albedo, tex_distances=None, max_bounces=8):
+    """Runs compute_pass.comp::main (render_mode 0 = DDGI) for every dispatched pixel.
+    Returns (frame RGBA8 [h,w], fp32 [h,w,4], lookups [h,w])."""
+    rs, f = _params(scene, probe_count, side_length, field_origin, s, screen=screen, max_bounces=max_bounces)
+    w, h = screen
+    t = np.ascontiguousarray(tex_albedo, dtype=np.uint32)
+    H, W = t.shape
+    d = np.zeros_like(t) if tex_distances is None else np.ascontiguousarray(tex_distances, dtype=np.uint32)
+    c = np.ascontiguousarray(cam, dtype=np.float32)
+    frame = np.zeros((h, w), dtype=np.uint32)
+    f32 = np.zeros((h, w, 4), dtype=np.float32)
+    lk = np.zeros((h, w), dtype=np.uint32)
+    load().ref_compute_pass(C.byref(rs), C.byref(f), c.ctypes.data, t.ctypes.data, d.ctypes.data, W, H, frame.ctypes.data,
+                            f32.ctypes.data, lk.ctypes.data)
+    return frame, f32, lk

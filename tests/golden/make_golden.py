@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN SHADERS run on the CPU
+(oracle/_ref/libddgi_ref.so = probe_pass.comp / compute_pass.comp transpiled where they lie
+by oracle/ref_glsl/build_ref.py).  Needs /root/reference, so it runs in the build container
+only; the fixtures are committed and travel to the GPU box.
+
+    python oracle/ref_glsl/build_ref.py && python tests/golden/make_golden.py
+
+Each fixture holds the inputs (ProbeRay list as the reference's generate_probe_rays lays it
+out, camera block) and the reference outputs: probe texture (RGBA8 + the fp32 value handed to
+imageStore), distance texture, per-invocation getBlockAt counts, frame (RGBA8 + fp32).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util  # noqa: E402
+from oracle import oracle, ref  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# name -> (scene, probe_count, side_length, field_origin, s, screen, camera origin, camera rotation)
+CASES = {
+    # BASELINE configs[0] geometry (SURVEY.md 8d cfg 1) at a 128x128 frame
+    "cornell_2x2x2": (1, (2, 2, 2), 15, (0.0, 0.0, 15.0), 8, (128, 128), (0.0, 0.0, -5.0), (0.0, 0.0, 0.0)),
+    # odd-count twin, README.md:245-247 layout
+    "cornell_3x3x3": (1, (3, 3, 3), 11, (0.0, 0.0, 15.0), 8, (128, 128), (0.0, 0.0, -5.0), (0.0, 0.0, 0.0)),
+    # the reference's cave with its procedural textures, reference camera (rvpt.cpp:212-227)
+    "cave_3x3x3": (0, (3, 3, 3), 7, (0.0, 0.0, 0.0), 8, (160, 96), (1.5, 2.0, -2.0), (-38.0, 36.0, 0.0)),
+    # scene 2 (house), two lights
+    "house_3x1x3": (2, (3, 1, 3), 9, (0.0, 0.0, 0.0), 6, (96, 64), (0.0, 0.0, -10.0), (0.0, 0.0, 0.0)),
+}
+
+
+def main():
+    import ddgi_b200
+
+    for name, (scene, pc, side, org, s, screen, cam_o, cam_r) in CASES.items():
+        sc = oracle.Scene(probe_count=pc, side_length=side, field_origin=org, rx=s, lights=oracle.default_lights(scene),
+                          scene=scene, procedural=True, literal_colors=True, screen=screen)
+        rays = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True))
+        alb, dist, f32, lk = ref.probe_pass(scene=scene, probe_count=pc, side_length=side, field_origin=org, s=s, rays=rays)
+        cam = ddgi_b200.Camera(screen[0] / float(screen[1]), cam_o, cam_r).get_data()
+        frame, frame_f32, frame_lk = ref.compute_pass(scene=scene, probe_count=pc, side_length=side, field_origin=org, s=s,
+                                                      screen=screen, cam=cam, tex_albedo=alb, tex_distances=dist)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, scene=scene, probe_count=np.array(pc), side_length=side, field_origin=np.array(org, dtype=np.float32),
+                            s=s, screen=np.array(screen), rays=rays, cam=cam, albedo=alb, distances=dist, albedo_f32=f32,
+                            lookups=lk, frame=frame, frame_f32=frame_f32, frame_lookups=frame_lk)
+        print(f"{name}: {rays.shape[0]} rays, mean getBlockAt/ray {lk.mean():.1f}, frame {screen}, {os.path.getsize(path)} bytes")
+
+
+if __name__ == "__main__":
+    main()
