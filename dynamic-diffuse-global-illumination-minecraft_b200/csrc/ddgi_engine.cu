@@ -21,7 +21,7 @@ struct ddgi_ctx {
     uint64_t launches = 0;
     int debug = 0;
     int variant = 1;
-    int march_min = 14;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
+    int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
     uint32_t* d_counter = nullptr;
 
     ddgi_render_settings rs{};

@@ -145,7 +145,8 @@ DDGI_HD void wf_begin_query(const FrameParams& P, WfRay& R)
     // and |origin| < 2^20 so that |p| stays below 2^22 over 125 cells (floor_small / add_round_up)
     bool slow = !(regular_component(R.md.x) && regular_component(R.md.y) && regular_component(R.md.z)) ||
                 !(regular_origin(origin.x) && regular_origin(origin.y) && regular_origin(origin.z));
-    R.inv = slow ? V3(0, 0, 0) : V3(rcp_exact(R.md.x), rcp_exact(R.md.y), rcp_exact(R.md.z));
+    // (irregular components produce a value that is never used: WF_MARCH_SLOW divides literally)
+    R.inv = V3(rcp_regular(R.md.x), rcp_regular(R.md.y), rcp_regular(R.md.z));
     R.sel = V3(R.md.x > 0 ? 1.0f : 0.0f, R.md.y > 0 ? 1.0f : 0.0f, R.md.z > 0 ? 1.0f : 0.0f);
     R.p = origin;
     R.t = 0.0f;

@@ -196,7 +196,7 @@ DDGI_API int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst
    state-machine kernel (default).  Results are identical. */
 DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
 /* Scheduling knob of variant 1: a warp keeps stepping its marches while at least
-   march_min/32 of the lanes that hold a ray are marching (1..32, default 14).  Results do
+   march_min/32 of the lanes that hold a ray are marching (1..32, default 16).  Results do
    not depend on it. */
 DDGI_API int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min);
 /* Cost-ordered scheduling (default on): the first ddgi_probe_update after the voxels, the

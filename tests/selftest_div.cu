@@ -2,7 +2,8 @@
 //   1. div_tenth(x) == x / 0.1f for ALL 2^32 float bit patterns (bitwise; NaN == NaN).
 //   2. div_markstein(a, d, 1/d) == a / d on `pairs` random operand pairs drawn from the DDA
 //      step's ranges: |a| in [2^-100, 1], |d| in [2^-60, 2], all mantissas, both signs.
-// Prints "tenth_mismatch=N markstein_mismatch=M pairs=K"; exit code 0 iff N == M == 0.
+//   3. rcp_regular(x) == __frcp_rn(x) == 1.0f / x for EVERY float with |x| in [2^-60, 2].
+// Prints "tenth_mismatch=N markstein_mismatch=M rcp_mismatch=R pairs=K"; exit code 0 iff all are 0.
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -29,6 +30,22 @@ __global__ void tenth_all(unsigned long long* bad, uint32_t* first)
         if (!same(want, got)) {
             local++;
             atomicMin(first, (uint32_t)b);
+        }
+    }
+    if (local) atomicAdd(bad, local);
+}
+
+// rcp_regular(x) == 1/x for every float with |x| in [2^-60, 2] (both signs)
+__global__ void rcp_all(unsigned long long* bad)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lo = 0x21800000u, hi = 0x40000000u;  // 2^-60 .. 2.0
+    unsigned long long local = 0;
+    for (uint64_t b = lo + i; b <= hi; b += stride) {
+        for (uint32_t sgn = 0; sgn < 2; sgn++) {
+            float x = __uint_as_float((uint32_t)b | (sgn << 31));
+            if (!same(__frcp_rn(x), rcp_regular(x)) || !same(1.0f / x, rcp_regular(x))) local++;
         }
     }
     if (local) atomicAdd(bad, local);
@@ -80,29 +97,31 @@ __global__ void markstein_random(uint64_t per_thread, unsigned long long* bad, f
 int main(int argc, char** argv)
 {
     uint64_t log2_pairs = argc > 1 ? strtoull(argv[1], 0, 10) : 34;
-    unsigned long long *bad, h[2] = {0, 0};
+    unsigned long long *bad, h[3] = {0, 0, 0};
     uint32_t* first;
     float* ex;
-    cudaMalloc(&bad, 16);
+    cudaMalloc(&bad, 24);
     cudaMalloc(&first, 4);
     cudaMalloc(&ex, 8);
-    cudaMemset(bad, 0, 16);
+    cudaMemset(bad, 0, 24);
     cudaMemset(first, 0xff, 4);
     cudaMemset(ex, 0, 8);
     tenth_all<<<148 * 16, 256>>>(bad, first);
     uint64_t threads = 148ull * 16 * 256;
     uint64_t per_thread = ((1ull << log2_pairs) + threads - 1) / threads;
     markstein_random<<<148 * 16, 256>>>(per_thread, bad + 1, ex);
+    rcp_all<<<148 * 16, 256>>>(bad + 2);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("cuda error %s\n", cudaGetErrorString(e)); return 2; }
     uint32_t hf;
     float hex[2];
-    cudaMemcpy(h, bad, 16, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, bad, 24, cudaMemcpyDeviceToHost);
     cudaMemcpy(&hf, first, 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(hex, ex, 8, cudaMemcpyDeviceToHost);
-    printf("tenth_mismatch=%llu markstein_mismatch=%llu pairs=%llu", h[0], h[1], (unsigned long long)(per_thread * threads));
+    printf("tenth_mismatch=%llu markstein_mismatch=%llu rcp_mismatch=%llu pairs=%llu", h[0], h[1], h[2],
+           (unsigned long long)(per_thread * threads));
     if (h[0]) printf(" first_tenth_bits=0x%08x", hf);
     if (h[1]) printf(" example a=%a d=%a", hex[0], hex[1]);
     printf("\n");
-    return (h[0] || h[1]) ? 1 : 0;
+    return (h[0] || h[1] || h[2]) ? 1 : 0;
 }
