@@ -21,6 +21,7 @@ struct ddgi_ctx {
     uint64_t launches = 0;
     int debug = 0;
     int variant = 1;
+    int color_mode = 0;  // 0 flat palette, 1 the reference's procedural colours
     int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
     uint32_t* d_counter = nullptr;
 
@@ -221,6 +222,7 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
     P->scene.occ = c->d_occ;
     P->scene.types = c->d_types;
     P->scene.palette = c->d_palette;
+    P->scene.color_mode = c->color_mode;
     for (int a = 0; a < 3; a++) {
         P->scene.vorg[a] = c->vorg[a];
         P->scene.vdim[a] = c->vdim[a];
@@ -910,6 +912,14 @@ int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min)
     if (!ctx) return DDGI_E_INVALID;
     NEED(march_min >= 1 && march_min <= 32, "march_min in [1,32]");
     ctx->march_min = march_min;
+    return DDGI_OK;
+}
+
+int ddgi_set_color_mode(ddgi_ctx* ctx, int32_t mode)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(mode == DDGI_COLOR_PALETTE || mode == DDGI_COLOR_LITERAL, "color mode must be DDGI_COLOR_PALETTE or DDGI_COLOR_LITERAL");
+    ctx->color_mode = mode;
     return DDGI_OK;
 }
 

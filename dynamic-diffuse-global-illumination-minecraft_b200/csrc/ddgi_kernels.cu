@@ -105,6 +105,7 @@ constexpr int kWfThreads = 128;
 #define DDGI_WF_MIN_BLOCKS 7  // 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
 
+template <bool kLiteral>
 __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_wavefront(const __grid_constant__ FrameParams P,
                                                                      const __grid_constant__ ProbeJob J,
                                                                      uint32_t* __restrict__ next_ray,
@@ -113,6 +114,8 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t n_rays = J.n_owned * J.rays_per_probe;
+    __shared__ float s_base[kLiteral ? 3 * kWfThreads : 1];  // procedural colour of the lane's bounce hit
+    float* stash = s_base + (kLiteral ? threadIdx.x : 0);
     WfRay R;
     R.mode = WF_FETCH;
     uint32_t k = 0xffffffffu;  // no ray yet
@@ -138,9 +141,9 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         if (best == WF_MARCH) continue;  // only marching lanes are left: lower the bar next pass
 
         if (best == WF_BOUNCE_HIT) {
-            if (R.mode == WF_BOUNCE_HIT) wf_resolve_bounce(P, R);
+            if (R.mode == WF_BOUNCE_HIT) wf_resolve_bounce<kLiteral>(P, R, stash, kWfThreads);
         } else if (best == WF_FEELER_HIT) {
-            if (R.mode == WF_FEELER_HIT) wf_resolve_feeler(P, R);
+            if (R.mode == WF_FEELER_HIT) wf_resolve_feeler<kLiteral>(P, R, stash, kWfThreads);
         } else if (best == WF_MARCH_SLOW) {
             if (R.mode == WF_MARCH_SLOW) wf_step_literal(P, R);
         } else {
@@ -302,7 +305,7 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront, kWfThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false>, kWfThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
@@ -311,7 +314,8 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
     uint32_t blocks_needed = (warps_needed + kWfThreads / 32 - 1) / (kWfThreads / 32);
     uint32_t grid = (uint32_t)(sms * blocks_per_sm);
     if (grid > blocks_needed) grid = blocks_needed;
-    probe_update_wavefront<<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    if (P.scene.color_mode != 0) probe_update_wavefront<true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    else probe_update_wavefront<false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -26,6 +26,7 @@ struct SceneView {
     int nb[3];    // bricks per axis (4 cells in x and y, 2 in z)
     float lo[3];  // (float)vorg
     float hi[3];  // (float)(vorg + vdim - 1)
+    int color_mode;  // 0: flat palette by block type, 1: the reference's procedural colours (ddgi_texture.cuh)
 };
 
 DDGI_HD int float_bits(float x)

@@ -8,7 +8,7 @@
 //   march / nearest_hit      assets/shaders/intersection.glsl:1051-1100, :1244-1301
 //   probe_direct_lighting    assets/shaders/probe_pass.comp:180-215
 #pragma once
-#include "ddgi_scene.cuh"
+#include "ddgi_texture.cuh"
 
 namespace ddgi {
 
@@ -213,7 +213,7 @@ DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32
             out.t = t;
             v3 n = face_normal(p, cell);
             out.normal = normalize(n);
-            out.base_color = scene_albedo(S, type);
+            out.base_color = scene_color(S, p, type, out.normal);
             out.emissive = V3(0, 0, 0);
             return true;
         }

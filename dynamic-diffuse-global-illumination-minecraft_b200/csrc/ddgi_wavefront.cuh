@@ -234,7 +234,12 @@ DDGI_HD void wf_aim_feeler(const FrameParams& P, WfRay& R)
 
 // WF_BOUNCE_HIT: the bounce ray's march ended.  Nearest of light sphere / block; on a
 // miss the ray is complete, else record the hit and aim the first feeler.
-DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
+// `stash` (3 floats, `stride` apart) keeps the procedural colour of the bounce hit until the
+// feelers are resolved (colour mode 1 only; the palette mode re-reads it by block type).
+// kLiteral is the colour mode as a compile-time constant: the palette kernel carries none of
+// the texture code.
+template <bool kLiteral>
+DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R, float* stash, int stride)
 {
     R.lookups += (uint32_t)R.steps;
     int which;
@@ -252,6 +257,12 @@ DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
         v3 cell = V3(ceilf(R.p.x), ceilf(R.p.y), ceilf(R.p.z));
         normal = face_normal_unit(R.p, cell);
         R.hblock = scene_type_at(P.scene, cell);
+        if (kLiteral) {
+            v3 c = block_color_literal(R.p, R.hblock, normal);
+            stash[0] = c.x;
+            stash[stride] = c.y;
+            stash[2 * stride] = c.z;
+        }
     } else {
         // a light sphere is the nearest hit (rare): redo the test for its normal
         v3 n;
@@ -272,7 +283,16 @@ DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R)
 }
 
 // WF_FEELER_HIT: the feeler to light R.phase-1 ended (probe_pass.comp:186-212).
-DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
+template <bool kLiteral>
+DDGI_HD v3 wf_base_color(const FrameParams& P, const WfRay& R, const float* stash, int stride)
+{
+    if (R.hblock < 0) return V3(0, 0, 0);  // light sphere: base_color is zero-initialised
+    if (kLiteral) return V3(stash[0], stash[stride], stash[2 * stride]);
+    return scene_albedo(P.scene, R.hblock);
+}
+
+template <bool kLiteral>
+DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R, const float* stash, int stride)
 {
     R.lookups += (uint32_t)R.steps;
     int which;
@@ -291,7 +311,7 @@ DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
             R.visible++;
         } else {
             // blocked by a voxel: ambient term, remaining lights are skipped
-            v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
+            v3 base = wf_base_color<kLiteral>(P, R, stash, stride);
             R.color = R.color + (base * 0.2f) * lambert;
             R.mode = WF_SCATTER;
             return;
@@ -301,7 +321,7 @@ DDGI_HD void wf_resolve_feeler(const FrameParams& P, WfRay& R)
     if (R.phase > P.n_lights) {
         v3 result = V3(0, 0, 0);
         if (R.visible != 0) {
-            v3 base = R.hblock >= 0 ? scene_albedo(P.scene, R.hblock) : V3(0, 0, 0);
+            v3 base = wf_base_color<kLiteral>(P, R, stash, stride);
             result = (base * R.direct) / (float)R.visible;
         }
         R.color = R.color + result;
@@ -333,6 +353,7 @@ DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction,
                                   uint32_t& lookups)
 {
     WfRay R;
+    float stash[3] = {0, 0, 0};
     wf_init(R, origin, direction, ray_index);
     if (P.max_bounces <= 0) wf_finish_ray(P, R);
     while (R.mode != WF_FETCH) {
@@ -340,8 +361,14 @@ DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction,
             case WF_MARCH: wf_step(P, R); break;
             case WF_MARCH_SLOW: wf_step_literal(P, R); break;
             case WF_QUERY: wf_begin_query(P, R); break;
-            case WF_BOUNCE_HIT: wf_resolve_bounce(P, R); break;
-            case WF_FEELER_HIT: wf_resolve_feeler(P, R); break;
+            case WF_BOUNCE_HIT:
+                if (P.scene.color_mode != 0) wf_resolve_bounce<true>(P, R, stash, 1);
+                else wf_resolve_bounce<false>(P, R, stash, 1);
+                break;
+            case WF_FEELER_HIT:
+                if (P.scene.color_mode != 0) wf_resolve_feeler<true>(P, R, stash, 1);
+                else wf_resolve_feeler<false>(P, R, stash, 1);
+                break;
             default: wf_scatter(P, R); break;
         }
     }

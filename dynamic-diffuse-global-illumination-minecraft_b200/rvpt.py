@@ -153,6 +153,10 @@ class RVPT:
             pal = palette.ctypes.data
         self._check(self._lib.ddgi_upload_voxels(self._ctx, d, o, types.ctypes.data, pal))
 
+    def set_color_mode(self, mode: int):
+        """capi.COLOR_PALETTE (flat colours) or capi.COLOR_LITERAL (the reference's procedural textures)."""
+        self._check(self._lib.ddgi_set_color_mode(self._ctx, mode))
+
     def read_voxels(self, dims) -> np.ndarray:
         out = np.empty((dims[2], dims[1], dims[0]), dtype=np.uint8)
         self._check(self._lib.ddgi_read_voxels(self._ctx, out.ctypes.data, out.nbytes))

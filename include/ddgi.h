@@ -129,6 +129,15 @@ DDGI_API int ddgi_bake_scene(ddgi_ctx* ctx, int32_t scene, const int32_t dims[3]
    cells filled at random (xorshift32, seed), six flat block types. */
 DDGI_API int ddgi_bake_synthetic(ddgi_ctx* ctx, const int32_t dims[3], const int32_t origin[3],
                         int32_t solid_permille, uint32_t seed);
+/* Albedo of a voxel hit (getColorAt, intersection.glsl:872-1047).
+   DDGI_COLOR_PALETTE (default): the flat colour of the block type from the palette — exactly
+   the reference for its flat types 2-5 (Cornell), the README's "flat colors" variant for the
+   cave.  DDGI_COLOR_LITERAL: the reference's procedural textures (worley / fbm / dots / hash of
+   the continuous hit point), evaluated on the device; with the scene baked by ddgi_bake_scene
+   over a box that holds every probe this reproduces the reference's textured cave. */
+#define DDGI_COLOR_PALETTE 0
+#define DDGI_COLOR_LITERAL 1
+DDGI_API int ddgi_set_color_mode(ddgi_ctx* ctx, int32_t mode);
 /* Copies the block types back (dims product bytes). */
 DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
 

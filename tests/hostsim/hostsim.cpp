@@ -67,6 +67,7 @@ static void build(const SimParams* S, const float* cam, Built* B)
     P.scene.occ = B->occ.data();
     P.scene.types = S->vox;
     P.scene.palette = S->palette;
+    P.scene.color_mode = S->color_mode == 0 ? 1 : 0;  // OrcParams: 0 = literal colours, 1 = palette
     P.n_lights = S->n_lights;
     for (int i = 0; i < S->n_lights; i++) {
         P.lights[i].intensity = S->lights[i].intensity;

@@ -110,3 +110,36 @@ def test_cuda_engine_reproduces_the_reference_shaders_on_cornell(name, variant):
         r.probe_update()
         r.sync()
         assert np.array_equal(r.read_probe_texture(0), g["albedo"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cuda_engine_reproduces_the_reference_shaders_on_the_textured_cave(variant):
+    """Colour mode DDGI_COLOR_LITERAL: the reference's procedural cave textures on the device.
+    The cave is baked over [-64,64)^3, which holds every probe and every surface a ray from
+    them can reach, so the stored-voxel engine must match the procedural reference exactly —
+    probe texture and final frame, bytes, fp32 bits and getBlockAt counts."""
+    g = np.load(os.path.join(HERE, "golden", "cave_3x3x3.npz"))
+    w, h = (int(v) for v in g["screen"])
+    with ddgi_b200.RVPT(w, h) as r:
+        r.set_debug(True)
+        r.render_settings.scene = 0
+        r.ir.probe_count[:] = (3, 3, 3)
+        r.ir.side_length = 7
+        r.ir.sqrt_rays_per_probe = 8
+        r.ir.field_origin[:] = (0.0, 0.0, 0.0)
+        r.scene_camera = ddgi_b200.Camera(w / float(h), (1.5, 2.0, -2.0), (-38.0, 36.0, 0.0))
+        r.bake_scene((128, 128, 128), (-64, -64, -64), scene=0)
+        r.set_color_mode(ddgi_b200.capi.COLOR_LITERAL)
+        r.set_kernel_variant(variant)
+        r.set_probe_rays(g["rays"])
+        r.update(advance_time=False)
+        assert np.array_equal(r.scene_camera.get_data().view(np.uint32), g["cam"].view(np.uint32))
+        r.draw()
+        r.sync()
+        assert np.array_equal(r.read_lookup_counts(0), g["lookups"])
+        assert np.array_equal(r.read_probe_texture(0, ddgi_b200.capi.FMT_F32).view(np.uint32), g["albedo_f32"].view(np.uint32))
+        assert np.array_equal(r.read_probe_texture(0), g["albedo"])
+        assert np.array_equal(r.read_lookup_counts(1).reshape(h, w), g["frame_lookups"])
+        assert np.array_equal(r.read_frame(ddgi_b200.capi.FMT_F32).view(np.uint32), g["frame_f32"].view(np.uint32))
+        assert np.array_equal(r.read_frame(), g["frame"])

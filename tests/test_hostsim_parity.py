@@ -81,3 +81,30 @@ def test_frame_headers_match_oracle():
     assert np.array_equal(lk, want_lk)
     assert np.array_equal(f32.view(np.uint32), want_f32.view(np.uint32))
     assert np.array_equal(frame, want)
+
+
+def test_literal_colour_mode_matches_oracle_on_the_textured_cave():
+    """Colour mode 1 (csrc/ddgi_texture.cuh: worley / fbm / dots / hash textures of
+    intersection.glsl:872-1047) on the baked cave against the oracle's literal procedural mode,
+    which tests/test_golden_reference.py pins to the reference's own shaders."""
+    g = np.load(__import__("os").path.join(util.ROOT, "tests", "golden", "cave_3x3x3.npz"))
+    vox = oracle.bake_scene(0, (128, 128, 128), (-64, -64, -64))
+    sc = oracle.Scene(probe_count=(3, 3, 3), side_length=7, field_origin=(0.0, 0.0, 0.0), rx=8, lights=oracle.default_lights(0),
+                      scene=0, voxels=vox, vorg=(-64, -64, -64), literal_colors=True, screen=tuple(int(v) for v in g["screen"]))
+    rays = g["rays"]
+    for variant in (0, 1):
+        alb, f32, lk = _sim_probe_update(sc, rays, variant)
+        assert np.array_equal(lk, g["lookups"])
+        assert np.array_equal(f32.view(np.uint32), g["albedo_f32"].view(np.uint32))
+        assert np.array_equal(alb, g["albedo"])
+    hs = util.hostsim()
+    w, h = sc.p.screen_width, sc.p.screen_height
+    frame = np.zeros((h, w), dtype=np.uint32)
+    f32 = np.zeros((h, w, 4), dtype=np.float32)
+    lk = np.zeros((h, w), dtype=np.uint32)
+    cam = np.ascontiguousarray(g["cam"])
+    tex = np.ascontiguousarray(g["albedo"])
+    hs.sim_render_frame(C.byref(sc.p), cam.ctypes.data, tex.ctypes.data, frame.ctypes.data, f32.ctypes.data, lk.ctypes.data)
+    assert np.array_equal(lk, g["frame_lookups"])
+    assert np.array_equal(f32.view(np.uint32), g["frame_f32"].view(np.uint32))
+    assert np.array_equal(frame, g["frame"])
