@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("DDGI_LIB") or os.path.join(_HERE, "libddgi_b200.so")
 OK, E_INVALID, E_CUDA, E_STATE = 0, -1, -2, -3
 FMT_RGBA8, FMT_F32 = 0, 1
 COLOR_PALETTE, COLOR_LITERAL = 0, 1
+BLEND_OVERWRITE, BLEND_HYSTERESIS = 0, 1
 MAX_LIGHTS = 8
 
 
@@ -94,6 +95,7 @@ PROTOTYPES = {
     "ddgi_bake_scene": (C.c_int, [_P, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "ddgi_bake_synthetic": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), _I32, C.c_uint32]),
     "ddgi_set_color_mode": (C.c_int, [_P, _I32]),
+    "ddgi_set_blend_mode": (C.c_int, [_P, _I32]),
     "ddgi_read_voxels": (C.c_int, [_P, _P, _SZ]),
     "ddgi_generate_probe_rays": (C.c_int, [_P, _I32]),
     "ddgi_set_ray_samples": (C.c_int, [_P, _P, _SZ]),

@@ -22,6 +22,7 @@ struct ddgi_ctx {
     int debug = 0;
     int variant = 1;
     int color_mode = 0;  // 0 flat palette, 1 the reference's procedural colours
+    int blend_mode = 0;  // 1: hysteresis blend into the previous texel (field.hysteresis)
     int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
     uint32_t* d_counter = nullptr;
 
@@ -754,6 +755,8 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         CU(cudaMemsetAsync(ctx->d_probe_cost, 0, num_probes(ctx) * sizeof(uint32_t), (cudaStream_t)stream));
         J.probe_cost = ctx->d_probe_cost;
     }
+    J.blend = ctx->blend_mode;
+    J.hysteresis = ctx->field.hysteresis;
     J.tex_w = ctx->tex_w;
     J.tex_h = ctx->tex_h;
     J.albedo = ctx->d_tex;
@@ -920,6 +923,14 @@ int ddgi_set_color_mode(ddgi_ctx* ctx, int32_t mode)
     if (!ctx) return DDGI_E_INVALID;
     NEED(mode == DDGI_COLOR_PALETTE || mode == DDGI_COLOR_LITERAL, "color mode must be DDGI_COLOR_PALETTE or DDGI_COLOR_LITERAL");
     ctx->color_mode = mode;
+    return DDGI_OK;
+}
+
+int ddgi_set_blend_mode(ddgi_ctx* ctx, int32_t mode)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(mode == DDGI_BLEND_OVERWRITE || mode == DDGI_BLEND_HYSTERESIS, "blend mode must be DDGI_BLEND_OVERWRITE or DDGI_BLEND_HYSTERESIS");
+    ctx->blend_mode = mode;
     return DDGI_OK;
 }
 

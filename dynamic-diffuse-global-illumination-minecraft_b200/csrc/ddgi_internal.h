@@ -26,6 +26,8 @@ struct ProbeJob {
     uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)
     float4* albedo_f32;   // debug: pre-quantisation values, or nullptr
     uint32_t* lookups;    // debug: per-ray voxel lookups, or nullptr
+    int blend;            // 1: blend into the old texel with `hysteresis` (probe_pass.comp:298-299 restored)
+    float hysteresis;
     int n_peers;          // fused exchange: replicas to store every texel into
     uint32_t* peer_albedo[kMaxPeers];
     uint32_t* peer_distance[kMaxPeers];

@@ -62,6 +62,7 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
                                             uint32_t lookups)
 {
     size_t t = (size_t)ty * J.tex_w + tx;
+    if (J.blend) color = blend_hysteresis(J.albedo[t], color, J.hysteresis);
     uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);
     J.albedo[t] = rgba;
     J.distance[t] = 0u;  // probe_pass.comp:276,302: distances = vec2(0)

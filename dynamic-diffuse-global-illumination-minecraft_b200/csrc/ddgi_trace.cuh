@@ -83,6 +83,14 @@ inline void light_bounds(FrameParams& P)
 DDGI_HD v3 lpos(const Light& l) { return V3(l.pos[0], l.pos[1], l.pos[2]); }
 DDGI_HD v3 lcol(const Light& l) { return V3(l.col[0], l.col[1], l.col[2]); }
 
+// The hysteresis blend the reference has commented out (probe_pass.comp:298-299):
+// old_color = imageLoad(albedo, texel).rgb; color = mix(old_color, color, hysteresis).
+DDGI_HD v3 blend_hysteresis(uint32_t old_texel, v3 color, float hysteresis)
+{
+    v3 old = unpack_rgb8(old_texel);
+    return V3(gmix(old.x, color.x, hysteresis), gmix(old.y, color.y, hysteresis), gmix(old.z, color.z, hysteresis));
+}
+
 // ------------------------------------------------------------------ RNG
 DDGI_HD uint32_t wang_hash(uint32_t seed)
 {

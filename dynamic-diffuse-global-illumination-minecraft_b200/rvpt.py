@@ -157,6 +157,10 @@ class RVPT:
         """capi.COLOR_PALETTE (flat colours) or capi.COLOR_LITERAL (the reference's procedural textures)."""
         self._check(self._lib.ddgi_set_color_mode(self._ctx, mode))
 
+    def set_blend_mode(self, mode: int):
+        """capi.BLEND_OVERWRITE (the reference as shipped) or capi.BLEND_HYSTERESIS (probe_pass.comp:298-299 restored)."""
+        self._check(self._lib.ddgi_set_blend_mode(self._ctx, mode))
+
     def read_voxels(self, dims) -> np.ndarray:
         out = np.empty((dims[2], dims[1], dims[0]), dtype=np.uint8)
         self._check(self._lib.ddgi_read_voxels(self._ctx, out.ctypes.data, out.nbytes))

@@ -138,6 +138,15 @@ DDGI_API int ddgi_bake_synthetic(ddgi_ctx* ctx, const int32_t dims[3], const int
 #define DDGI_COLOR_PALETTE 0
 #define DDGI_COLOR_LITERAL 1
 DDGI_API int ddgi_set_color_mode(ddgi_ctx* ctx, int32_t mode);
+/* How a new probe-ray colour meets the old texel.  DDGI_BLEND_OVERWRITE (default) is the
+   reference as shipped: the texel is overwritten every frame.  DDGI_BLEND_HYSTERESIS restores
+   the blend the reference has commented out (probe_pass.comp:298-299):
+   color = mix(imageLoad(albedo, texel).rgb, color, irradiance_field.hysteresis) — note that
+   the reference weights the NEW colour by `hysteresis`.  The texture then carries state from
+   frame to frame (ddgi_write_probe_texture / ddgi_read_probe_texture checkpoint it). */
+#define DDGI_BLEND_OVERWRITE 0
+#define DDGI_BLEND_HYSTERESIS 1
+DDGI_API int ddgi_set_blend_mode(ddgi_ctx* ctx, int32_t mode);
 /* Copies the block types back (dims product bytes). */
 DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
 

@@ -38,6 +38,8 @@ class OrcParams(C.Structure):
         ("max_bounces", C.c_int32),
         ("screen_width", C.c_int32),
         ("screen_height", C.c_int32),
+        ("blend_mode", C.c_int32),
+        ("hysteresis", C.c_float),
     ]
 
 
@@ -118,7 +120,7 @@ class Scene:
 
     def __init__(self, *, probe_count, side_length, field_origin, rx, ry=None, lights, scene=1,
                  voxels=None, vorg=(0, 0, 0), palette=None, max_bounces=8, screen=(0, 0), procedural=False,
-                 literal_colors=False):
+                 literal_colors=False, hysteresis=None):
         self.p = OrcParams()
         p = self.p
         p.scene_mode = 0 if procedural else 1
@@ -146,6 +148,8 @@ class Scene:
         p.field_origin[:] = tuple(field_origin)
         p.max_bounces = max_bounces
         p.screen_width, p.screen_height = screen
+        p.blend_mode = 0 if hysteresis is None else 1   # None = the reference as shipped (blend commented out)
+        p.hysteresis = 0.0 if hysteresis is None else float(hysteresis)
 
     @property
     def num_rays(self):

@@ -43,6 +43,7 @@ def load() -> C.CDLL:
         lib = C.CDLL(LIB_PATH)
         vp = C.c_void_p
         lib.ref_probe_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.ref_probe_pass_hysteresis.argtypes = lib.ref_probe_pass.argtypes
         lib.ref_compute_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
         _lib = lib
     return _lib
@@ -59,19 +60,23 @@ def _params(scene, probe_count, side_length, field_origin, s, screen=(0, 0), max
     return rs, f
 
 
-def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bounces=8):
+def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bounces=8, hysteresis=None, previous=None):
     """Runs probe_pass.comp::main for every texel.  rays: float32 [R, 12] in the reference's
-    ProbeRay layout.  Returns (albedo RGBA8 [H,W], distances RGBA8 [H,W], fp32 [H,W,4], lookups [R])."""
+    ProbeRay layout.  Returns (albedo RGBA8 [H,W], distances RGBA8 [H,W], fp32 [H,W,4], lookups [R]).
+    hysteresis=h runs the build with the reference's commented-out blend restored
+    (probe_pass.comp:298-299) on top of the texture `previous` (zeros if None)."""
     rs, f = _params(scene, probe_count, side_length, field_origin, s, max_bounces=max_bounces)
+    if hysteresis is not None:
+        f.hysteresis = float(hysteresis)
     W = probe_count[0] * probe_count[2] * s
     H = probe_count[1] * s
     r = np.ascontiguousarray(rays, dtype=np.float32)
-    alb = np.zeros((H, W), dtype=np.uint32)
+    alb = np.zeros((H, W), dtype=np.uint32) if previous is None else np.array(previous, dtype=np.uint32, copy=True)
     dist = np.full((H, W), 0xdeadbeef, dtype=np.uint32)
     f32 = np.zeros((H, W, 4), dtype=np.float32)
     lk = np.zeros(r.shape[0], dtype=np.uint32)
-    load().ref_probe_pass(C.byref(rs), C.byref(f), r.ctypes.data, r.shape[0], W, H, alb.ctypes.data, dist.ctypes.data,
-                          f32.ctypes.data, lk.ctypes.data)
+    fn = load().ref_probe_pass if hysteresis is None else load().ref_probe_pass_hysteresis
+    fn(C.byref(rs), C.byref(f), r.ctypes.data, r.shape[0], W, H, alb.ctypes.data, dist.ctypes.data, f32.ctypes.data, lk.ctypes.data)
     return alb, dist, f32, lk
 
 

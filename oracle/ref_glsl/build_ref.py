@@ -20,6 +20,8 @@ grammar — and touches only what differs:
     every invocation (GLSL evaluates them per invocation, probe_pass.comp:55-57);
   * `glsl_count_lookup();` is inserted at the top of getBlockAt so the harness can report the
     reference's own voxel-lookup count per invocation.
+A second build of probe_pass.comp (entry ref_probe_pass_hysteresis) removes the comment markers
+around the reference's own hysteresis blend (probe_pass.comp:298-299) and nothing else.
 
     python oracle/ref_glsl/build_ref.py [--reference /root/reference] [--keep-going]
 """
@@ -132,7 +134,7 @@ struct RefField { int probe_count[3]; int side_length; float hysteresis; int sqr
 '''
 
 HARNESS_PROBE = r'''
-namespace probe_pass {
+namespace %(ns)s {
 static void reinit_globals() { %(reinit)s }
 static void apply(const RefSettings* s, const RefField* f)
 {
@@ -145,15 +147,15 @@ static void apply(const RefSettings* s, const RefField* f)
     irradiance_field.sqrt_rays_per_probe = f->sqrt_rays_per_probe;
     irradiance_field.field_origin = vec3(f->field_origin[0], f->field_origin[1], f->field_origin[2]);
 }
-}  // namespace probe_pass
+}  // namespace %(ns)s
 
 // One probe_pass.comp invocation per texel of the W x H probe texture (W, H multiples of the
 // tile; invocations of the rounded-up dispatch beyond W or H are not executed, oracle PIN 6).
 extern "C" __attribute__((visibility("default")))
-void ref_probe_pass(const RefSettings* s, const RefField* f, const float* rays12, uint32_t n_rays, int W, int H,
+void %(entry)s(const RefSettings* s, const RefField* f, const float* rays12, uint32_t n_rays, int W, int H,
                     uint32_t* albedo, uint32_t* distances, float* albedo_f32, uint32_t* lookups)
 {
-    using namespace probe_pass;
+    using namespace %(ns)s;
     apply(s, f);
     std::vector<ProbeRay> list(n_rays);
     for (uint32_t k = 0; k < n_rays; k++) {
@@ -217,9 +219,19 @@ void ref_compute_pass(const RefSettings* s, const RefField* f, const float* cam2
 '''
 
 
-def build_unit(shader: str, ns: str, shader_dir: str, harness: str) -> tuple[str, list[str]]:
+HYSTERESIS_BLOCK = re.compile(
+    r"/\*(\s*vec3 old_color = vec3\(imageLoad\(probe_image_albedo, texture_coords\)\);\s*"
+    r"color = mix\(old_color, color, irradiance_field\.hysteresis\);)\*/")
+
+
+def build_unit(shader: str, ns: str, shader_dir: str, harness: str, entry: str = "", restore_hysteresis: bool = False) -> tuple[str, list[str]]:
     seen: list[str] = []
     src = resolve_includes(os.path.join(shader_dir, shader), shader_dir, seen)
+    if restore_hysteresis:
+        # the blend the reference has commented out (probe_pass.comp:298-299), comment markers removed
+        src, n = HYSTERESIS_BLOCK.subn(r"\1", src)
+        if n != 1:
+            raise SystemExit(f"{shader}: commented hysteresis block not found")
     cpp = transpile(src)
     # lookup counter at the top of getBlockAt
     cpp, n = re.subn(r"(\bint\s+getBlockAt\s*\([^)]*\)\s*\{)", r"\1 glsl_count_lookup();", cpp, count=1)
@@ -227,7 +239,7 @@ def build_unit(shader: str, ns: str, shader_dir: str, harness: str) -> tuple[str
         raise SystemExit(f"{shader}: getBlockAt not found")
     inits = file_scope_initialisers(cpp)
     reinit = " ".join(f"{name} = {expr};" for name, expr in inits)
-    body = f"namespace {ns} {{\n{cpp}\n}}  // namespace {ns}\n" + harness % {"reinit": reinit}
+    body = f"namespace {ns} {{\n{cpp}\n}}  // namespace {ns}\n" + harness % {"reinit": reinit, "ns": ns, "entry": entry}
     return body, seen
 
 
@@ -242,9 +254,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     head = '#include <vector>\n#include "../ref_glsl/glsl_shim.h"\n' + HARNESS_COMMON
     units = []
-    for shader, ns, harness in (("probe_pass.comp", "probe_pass", HARNESS_PROBE), ("compute_pass.comp", "compute_pass", HARNESS_PIXEL)):
-        body, seen = build_unit(shader, ns, shader_dir, harness)
-        path = os.path.join(OUT, shader.replace(".comp", "_ref.cpp"))
+    for shader, ns, harness, entry, hyst in (("probe_pass.comp", "probe_pass", HARNESS_PROBE, "ref_probe_pass", False),
+                                             ("probe_pass.comp", "probe_pass_hysteresis", HARNESS_PROBE, "ref_probe_pass_hysteresis", True),
+                                             ("compute_pass.comp", "compute_pass", HARNESS_PIXEL, "ref_compute_pass", False)):
+        body, seen = build_unit(shader, ns, shader_dir, harness, entry, hyst)
+        path = os.path.join(OUT, ns + "_ref.cpp")
         with open(path, "w") as f:
             f.write(f"// GENERATED by oracle/ref_glsl/build_ref.py from {shader} + {', '.join(seen)} — do not commit\n")
             f.write(head + body)

@@ -47,8 +47,15 @@ def main():
         cam = ddgi_b200.Camera(screen[0] / float(screen[1]), cam_o, cam_r).get_data()
         frame, frame_f32, frame_lk = ref.compute_pass(scene=scene, probe_count=pc, side_length=side, field_origin=org, s=s,
                                                       screen=screen, cam=cam, tex_albedo=alb, tex_distances=dist)
+        # three frames of the reference's own (commented-out) hysteresis blend, probe_pass.comp:298-299 restored
+        hyst = []
+        prev = None
+        for _ in range(3):
+            prev = ref.probe_pass(scene=scene, probe_count=pc, side_length=side, field_origin=org, s=s, rays=rays,
+                                  hysteresis=0.9, previous=prev)[0]
+            hyst.append(prev)
         path = os.path.join(HERE, name + ".npz")
-        np.savez_compressed(path, scene=scene, probe_count=np.array(pc), side_length=side, field_origin=np.array(org, dtype=np.float32),
+        np.savez_compressed(path, hysteresis=np.float32(0.9), albedo_hysteresis=np.stack(hyst), scene=scene, probe_count=np.array(pc), side_length=side, field_origin=np.array(org, dtype=np.float32),
                             s=s, screen=np.array(screen), rays=rays, cam=cam, albedo=alb, distances=dist, albedo_f32=f32,
                             lookups=lk, frame=frame, frame_f32=frame_f32, frame_lookups=frame_lk)
         print(f"{name}: {rays.shape[0]} rays, mean getBlockAt/ray {lk.mean():.1f}, frame {screen}, {os.path.getsize(path)} bytes")

@@ -29,6 +29,8 @@ struct SimParams {
     float field_origin[3];
     int32_t max_bounces;
     int32_t screen_width, screen_height;
+    int32_t blend_mode;
+    float hysteresis;
 };
 
 struct Built {
@@ -112,6 +114,7 @@ void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32
         v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n)
                             : wavefront_trace_scalar(P, o, d, (uint32_t)k, n);
         size_t t = (size_t)ty * W + tx;
+        if (S->blend_mode) c = blend_hysteresis(albedo[t], c, S->hysteresis);
         albedo[t] = pack_rgba8(c.x, c.y, c.z, 1.0f);
         if (f32) { f32[4 * t] = c.x; f32[4 * t + 1] = c.y; f32[4 * t + 2] = c.z; f32[4 * t + 3] = 1.0f; }
         if (lookups) lookups[k] = n;

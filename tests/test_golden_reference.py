@@ -54,6 +54,22 @@ def test_oracle_reproduces_the_reference_shaders(path):
     assert np.array_equal(frame, g["frame"])
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_hysteresis_mode_reproduces_the_restored_reference_blend(path):
+    """blend_mode 1 against probe_pass.comp built with the comment markers around its own
+    hysteresis blend (:298-299) removed: three successive frames from a zero texture."""
+    g = np.load(path)
+    scene, s = int(g["scene"]), int(g["s"])
+    sc = oracle.Scene(probe_count=tuple(int(v) for v in g["probe_count"]), side_length=int(g["side_length"]),
+                      field_origin=tuple(float(v) for v in g["field_origin"]), rx=s, lights=oracle.default_lights(scene),
+                      scene=scene, procedural=True, literal_colors=True, hysteresis=float(g["hysteresis"]))
+    tex = np.zeros_like(g["albedo"])
+    for want in g["albedo_hysteresis"]:
+        oracle.probe_update(sc, g["rays"], tex=tex)
+        assert np.array_equal(tex, want)
+    assert not np.array_equal(g["albedo_hysteresis"][0], g["albedo_hysteresis"][2])  # the texture does carry state
+
+
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference; prebuilt .so travels to the GPU box)")
 @pytest.mark.parametrize("scene,pc,side,org,s,cam_o,cam_r", [
     (1, (2, 3, 2), 9, (1.0, -1.0, 14.0), 6, (2.0, 1.0, -4.0), (-10.0, 8.0, 0.0)),   # even/odd mix, s not a power of two
@@ -143,3 +159,28 @@ def test_cuda_engine_reproduces_the_reference_shaders_on_the_textured_cave(varia
         assert np.array_equal(r.read_lookup_counts(1).reshape(h, w), g["frame_lookups"])
         assert np.array_equal(r.read_frame(ddgi_b200.capi.FMT_F32).view(np.uint32), g["frame_f32"].view(np.uint32))
         assert np.array_equal(r.read_frame(), g["frame"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cuda_engine_hysteresis_mode_reproduces_the_restored_reference_blend(variant):
+    """DDGI_BLEND_HYSTERESIS on Cornell against the reference shader with its own blend restored."""
+    g = np.load(os.path.join(HERE, "golden", "cornell_3x3x3.npz"))
+    cfg = util.small(util.configs.CONFIGS["cornell_3x3x3"], screen=(64, 64))
+    with ddgi_b200.RVPT(64, 64) as r:
+        util.configs.apply(r, cfg)
+        r.ir.hysteresis = float(g["hysteresis"])
+        r.set_blend_mode(ddgi_b200.capi.BLEND_HYSTERESIS)
+        r.set_kernel_variant(variant)
+        r.set_probe_rays(g["rays"])
+        r.update(advance_time=False)
+        r.write_probe_texture(np.zeros_like(g["albedo"]))
+        for want in g["albedo_hysteresis"]:
+            r.probe_update()
+            r.sync()
+            assert np.array_equal(r.read_probe_texture(0), want)
+        # checkpoint / resume: frame 3 from a re-uploaded frame 2
+        r.write_probe_texture(g["albedo_hysteresis"][1])
+        r.probe_update()
+        r.sync()
+        assert np.array_equal(r.read_probe_texture(0), g["albedo_hysteresis"][2])

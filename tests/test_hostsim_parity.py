@@ -108,3 +108,20 @@ def test_literal_colour_mode_matches_oracle_on_the_textured_cave():
     assert np.array_equal(lk, g["frame_lookups"])
     assert np.array_equal(f32.view(np.uint32), g["frame_f32"].view(np.uint32))
     assert np.array_equal(frame, g["frame"])
+
+
+def test_hysteresis_blend_in_the_engine_headers():
+    """blend_hysteresis (csrc/ddgi_trace.cuh) against the restored reference blend (golden)."""
+    g = np.load(__import__("os").path.join(util.ROOT, "tests", "golden", "cornell_2x2x2.npz"))
+    cfg = CFG["cornell_2x2x2"]
+    sc = util.oracle_scene(cfg)
+    sc.p.blend_mode = 1
+    sc.p.hysteresis = float(g["hysteresis"])
+    hs = util.hostsim()
+    W, H = sc.tex_size
+    rays = np.ascontiguousarray(g["rays"])
+    for variant in (0, 1):
+        alb = np.zeros((H, W), dtype=np.uint32)
+        for want in g["albedo_hysteresis"]:
+            hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, None, None)
+            assert np.array_equal(alb, want)
