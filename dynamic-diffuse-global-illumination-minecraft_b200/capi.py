@@ -18,6 +18,9 @@ OK, E_INVALID, E_CUDA, E_STATE = 0, -1, -2, -3
 FMT_RGBA8, FMT_F32 = 0, 1
 COLOR_PALETTE, COLOR_LITERAL = 0, 1
 BLEND_OVERWRITE, BLEND_HYSTERESIS = 0, 1
+WEIGHT_LITERAL, WEIGHT_CHEBYSHEV = 0, 1
+DISTANCE_ZERO, DISTANCE_MOMENTS = 0, 1
+RENDER_DDGI, RENDER_DIRECT, RENDER_INDIRECT, RENDER_COLOR, RENDER_NORMAL, RENDER_DEPTH = range(6)  # rvpt.h:25-31
 MAX_LIGHTS = 8
 
 
@@ -90,12 +93,16 @@ PROTOTYPES = {
     "ddgi_set_camera": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ddgi_set_lights": (C.c_int, [_P, _I32, C.POINTER(Light)]),
     "ddgi_default_lights": (C.c_int, [_I32, C.POINTER(Light), C.POINTER(_I32)]),
+    "ddgi_update_lights": (C.c_int, [_I32, C.c_float, C.POINTER(Light), _I32, C.POINTER(Light)]),
     "ddgi_cave_lights4": (C.c_int, [C.c_float, C.POINTER(Light)]),
     "ddgi_upload_voxels": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), _P, _P]),
     "ddgi_bake_scene": (C.c_int, [_P, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "ddgi_bake_synthetic": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), _I32, C.c_uint32]),
     "ddgi_set_color_mode": (C.c_int, [_P, _I32]),
     "ddgi_set_blend_mode": (C.c_int, [_P, _I32]),
+    "ddgi_set_weight_mode": (C.c_int, [_P, _I32]),
+    "ddgi_set_distance_mode": (C.c_int, [_P, _I32, C.c_float]),
+    "ddgi_edit_voxels": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), _P, _P]),
     "ddgi_read_voxels": (C.c_int, [_P, _P, _SZ]),
     "ddgi_generate_probe_rays": (C.c_int, [_P, _I32]),
     "ddgi_set_ray_samples": (C.c_int, [_P, _P, _SZ]),

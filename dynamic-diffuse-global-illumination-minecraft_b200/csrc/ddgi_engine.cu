@@ -23,6 +23,9 @@ struct ddgi_ctx {
     int variant = 1;
     int color_mode = 0;  // 0 flat palette, 1 the reference's procedural colours
     int blend_mode = 0;  // 1: hysteresis blend into the previous texel (field.hysteresis)
+    int weight_mode = 0;    // 1: Chebyshev visibility weight restored in the cage sample
+    int distance_mode = 0;  // 1: the probe pass stores first-hit distance moments
+    float distance_scale = 1.0f;
     int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
     uint32_t* d_counter = nullptr;
 
@@ -39,6 +42,8 @@ struct ddgi_ctx {
     int vdim[3] = {0, 0, 0}, vorg[3] = {0, 0, 0}, borg[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
     uint8_t* d_types = nullptr;
     uint32_t* d_occ = nullptr;  // one word per 4x4x2 brick
+    uint8_t* d_edit = nullptr;  // staging buffer of ddgi_edit_voxels
+    size_t edit_cap = 0;
     float* d_palette = nullptr;
 
     // rays
@@ -246,6 +251,10 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
     memcpy(P->cam, c->cam, sizeof(P->cam));
     // camera.glsl:37  w = 1.0/tan(0.5*hfov): a per-frame uniform, evaluated once here
     P->cam_w = 1.0f / (float)tan((double)(0.5f * c->cam[17]));
+    P->render_mode = c->rs.render_mode;
+    P->visualize_probes = c->rs.visualize_probes != 0;
+    P->weight_mode = c->weight_mode;
+    P->distance_scale = c->distance_scale;
 }
 
 // The flat-colour table of the reference's block types: 2-5 are getColorAt's own flat
@@ -294,7 +303,8 @@ static int finish_voxels(ddgi_ctx* ctx)
 {
     int l = 0;
     int shift[3] = {ctx->vorg[0] - ctx->borg[0], ctx->vorg[1] - ctx->borg[1], ctx->vorg[2] - ctx->borg[2]};
-    CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
+    int b0[3] = {0, 0, 0};
+    CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, b0, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
     ctx->launches += l;
     CU(cudaDeviceSynchronize());
     ctx->calibrated = false;  // a new scene: measure the per-probe costs again
@@ -375,6 +385,7 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_counter);
     dfree(ctx->d_types);
     dfree(ctx->d_occ);
+    dfree(ctx->d_edit);
     dfree(ctx->d_palette);
     dfree(ctx->d_dirs);
     dfree(ctx->d_rays);
@@ -400,8 +411,8 @@ int ddgi_set_render_settings(ddgi_ctx* ctx, const ddgi_render_settings* rs)
          "bad screen size");
     NEED(rs->max_bounces >= 0 && rs->max_bounces <= 64, "max_bounces out of range");
     NEED(rs->camera_mode == 0, "only the pinhole camera (camera_mode 0) is supported");
-    NEED(rs->render_mode == 0, "only the DDGI integrator (render_mode 0) is supported");
-    NEED(rs->visualize_probes == 0, "probe visualisation is not supported");
+    // render_mode: any value is legal, as in eval_integrator's switch (compute_pass.comp:58-87):
+    // 1-5 are the debug views, everything else the DDGI integrator
     CU(cudaSetDevice(ctx->device));
     ctx->rs = *rs;
     return resize_frame(ctx);
@@ -490,6 +501,37 @@ int ddgi_default_lights(int32_t scene, ddgi_light* out, int32_t* n)
     return DDGI_E_INVALID;
 }
 
+// update_lights, probe_pass.comp:217-250 (== compute_pass.comp:126-160)
+int ddgi_update_lights(int32_t scene, float time, const ddgi_light* base, int32_t n, ddgi_light* out)
+{
+    if (!base || !out || n < 0 || n > DDGI_MAX_LIGHTS || scene < 0 || scene > 2) return DDGI_E_INVALID;
+    for (int i = 0; i < n; i++) {
+        ddgi_light l = base[i];
+        if (scene == 0) {
+            float t = 0.05f * time;
+            if (i == 0) {
+                l.pos[2] = base[i].pos[2] + 10.0f * pin_cos(t * 0.1f);
+            } else {
+                float sn = pin_sin(t * 0.5f), cs = pin_cos(t * 0.5f);
+                l.pos[0] = base[i].pos[0] + (float)((i + 1) * 2) * sn;
+                l.pos[1] = base[i].pos[1] + (float)((i / 2) * 4) * sn;
+                l.pos[2] = base[i].pos[2] + (float)((i + 1) * 2) * cs;
+            }
+        } else if (scene == 1) {
+            float t = 0.005f * time;
+            float sn = pin_sin(t), cs = pin_cos(t);
+            l.pos[0] = base[i].pos[0] + (float)(i + 1) * sn;
+            l.pos[1] = base[i].pos[1] + (float)((i / 2) * 4) * sn;
+            l.pos[2] = base[i].pos[2] + (float)(i + 1) * cs;
+        } else {
+            float d = 0.00005f * time;
+            for (int a = 0; a < 3; a++) l.pos[a] = base[i].pos[a] + d;
+        }
+        out[i] = l;
+    }
+    return DDGI_OK;
+}
+
 int ddgi_cave_lights4(float time, ddgi_light* out)
 {
     if (!out) return DDGI_E_INVALID;
@@ -549,6 +591,45 @@ int ddgi_bake_synthetic(ddgi_ctx* ctx, const int32_t dims[3], const int32_t orig
     CU(launch_bake_synthetic(ctx->vdim, ctx->vorg, solid_permille, seed, ctx->d_types, 0, &l));
     ctx->launches += l;
     return finish_voxels(ctx);
+}
+
+int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[3], const uint8_t* types, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_types && ctx->d_occ, "no voxel field");
+    NEED(origin && dims && types, "null origin / dims / types");
+    int at[3], ext[3];
+    for (int a = 0; a < 3; a++) {
+        at[a] = origin[a] - ctx->vorg[a];
+        ext[a] = dims[a];
+        NEED(ext[a] > 0 && at[a] >= 0 && at[a] + ext[a] <= ctx->vdim[a], "edit box must lie inside the voxel field");
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t n = (size_t)ext[0] * ext[1] * ext[2];
+    if (n > ctx->edit_cap) {
+        CU(cudaStreamSynchronize(s));  // an earlier edit may still read the old staging buffer
+        dfree(ctx->d_edit);
+        CU(cudaMalloc(&ctx->d_edit, n));
+        ctx->edit_cap = n;
+    }
+    CU(cudaMemcpyAsync(ctx->d_edit, types, n, cudaMemcpyHostToDevice, s));
+    int l = 0;
+    CU(launch_edit_voxels(ctx->vdim, at, ext, ctx->d_edit, ctx->d_types, s, &l));
+    // the bricks the box touches (bricks are 4x4x2 cells, aligned to borg)
+    int shift[3], b0[3], bn[3];
+    for (int a = 0; a < 3; a++) {
+        int cells = a == 2 ? 2 : 4;
+        shift[a] = ctx->vorg[a] - ctx->borg[a];
+        b0[a] = (at[a] + shift[a]) / cells;
+        bn[a] = (at[a] + ext[a] - 1 + shift[a]) / cells - b0[a] + 1;
+    }
+    CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, b0, bn, ctx->d_types, ctx->d_occ, s, &l));
+    ctx->launches += l;
+    // host memory is pageable in general: the copy above has completed or been staged by the
+    // runtime when cudaMemcpyAsync returns only for pinned memory, so wait for it here
+    CU(cudaStreamSynchronize(s));
+    return DDGI_OK;
 }
 
 int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes)
@@ -757,6 +838,8 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     }
     J.blend = ctx->blend_mode;
     J.hysteresis = ctx->field.hysteresis;
+    J.distance_mode = ctx->distance_mode;
+    J.distance_scale = ctx->distance_scale;
     J.tex_w = ctx->tex_w;
     J.tex_h = ctx->tex_h;
     J.albedo = ctx->d_tex;
@@ -803,6 +886,7 @@ int ddgi_render_frame(ddgi_ctx* ctx, void* stream)
     PixelJob J;
     memset(&J, 0, sizeof(J));
     J.albedo = ctx->d_tex;
+    J.distance = ctx->d_tex + tex_texels(ctx);
     J.tex_w = ctx->tex_w;
     J.frame = ctx->d_frame;
     J.frame_f32 = ctx->debug ? ctx->d_frame_f32 : nullptr;
@@ -931,6 +1015,24 @@ int ddgi_set_blend_mode(ddgi_ctx* ctx, int32_t mode)
     if (!ctx) return DDGI_E_INVALID;
     NEED(mode == DDGI_BLEND_OVERWRITE || mode == DDGI_BLEND_HYSTERESIS, "blend mode must be DDGI_BLEND_OVERWRITE or DDGI_BLEND_HYSTERESIS");
     ctx->blend_mode = mode;
+    return DDGI_OK;
+}
+
+int ddgi_set_weight_mode(ddgi_ctx* ctx, int32_t mode)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(mode == DDGI_WEIGHT_LITERAL || mode == DDGI_WEIGHT_CHEBYSHEV, "weight mode must be DDGI_WEIGHT_LITERAL or DDGI_WEIGHT_CHEBYSHEV");
+    ctx->weight_mode = mode;
+    return DDGI_OK;
+}
+
+int ddgi_set_distance_mode(ddgi_ctx* ctx, int32_t mode, float scale)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(mode == DDGI_DISTANCE_ZERO || mode == DDGI_DISTANCE_MOMENTS, "distance mode must be DDGI_DISTANCE_ZERO or DDGI_DISTANCE_MOMENTS");
+    NEED(scale > 0.0f && scale < 1e30f, "distance scale must be positive and finite");
+    ctx->distance_mode = mode;
+    ctx->distance_scale = scale;
     return DDGI_OK;
 }
 

@@ -28,13 +28,16 @@ struct ProbeJob {
     uint32_t* lookups;    // debug: per-ray voxel lookups, or nullptr
     int blend;            // 1: blend into the old texel with `hysteresis` (probe_pass.comp:298-299 restored)
     float hysteresis;
+    int distance_mode;    // 1: store first-hit distance moments (d, d*d), d = t / distance_scale; 0: zeros as shipped
+    float distance_scale;
     int n_peers;          // fused exchange: replicas to store every texel into
     uint32_t* peer_albedo[kMaxPeers];
     uint32_t* peer_distance[kMaxPeers];
 };
 
 struct PixelJob {
-    const uint32_t* albedo;  // probe texture
+    const uint32_t* albedo;    // probe texture
+    const uint32_t* distance;  // distance texture (read only by the restored Chebyshev weight)
     int tex_w;
     uint32_t* frame;        // w*h RGBA8
     float4* frame_f32;      // debug or nullptr
@@ -48,7 +51,11 @@ cudaError_t launch_bake_scene(int scene, const int dims[3], const int org[3], ui
                               cudaStream_t s, int* launches);
 cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permille, uint32_t seed,
                                   uint8_t* types, cudaStream_t s, int* launches);
-cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const uint8_t* types,
-                                   uint32_t* occ, cudaStream_t s, int* launches);
+// Rebuilds the occupancy words of the brick box [b0, b0 + bn) from the block types.
+cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const int b0[3], const int bn[3],
+                                   const uint8_t* types, uint32_t* occ, cudaStream_t s, int* launches);
+// Copies a box of block types (device staging buffer, x fastest) into the field at grid cell `at`.
+cudaError_t launch_edit_voxels(const int dims[3], const int at[3], const int ext[3], const uint8_t* src, uint8_t* types,
+                               cudaStream_t s, int* launches);
 
 }  // namespace ddgi

@@ -58,18 +58,26 @@ __device__ __forceinline__ uint32_t shard_ray(const ProbeJob& J, uint32_t idx)
     return __ldg(J.order + slot) * J.rays_per_probe + i;
 }
 
+// `first_t`: t of the ray's first nearest-hit query (INF on a miss); only read in distance mode 1.
 __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v3 color, uint32_t k,
-                                            uint32_t lookups)
+                                            uint32_t lookups, float first_t)
 {
     size_t t = (size_t)ty * J.tex_w + tx;
     if (J.blend) color = blend_hysteresis(J.albedo[t], color, J.hysteresis);
     uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);
     J.albedo[t] = rgba;
-    J.distance[t] = 0u;  // probe_pass.comp:276,302: distances = vec2(0)
+    // probe_pass.comp:276,302: distances = vec2(0) as shipped; distance mode 1 stores the
+    // first-hit moments (d, d*d), d = t / distance_scale
+    uint32_t moments = 0u;
+    if (J.distance_mode == 1) {
+        float d = first_t / J.distance_scale;
+        moments = pack_rgba8(d, d * d, 0.0f, 0.0f);
+    }
+    J.distance[t] = moments;
 #pragma unroll 1
     for (int g = 0; g < J.n_peers; g++) {
         J.peer_albedo[g][t] = rgba;
-        J.peer_distance[g][t] = 0u;
+        J.peer_distance[g][t] = moments;
     }
     if (J.albedo_f32) J.albedo_f32[t] = make_float4(color.x, color.y, color.z, 1.0f);
     if (J.lookups) J.lookups[k] = lookups;
@@ -85,8 +93,9 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
     uint32_t k = shard_ray(J, idx);
     RayIn r = fetch_ray(P, J, k);
     uint32_t lookups = 0;
-    v3 color = trace_probe_ray(P, r.origin, r.direction, k, lookups);
-    store_texel(J, r.tx, r.ty, color, k, lookups);
+    float first_t = 0.0f;
+    v3 color = trace_probe_ray(P, r.origin, r.direction, k, lookups, &first_t);
+    store_texel(J, r.tx, r.ty, color, k, lookups, first_t);
 }
 
 // ------------------------------------------------------------------ variant 1
@@ -116,7 +125,9 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     const int lane = threadIdx.x & 31;
     const uint32_t n_rays = J.n_owned * J.rays_per_probe;
     __shared__ float s_base[kLiteral ? 3 * kWfThreads : 1];  // procedural colour of the lane's bounce hit
+    __shared__ float s_first_t[kWfThreads];                  // t of the lane's first query (distance mode 1)
     float* stash = s_base + (kLiteral ? threadIdx.x : 0);
+    const bool want_first_t = J.distance_mode == 1;
     WfRay R;
     R.mode = WF_FETCH;
     uint32_t k = 0xffffffffu;  // no ray yet
@@ -142,7 +153,10 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         if (best == WF_MARCH) continue;  // only marching lanes are left: lower the bar next pass
 
         if (best == WF_BOUNCE_HIT) {
-            if (R.mode == WF_BOUNCE_HIT) wf_resolve_bounce<kLiteral>(P, R, stash, kWfThreads);
+            if (R.mode == WF_BOUNCE_HIT) {
+                float* first_t = (want_first_t && R.bounce == 0) ? &s_first_t[threadIdx.x] : nullptr;
+                wf_resolve_bounce<kLiteral>(P, R, stash, kWfThreads, first_t);
+            }
         } else if (best == WF_FEELER_HIT) {
             if (R.mode == WF_FEELER_HIT) wf_resolve_feeler<kLiteral>(P, R, stash, kWfThreads);
         } else if (best == WF_MARCH_SLOW) {
@@ -150,7 +164,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         } else {
             // WF_FETCH: store the finished ray, take the next one
             bool need = R.mode == WF_FETCH;
-            if (need && k != 0xffffffffu) store_texel(J, tx, ty, R.color, k, R.lookups);
+            if (need && k != 0xffffffffu) store_texel(J, tx, ty, R.color, k, R.lookups, want_first_t ? s_first_t[threadIdx.x] : 0.0f);
             unsigned want = __ballot_sync(full, need);
             uint32_t cnt = (uint32_t)__popc(want);
             uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
@@ -198,6 +212,9 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
 // ------------------------------------------------------------------ pixel pass
 // The reference dispatches floor(w/16) x floor(h/16) groups of 16x16: pixels beyond
 // that are never written (src/rvpt/rvpt.cpp:1139-1140).
+// kExt = false: the DDGI frame as shipped; true: debug integrators (render_mode 1-5), probe
+// markers, restored Chebyshev weight.
+template <bool kExt>
 __global__ void __launch_bounds__(256) render_frame_kernel(const __grid_constant__ FrameParams P,
                                                            const __grid_constant__ PixelJob J)
 {
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(256) render_frame_kernel(const __grid_constant
     v3 o, d;
     pinhole_ray(P, cx, cy, &o, &d);
     uint32_t lookups = 0;
-    v3 s = shade_ddgi(P, J.albedo, J.tex_w, o, d, lookups);
+    v3 s = shade_pixel<kExt>(P, J.albedo, J.distance, J.tex_w, o, d, lookups);
     s = V3(0, 0, 0) + s;  // `sampled += ...`
     size_t at = (size_t)gy * P.screen_w + gx;
     J.frame[at] = pack_rgba8(s.x, s.y, s.z, 1.0f);
@@ -266,15 +283,16 @@ __global__ void bake_synthetic_kernel(int dx, int dy, int dz, int permille, uint
     }
 }
 
-// One thread per 4x4x2 brick: gathers 32 type bytes into the occupancy word.
-__global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, int sz, int nbx, int nby, int nbz,
-                                       const uint8_t* types, uint32_t* occ)
+// One thread per 4x4x2 brick of the brick box [b0, b0 + bn): gathers 32 type bytes into the
+// occupancy word.  The whole grid after an upload / bake, the touched bricks after an edit.
+__global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, int sz, int nbx, int nby, int b0x, int b0y,
+                                       int b0z, int bnx, int bny, int bnz, const uint8_t* types, uint32_t* occ)
 {
-    size_t nb = (size_t)nbx * nby * nbz;
+    size_t nb = (size_t)bnx * bny * bnz;
     for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
-        int bx = (int)(b % nbx);
-        int by = (int)((b / nbx) % nby);
-        int bz = (int)(b / ((size_t)nbx * nby));
+        int bx = b0x + (int)(b % bnx);
+        int by = b0y + (int)((b / bnx) % bny);
+        int bz = b0z + (int)(b / ((size_t)bnx * bny));
         uint32_t w = 0u;
         for (int z = 0; z < 2; z++)
             for (int y = 0; y < 4; y++)
@@ -285,7 +303,19 @@ __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, i
                         types[((size_t)gz * dy + gy) * dx + gx] != 0)
                         w |= 1u << (x | (y << 2) | (z << 4));
                 }
-        occ[b] = w;
+        occ[((size_t)bz * nby + by) * nbx + bx] = w;
+    }
+}
+
+// Per-frame voxel edit: copies an ex x ey x ez box of block types (x fastest) into the field at
+// grid cell (x0, y0, z0).
+__global__ void edit_voxels_kernel(int dx, int dy, int x0, int y0, int z0, int ex, int ey, int ez, const uint8_t* src,
+                                   uint8_t* types)
+{
+    size_t n = (size_t)ex * ey * ez;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % ex), y = (int)((i / ex) % ey), z = (int)(i / ((size_t)ex * ey));
+        types[((size_t)(z0 + z) * dy + (y0 + y)) * dx + (x0 + x)] = src[i];
     }
 }
 
@@ -325,7 +355,9 @@ cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStr
 {
     dim3 grid(P.screen_w / 16, P.screen_h / 16);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-    render_frame_kernel<<<grid, 256, 0, s>>>(P, J);
+    bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0;
+    if (ext) render_frame_kernel<true><<<grid, 256, 0, s>>>(P, J);
+    else render_frame_kernel<false><<<grid, 256, 0, s>>>(P, J);
     (*launches)++;
     return cudaGetLastError();
 }
@@ -356,12 +388,23 @@ cudaError_t launch_bake_synthetic(const int dims[3], const int org[3], int permi
     return cudaGetLastError();
 }
 
-cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const uint8_t* types,
-                                   uint32_t* occ, cudaStream_t s, int* launches)
+cudaError_t launch_build_occupancy(const int dims[3], const int shift[3], const int nb[3], const int b0[3], const int bn[3],
+                                   const uint8_t* types, uint32_t* occ, cudaStream_t s, int* launches)
 {
-    size_t n = (size_t)nb[0] * nb[1] * nb[2];
-    build_occupancy_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], shift[0], shift[1], shift[2], nb[0], nb[1], nb[2],
-                                                        types, occ);
+    size_t n = (size_t)bn[0] * bn[1] * bn[2];
+    if (n == 0) return cudaSuccess;
+    build_occupancy_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], dims[2], shift[0], shift[1], shift[2], nb[0], nb[1], b0[0],
+                                                        b0[1], b0[2], bn[0], bn[1], bn[2], types, occ);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_edit_voxels(const int dims[3], const int at[3], const int ext[3], const uint8_t* src, uint8_t* types,
+                               cudaStream_t s, int* launches)
+{
+    size_t n = (size_t)ext[0] * ext[1] * ext[2];
+    if (n == 0) return cudaSuccess;
+    edit_voxels_kernel<<<grid_for(n), 256, 0, s>>>(dims[0], dims[1], at[0], at[1], at[2], ext[0], ext[1], ext[2], src, types);
     (*launches)++;
     return cudaGetLastError();
 }

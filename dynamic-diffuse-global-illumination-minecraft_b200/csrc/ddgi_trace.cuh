@@ -40,6 +40,13 @@ struct FrameParams {
     // lights for a query that ends far from every one of them
     float lights_centre[3];
     float lights_radius;
+    // pixel pass: integrator (compute_pass.comp:58-87) and probe markers (integrators.glsl:45-67)
+    int render_mode;
+    int visualize_probes;
+    // 1: the reference's commented-out `weight *= chebyshevWeight` restored (intersection.glsl:1382)
+    int weight_mode;
+    // distance moments are stored and compared in units of distance_scale (1 = the reference's text)
+    float distance_scale;
 };
 
 struct Hit {
@@ -295,15 +302,19 @@ DDGI_HD v3 probe_direct_lighting(const FrameParams& P, const Hit& info, uint32_t
 }
 
 // Whole probe-ray path: up to max_bounces hits, each adding its direct term.
+// `first_t` (optional) receives t of the first query (INF on a miss, 0 without bounces).
 DDGI_HD v3 trace_probe_ray(const FrameParams& P, v3 origin, v3 direction, uint32_t ray_index,
-                           uint32_t& lookups)
+                           uint32_t& lookups, float* first_t = nullptr)
 {
     uint32_t rng = wang_hash(ray_index);
     v3 color = V3(0, 0, 0);
     v3 o = origin, d = direction;
     Hit hit;
+    if (first_t) *first_t = 0.0f;
     for (int b = 0; b < P.max_bounces; b++) {
-        if (!nearest_hit(P, o, d, hit, lookups)) break;
+        bool isect = nearest_hit(P, o, d, hit, lookups);
+        if (first_t && b == 0) *first_t = hit.t;
+        if (!isect) break;
         color = color + probe_direct_lighting(P, hit, lookups);
         o = hit.pos + hit.normal * 0.0001f;
         d = hemisphere_dir(hit.normal, rng);

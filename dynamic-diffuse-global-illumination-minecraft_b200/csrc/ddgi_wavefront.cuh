@@ -237,15 +237,17 @@ DDGI_HD void wf_aim_feeler(const FrameParams& P, WfRay& R)
 // `stash` (3 floats, `stride` apart) keeps the procedural colour of the bounce hit until the
 // feelers are resolved (colour mode 1 only; the palette mode re-reads it by block type).
 // kLiteral is the colour mode as a compile-time constant: the palette kernel carries none of
-// the texture code.
+// the texture code.  `nearest_t` (optional) receives the query's t (INF on a miss): the
+// distance-moment mode keeps it for the ray's first query.
 template <bool kLiteral>
-DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R, float* stash, int stride)
+DDGI_HD void wf_resolve_bounce(const FrameParams& P, WfRay& R, float* stash, int stride, float* nearest_t = nullptr)
 {
     R.lookups += (uint32_t)R.steps;
     int which;
     float closest = light_test(P, R.mo, R.qd, R.t, &which, nullptr);
     bool block_hit = R.t < closest;
     if (block_hit) closest = R.t;
+    if (nearest_t) *nearest_t = closest;
     if (!(closest < inf_f())) {
         wf_finish_ray(P, R);
         return;
@@ -350,8 +352,9 @@ DDGI_HD void wf_scatter(const FrameParams& P, WfRay& R)
 
 // Scalar driver (tests/hostsim): the state machine stepped for a single ray.
 DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction, uint32_t ray_index,
-                                  uint32_t& lookups)
+                                  uint32_t& lookups, float* first_t = nullptr)
 {
+    if (first_t) *first_t = 0.0f;
     WfRay R;
     float stash[3] = {0, 0, 0};
     wf_init(R, origin, direction, ray_index);
@@ -361,10 +364,12 @@ DDGI_HD v3 wavefront_trace_scalar(const FrameParams& P, v3 origin, v3 direction,
             case WF_MARCH: wf_step(P, R); break;
             case WF_MARCH_SLOW: wf_step_literal(P, R); break;
             case WF_QUERY: wf_begin_query(P, R); break;
-            case WF_BOUNCE_HIT:
-                if (P.scene.color_mode != 0) wf_resolve_bounce<true>(P, R, stash, 1);
-                else wf_resolve_bounce<false>(P, R, stash, 1);
+            case WF_BOUNCE_HIT: {
+                float* ft = R.bounce == 0 ? first_t : nullptr;
+                if (P.scene.color_mode != 0) wf_resolve_bounce<true>(P, R, stash, 1, ft);
+                else wf_resolve_bounce<false>(P, R, stash, 1, ft);
                 break;
+            }
             case WF_FEELER_HIT:
                 if (P.scene.color_mode != 0) wf_resolve_feeler<true>(P, R, stash, 1);
                 else wf_resolve_feeler<false>(P, R, stash, 1);

@@ -86,6 +86,7 @@ class RVPT:
         self.ray_tile = None  # (rx, ry) extension; None = square sqrt_rays_per_probe
         self.stream = None    # cudaStream_t as int, None = default stream
         self.lights = None    # None = the reference's table for render_settings.scene
+        self.animate_lights = False  # True = update_lights() restored: lights move with render_settings.time
         self._applied_field = None
 
     # -- plumbing -------------------------------------------------------------------
@@ -118,14 +119,21 @@ class RVPT:
             self._check(self._lib.ddgi_set_ray_tile(self._ctx, int(self.ray_tile[0]), int(self.ray_tile[1])))
 
     def _apply_lights(self):
+        arr = (capi.Light * capi.MAX_LIGHTS)()
+        n = C.c_int32()
         if self.lights is None:
-            arr = (capi.Light * capi.MAX_LIGHTS)()
-            n = C.c_int32()
             self._check(self._lib.ddgi_default_lights(self.render_settings.scene, arr, C.byref(n)))
-            self._check(self._lib.ddgi_set_lights(self._ctx, n.value, arr))
         else:
-            arr = (capi.Light * len(self.lights))(*self.lights)
-            self._check(self._lib.ddgi_set_lights(self._ctx, len(self.lights), arr))
+            n.value = len(self.lights)
+            for i, l in enumerate(self.lights):
+                arr[i] = l
+        if self.animate_lights:
+            # the `update_lights();` call both shaders have commented out (probe_pass.comp:254,
+            # compute_pass.comp:174): positions as a function of render_settings.time
+            moved = (capi.Light * capi.MAX_LIGHTS)()
+            self._check(self._lib.ddgi_update_lights(self.render_settings.scene, self.render_settings.time, arr, n.value, moved))
+            arr = moved
+        self._check(self._lib.ddgi_set_lights(self._ctx, n.value, arr))
 
     # -- scene ----------------------------------------------------------------------
     def bake_scene(self, dims, origin, scene=None):
@@ -153,6 +161,38 @@ class RVPT:
             pal = palette.ctypes.data
         self._check(self._lib.ddgi_upload_voxels(self._ctx, d, o, types.ctypes.data, pal))
 
+    def edit_voxels(self, types: np.ndarray, origin):
+        """Overwrites the box of voxel ids starting at `origin` with `types` ([z, y, x] uint8) and
+        rebuilds the occupancy bricks it touches (per-frame scene edits)."""
+        types = np.ascontiguousarray(types, dtype=np.uint8)
+        dz, dy, dx = types.shape
+        d = (C.c_int32 * 3)(dx, dy, dz)
+        o = (C.c_int32 * 3)(*origin)
+        self._check(self._lib.ddgi_edit_voxels(self._ctx, o, d, types.ctypes.data, self.stream))
+
+    VOXEL_MAGIC = b"DDGIVOX1"
+
+    def save_voxels(self, path: str, dims, origin):
+        """Raw voxel file: magic, dims (x, y, z), origin, then dims product block types, x fastest."""
+        vox = self.read_voxels(dims)
+        with open(path, "wb") as f:
+            f.write(self.VOXEL_MAGIC)
+            f.write(np.array(list(dims) + list(origin), dtype="<i4").tobytes())
+            f.write(vox.tobytes())
+
+    def load_voxels(self, path: str, palette: np.ndarray | None = None):
+        """Uploads a file written by save_voxels; returns (dims, origin)."""
+        with open(path, "rb") as f:
+            if f.read(8) != self.VOXEL_MAGIC:
+                raise DDGIError(capi.E_INVALID, f"{path}: not a voxel file")
+            hdr = np.frombuffer(f.read(24), dtype="<i4")
+            dims, origin = tuple(int(v) for v in hdr[:3]), tuple(int(v) for v in hdr[3:])
+            vox = np.frombuffer(f.read(), dtype=np.uint8)
+        if vox.size != dims[0] * dims[1] * dims[2]:
+            raise DDGIError(capi.E_INVALID, f"{path}: truncated voxel file")
+        self.upload_voxels(vox.reshape(dims[2], dims[1], dims[0]), origin, palette)
+        return dims, origin
+
     def set_color_mode(self, mode: int):
         """capi.COLOR_PALETTE (flat colours) or capi.COLOR_LITERAL (the reference's procedural textures)."""
         self._check(self._lib.ddgi_set_color_mode(self._ctx, mode))
@@ -160,6 +200,14 @@ class RVPT:
     def set_blend_mode(self, mode: int):
         """capi.BLEND_OVERWRITE (the reference as shipped) or capi.BLEND_HYSTERESIS (probe_pass.comp:298-299 restored)."""
         self._check(self._lib.ddgi_set_blend_mode(self._ctx, mode))
+
+    def set_weight_mode(self, mode: int):
+        """capi.WEIGHT_LITERAL (as shipped) or capi.WEIGHT_CHEBYSHEV (intersection.glsl:1382 restored)."""
+        self._check(self._lib.ddgi_set_weight_mode(self._ctx, mode))
+
+    def set_distance_mode(self, mode: int, scale: float = 1.0):
+        """capi.DISTANCE_ZERO (as shipped) or capi.DISTANCE_MOMENTS (first-hit (d, d^2) / scale)."""
+        self._check(self._lib.ddgi_set_distance_mode(self._ctx, mode, float(scale)))
 
     def read_voxels(self, dims) -> np.ndarray:
         out = np.empty((dims[2], dims[1], dims[0]), dtype=np.uint8)
@@ -257,6 +305,37 @@ class RVPT:
             out = np.empty((h, w), dtype=np.uint32) if fmt == capi.FMT_RGBA8 else np.empty((h, w, 4), dtype=np.float32)
         self._check(self._lib.ddgi_read_frame(self._ctx, fmt, out.ctypes.data, out.nbytes))
         return out
+
+    # -- checkpoint / resume ----------------------------------------------------------
+    # The reference recomputes the probe texture from scratch every frame and has nothing to
+    # save; with the hysteresis blend the texture carries state from frame to frame.
+    CHECKPOINT_MAGIC = b"DDGIPTX1"
+
+    def save_checkpoint(self, path: str):
+        """Probe-texture dump: magic, (W, H, time) header, albedo plane, distance plane (RGBA8 rows)."""
+        w, h = self.probe_texture_size
+        with open(path, "wb") as f:
+            f.write(self.CHECKPOINT_MAGIC)
+            f.write(np.array([w, h], dtype="<i4").tobytes())
+            f.write(np.array([self.render_settings.time], dtype="<f4").tobytes())
+            f.write(self.read_probe_texture(0).astype("<u4").tobytes())
+            f.write(self.read_probe_texture(1).astype("<u4").tobytes())
+
+    def load_checkpoint(self, path: str):
+        """Restores both texture planes and render_settings.time; the field must already have the dumped shape."""
+        w, h = self.probe_texture_size
+        with open(path, "rb") as f:
+            if f.read(8) != self.CHECKPOINT_MAGIC:
+                raise DDGIError(capi.E_INVALID, f"{path}: not a probe-texture checkpoint")
+            fw, fh = np.frombuffer(f.read(8), dtype="<i4")
+            if (fw, fh) != (w, h):
+                raise DDGIError(capi.E_INVALID, f"{path}: checkpoint is {fw}x{fh}, the field's texture is {w}x{h}")
+            self.render_settings.time = float(np.frombuffer(f.read(4), dtype="<f4")[0])
+            for which in (0, 1):
+                plane = np.frombuffer(f.read(w * h * 4), dtype="<u4")
+                if plane.size != w * h:
+                    raise DDGIError(capi.E_INVALID, f"{path}: truncated checkpoint")
+                self.write_probe_texture(plane.reshape(h, w), which)
 
     # -- instrumentation / multi-GPU ------------------------------------------------
     def set_debug(self, on: bool):

@@ -52,10 +52,11 @@ typedef struct ddgi_render_settings {
     int32_t screen_height;
     int32_t max_bounces;
     int32_t camera_mode; /* only 0 (pinhole) is on the path */
-    int32_t render_mode; /* only 0 (DDGI) is on the path */
+    int32_t render_mode; /* eval_integrator, compute_pass.comp:58-87: 0 DDGI, 1 direct, 2 indirect,
+                            3 colour, 4 normal, 5 depth; any other value = DDGI (the default branch) */
     int32_t scene;       /* 0 cave, 1 Cornell, 2 house: selects the built-in baker / lights */
     float time;
-    int32_t visualize_probes; /* must be 0 */
+    int32_t visualize_probes; /* != 0: probe markers over render modes 0 and 2 (integrators.glsl:45-67) */
 } ddgi_render_settings;
 
 /* RVPT::IrradianceField, src/rvpt/rvpt.h:82-90 (48 bytes, std140) */
@@ -112,6 +113,11 @@ DDGI_API int ddgi_set_camera(ddgi_ctx* ctx, const float cam[20]);
 DDGI_API int ddgi_set_lights(ddgi_ctx* ctx, int32_t n, const ddgi_light* lights);
 /* The reference's table for `scene` (n = 1,1,2) */
 DDGI_API int ddgi_default_lights(int32_t scene, ddgi_light* out, int32_t* n);
+/* update_lights (probe_pass.comp:217-250 == compute_pass.comp:126-160): the light animation whose
+   call the reference has commented out in both main()s (probe_pass.comp:254, compute_pass.comp:174),
+   as a function of render_settings.time applied to a table of n lights of `scene` (0 cave, 1 Cornell,
+   2 house).  Pass the result to ddgi_set_lights each frame for dynamic lights. */
+DDGI_API int ddgi_update_lights(int32_t scene, float time, const ddgi_light* base, int32_t n, ddgi_light* out);
 /* The commented 4-light cave table (structs.glsl:65-69) moved by update_lights' cave
    branch (probe_pass.comp:219-235) for `time`. */
 DDGI_API int ddgi_cave_lights4(float time, ddgi_light* out);
@@ -147,6 +153,28 @@ DDGI_API int ddgi_set_color_mode(ddgi_ctx* ctx, int32_t mode);
 #define DDGI_BLEND_OVERWRITE 0
 #define DDGI_BLEND_HYSTERESIS 1
 DDGI_API int ddgi_set_blend_mode(ddgi_ctx* ctx, int32_t mode);
+/* Cage-sample weight.  DDGI_WEIGHT_LITERAL (default) is the reference as shipped: the Chebyshev
+   visibility term is computed and discarded (intersection.glsl:1367-1383).  DDGI_WEIGHT_CHEBYSHEV
+   restores the commented-out `weight *= chebyshevWeight;` (:1382), reading mean / mean^2 from the
+   distance texture exactly as that code does (sample_probe(.., 1).rg). */
+#define DDGI_WEIGHT_LITERAL 0
+#define DDGI_WEIGHT_CHEBYSHEV 1
+DDGI_API int ddgi_set_weight_mode(ddgi_ctx* ctx, int32_t mode);
+/* Distance texture.  DDGI_DISTANCE_ZERO (default) is the reference as shipped: `distances =
+   vec2(0)` (probe_pass.comp:276,302).  DDGI_DISTANCE_MOMENTS (extension; the reference has no
+   code for it) stores (d, d*d) with d = t / scale of the probe ray's first intersect_scene (INF on
+   a miss: saturates to 1 in the UNORM store); the Chebyshev weight then compares
+   length(pos - probe_pos) / scale with it.  scale = 1 leaves the restored reference text
+   unchanged (x / 1 is exact); scale ~ the probe spacing makes the RGBA8 moments useful. */
+#define DDGI_DISTANCE_ZERO 0
+#define DDGI_DISTANCE_MOMENTS 1
+DDGI_API int ddgi_set_distance_mode(ddgi_ctx* ctx, int32_t mode, float scale);
+/* Per-frame scene edit (dynamic scenes; the reference's scene is compiled into its shaders and
+   cannot change): overwrites the box of voxel ids [origin, origin + dims) with `types` (x fastest)
+   and rebuilds only the occupancy bricks it touches.  The box must lie inside the uploaded field.
+   Ordered on `stream` with the dispatches; returns when `types` may be reused.  The cost-ordered
+   schedule keeps its last calibration (results never depend on it). */
+DDGI_API int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[3], const uint8_t* types, void* stream);
 /* Copies the block types back (dims product bytes). */
 DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
 

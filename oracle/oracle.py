@@ -40,6 +40,11 @@ class OrcParams(C.Structure):
         ("screen_height", C.c_int32),
         ("blend_mode", C.c_int32),
         ("hysteresis", C.c_float),
+        ("render_mode", C.c_int32),
+        ("visualize_probes", C.c_int32),
+        ("weight_mode", C.c_int32),
+        ("distance_mode", C.c_int32),
+        ("distance_scale", C.c_float),
     ]
 
 
@@ -80,7 +85,8 @@ def load() -> C.CDLL:
     lib.orc_generate_samples.argtypes = [C.c_int, C.c_int, C.c_int, vp]
     lib.orc_generate_probe_rays.argtypes = [P, vp, vp]
     lib.orc_probe_update.argtypes = [P, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, C.c_int]
-    lib.orc_render_frame.argtypes = [P, vp, vp, vp, vp, vp, C.c_int]
+    lib.orc_render_frame.argtypes = [P, vp, vp, vp, vp, vp, vp, C.c_int]
+    lib.orc_update_lights.argtypes = [C.c_int, C.POINTER(OrcLight), C.c_int, C.c_float, C.POINTER(OrcLight)]
     lib.orc_sample_probe.argtypes = [P, vp, C.c_int, vp, vp]
     lib.orc_get_block_at.restype = C.c_int
     lib.orc_get_block_at.argtypes = [P, vp]
@@ -115,12 +121,22 @@ def cave_lights4(time: float):
     return [out[i] for i in range(4)]
 
 
+def update_lights(scene: int, lights, time: float):
+    """update_lights (probe_pass.comp:217-250 == compute_pass.comp:126-160) applied to a light table."""
+    n = len(lights)
+    base = (OrcLight * 8)(*lights)
+    out = (OrcLight * 8)()
+    load().orc_update_lights(scene, base, n, C.c_float(time), out)
+    return [out[i] for i in range(n)]
+
+
 class Scene:
     """Keeps the numpy arrays an OrcParams points into alive."""
 
     def __init__(self, *, probe_count, side_length, field_origin, rx, ry=None, lights, scene=1,
                  voxels=None, vorg=(0, 0, 0), palette=None, max_bounces=8, screen=(0, 0), procedural=False,
-                 literal_colors=False, hysteresis=None):
+                 literal_colors=False, hysteresis=None, render_mode=0, visualize_probes=False, chebyshev=False,
+                 distance_scale=None):
         self.p = OrcParams()
         p = self.p
         p.scene_mode = 0 if procedural else 1
@@ -150,6 +166,11 @@ class Scene:
         p.screen_width, p.screen_height = screen
         p.blend_mode = 0 if hysteresis is None else 1   # None = the reference as shipped (blend commented out)
         p.hysteresis = 0.0 if hysteresis is None else float(hysteresis)
+        p.render_mode = render_mode
+        p.visualize_probes = 1 if visualize_probes else 0
+        p.weight_mode = 1 if chebyshev else 0           # 1: `weight *= chebyshevWeight` restored (G:1382)
+        p.distance_mode = 0 if distance_scale is None else 1  # None = the reference as shipped: distances = vec2(0)
+        p.distance_scale = 1.0 if distance_scale is None else float(distance_scale)
 
     @property
     def num_rays(self):
@@ -189,7 +210,7 @@ def probe_update(sc: Scene, rays: np.ndarray, k0: int = 0, k1: int | None = None
     return alb, dist, f32, steps, oob
 
 
-def render_frame(sc: Scene, cam: np.ndarray, tex_albedo: np.ndarray, threads: int = 0):
+def render_frame(sc: Scene, cam: np.ndarray, tex_albedo: np.ndarray, threads: int = 0, tex_distances=None):
     """Returns (frame RGBA8 [h,w], fp32 [h,w,4], lookups [h,w])."""
     w, h = sc.p.screen_width, sc.p.screen_height
     frame = np.zeros((h, w), dtype=np.uint32)
@@ -197,7 +218,8 @@ def render_frame(sc: Scene, cam: np.ndarray, tex_albedo: np.ndarray, threads: in
     steps = np.zeros((h, w), dtype=np.uint32)
     c = np.ascontiguousarray(cam, dtype=np.float32)
     t = np.ascontiguousarray(tex_albedo, dtype=np.uint32)
-    load().orc_render_frame(C.byref(sc.p), _ptr(c), _ptr(t), _ptr(frame), _ptr(f32), _ptr(steps), threads)
+    d = np.zeros_like(t) if tex_distances is None else np.ascontiguousarray(tex_distances, dtype=np.uint32)
+    load().orc_render_frame(C.byref(sc.p), _ptr(c), _ptr(t), _ptr(d), _ptr(frame), _ptr(f32), _ptr(steps), threads)
     return frame, f32, steps
 
 

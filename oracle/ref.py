@@ -44,13 +44,17 @@ def load() -> C.CDLL:
         vp = C.c_void_p
         lib.ref_probe_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, C.c_uint32, C.c_int, C.c_int, vp, vp, vp, vp]
         lib.ref_probe_pass_hysteresis.argtypes = lib.ref_probe_pass.argtypes
+        lib.ref_probe_pass_lights.argtypes = lib.ref_probe_pass.argtypes
         lib.ref_compute_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        lib.ref_compute_pass_lights.argtypes = lib.ref_compute_pass.argtypes
+        lib.ref_compute_pass_chebyshev.argtypes = lib.ref_compute_pass.argtypes
         _lib = lib
     return _lib
 
 
-def _params(scene, probe_count, side_length, field_origin, s, screen=(0, 0), max_bounces=8, time=0.0):
-    rs = RefSettings(screen[0], screen[1], max_bounces, 0, 0, scene, time, 0)
+def _params(scene, probe_count, side_length, field_origin, s, screen=(0, 0), max_bounces=8, time=0.0, render_mode=0,
+            visualize_probes=False):
+    rs = RefSettings(screen[0], screen[1], max_bounces, 0, render_mode, scene, time, 1 if visualize_probes else 0)
     f = RefField()
     f.probe_count[:] = tuple(probe_count)
     f.side_length = side_length
@@ -60,12 +64,17 @@ def _params(scene, probe_count, side_length, field_origin, s, screen=(0, 0), max
     return rs, f
 
 
-def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bounces=8, hysteresis=None, previous=None):
+def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bounces=8, hysteresis=None, previous=None,
+               animate_lights_time=None):
     """Runs probe_pass.comp::main for every texel.  rays: float32 [R, 12] in the reference's
     ProbeRay layout.  Returns (albedo RGBA8 [H,W], distances RGBA8 [H,W], fp32 [H,W,4], lookups [R]).
     hysteresis=h runs the build with the reference's commented-out blend restored
-    (probe_pass.comp:298-299) on top of the texture `previous` (zeros if None)."""
-    rs, f = _params(scene, probe_count, side_length, field_origin, s, max_bounces=max_bounces)
+    (probe_pass.comp:298-299) on top of the texture `previous` (zeros if None).
+    animate_lights_time=t runs the build with `update_lights();` restored (probe_pass.comp:254) at
+    render_settings.time = t."""
+    assert hysteresis is None or animate_lights_time is None
+    rs, f = _params(scene, probe_count, side_length, field_origin, s, max_bounces=max_bounces,
+                    time=0.0 if animate_lights_time is None else float(animate_lights_time))
     if hysteresis is not None:
         f.hysteresis = float(hysteresis)
     W = probe_count[0] * probe_count[2] * s
@@ -76,14 +85,23 @@ def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bo
     f32 = np.zeros((H, W, 4), dtype=np.float32)
     lk = np.zeros(r.shape[0], dtype=np.uint32)
     fn = load().ref_probe_pass if hysteresis is None else load().ref_probe_pass_hysteresis
+    if animate_lights_time is not None:
+        fn = load().ref_probe_pass_lights
     fn(C.byref(rs), C.byref(f), r.ctypes.data, r.shape[0], W, H, alb.ctypes.data, dist.ctypes.data, f32.ctypes.data, lk.ctypes.data)
     return alb, dist, f32, lk
 
 
-def compute_pass(*, scene, probe_count, side_length, field_origin, s, screen, cam, tex_albedo, tex_distances=None, max_bounces=8):
-    """Runs compute_pass.comp::main (render_mode 0 = DDGI) for every dispatched pixel.
+def compute_pass(*, scene, probe_count, side_length, field_origin, s, screen, cam, tex_albedo, tex_distances=None, max_bounces=8,
+                 render_mode=0, visualize_probes=False, chebyshev=False, animate_lights_time=None):
+    """Runs compute_pass.comp::main for every dispatched pixel (render_mode selects the integrator,
+    compute_pass.comp:58-87).  chebyshev=True runs the build with `weight *= chebyshevWeight;`
+    restored (intersection.glsl:1382); animate_lights_time=t the build with `update_lights();`
+    restored (compute_pass.comp:174) at render_settings.time = t.
     Returns (frame RGBA8 [h,w], fp32 [h,w,4], lookups [h,w])."""
-    rs, f = _params(scene, probe_count, side_length, field_origin, s, screen=screen, max_bounces=max_bounces)
+    assert not (chebyshev and animate_lights_time is not None)
+    rs, f = _params(scene, probe_count, side_length, field_origin, s, screen=screen, max_bounces=max_bounces,
+                    time=0.0 if animate_lights_time is None else float(animate_lights_time), render_mode=render_mode,
+                    visualize_probes=visualize_probes)
     w, h = screen
     t = np.ascontiguousarray(tex_albedo, dtype=np.uint32)
     H, W = t.shape
@@ -92,6 +110,11 @@ def compute_pass(*, scene, probe_count, side_length, field_origin, s, screen, ca
     frame = np.zeros((h, w), dtype=np.uint32)
     f32 = np.zeros((h, w, 4), dtype=np.float32)
     lk = np.zeros((h, w), dtype=np.uint32)
-    load().ref_compute_pass(C.byref(rs), C.byref(f), c.ctypes.data, t.ctypes.data, d.ctypes.data, W, H, frame.ctypes.data,
+    fn = load().ref_compute_pass
+    if chebyshev:
+        fn = load().ref_compute_pass_chebyshev
+    if animate_lights_time is not None:
+        fn = load().ref_compute_pass_lights
+    fn(C.byref(rs), C.byref(f), c.ctypes.data, t.ctypes.data, d.ctypes.data, W, H, frame.ctypes.data,
                             f32.ctypes.data, lk.ctypes.data)
     return frame, f32, lk

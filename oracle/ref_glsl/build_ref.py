@@ -20,8 +20,12 @@ grammar — and touches only what differs:
     every invocation (GLSL evaluates them per invocation, probe_pass.comp:55-57);
   * `glsl_count_lookup();` is inserted at the top of getBlockAt so the harness can report the
     reference's own voxel-lookup count per invocation.
-A second build of probe_pass.comp (entry ref_probe_pass_hysteresis) removes the comment markers
-around the reference's own hysteresis blend (probe_pass.comp:298-299) and nothing else.
+Further builds restore lines the reference itself has commented out — comment markers removed,
+nothing else (RESTORE below):
+  ref_probe_pass_hysteresis   the hysteresis blend, probe_pass.comp:298-299;
+  ref_probe_pass_lights / ref_compute_pass_lights   the `update_lights();` call at the top of
+                              both main()s, probe_pass.comp:254 / compute_pass.comp:174;
+  ref_compute_pass_chebyshev  `weight *= chebyshevWeight;`, intersection.glsl:1382.
 
     python oracle/ref_glsl/build_ref.py [--reference /root/reference] [--keep-going]
 """
@@ -182,17 +186,17 @@ void %(entry)s(const RefSettings* s, const RefField* f, const float* rays12, uin
 '''
 
 HARNESS_PIXEL = r'''
-namespace compute_pass {
+namespace %(ns)s {
 static void reinit_globals() { %(reinit)s }
-}  // namespace compute_pass
+}  // namespace %(ns)s
 
 // One compute_pass.comp invocation per pixel of the floor(w/16) x floor(h/16) groups the
 // reference dispatches (src/rvpt/rvpt.cpp:1139-1140).  cam20 = Camera::get_data().
 extern "C" __attribute__((visibility("default")))
-void ref_compute_pass(const RefSettings* s, const RefField* f, const float* cam20, const uint32_t* tex_albedo,
+void %(entry)s(const RefSettings* s, const RefField* f, const float* cam20, const uint32_t* tex_albedo,
                       const uint32_t* tex_distances, int W, int H, uint32_t* frame, float* frame_f32, uint32_t* lookups)
 {
-    using namespace compute_pass;
+    using namespace %(ns)s;
     render_settings.screen_width = s->screen_width; render_settings.screen_height = s->screen_height;
     render_settings.max_bounces = s->max_bounces; render_settings.camera_mode = s->camera_mode;
     render_settings.render_mode = s->render_mode; render_settings.scene = s->scene;
@@ -219,19 +223,26 @@ void ref_compute_pass(const RefSettings* s, const RefField* f, const float* cam2
 '''
 
 
-HYSTERESIS_BLOCK = re.compile(
-    r"/\*(\s*vec3 old_color = vec3\(imageLoad\(probe_image_albedo, texture_coords\)\);\s*"
-    r"color = mix\(old_color, color, irradiance_field\.hysteresis\);)\*/")
+# Lines the reference has commented out, restored by removing the comment markers only.
+RESTORE = {
+    "hysteresis": (re.compile(
+        r"/\*(\s*vec3 old_color = vec3\(imageLoad\(probe_image_albedo, texture_coords\)\);\s*"
+        r"color = mix\(old_color, color, irradiance_field\.hysteresis\);)\*/"), r"\1"),
+    "lights": (re.compile(r"//(update_lights\(\);)"), r"\1"),
+    "chebyshev": (re.compile(r"//(weight \*= chebyshevWeight;)"), r"\1"),
+}
+
+LIGHT_TABLE = re.compile(r"^Light\s+(\w+)\s*\[(\w+\s*\[\s*\d+\s*\])\]\s*=\s*(\{.*?\})\s*;", re.S | re.M)
 
 
-def build_unit(shader: str, ns: str, shader_dir: str, harness: str, entry: str = "", restore_hysteresis: bool = False) -> tuple[str, list[str]]:
+def build_unit(shader: str, ns: str, shader_dir: str, harness: str, entry: str = "", restore: str = "") -> tuple[str, list[str]]:
     seen: list[str] = []
     src = resolve_includes(os.path.join(shader_dir, shader), shader_dir, seen)
-    if restore_hysteresis:
-        # the blend the reference has commented out (probe_pass.comp:298-299), comment markers removed
-        src, n = HYSTERESIS_BLOCK.subn(r"\1", src)
+    if restore:
+        pat, rep = RESTORE[restore]
+        src, n = pat.subn(rep, src)
         if n != 1:
-            raise SystemExit(f"{shader}: commented hysteresis block not found")
+            raise SystemExit(f"{shader}: commented-out {restore} line not found exactly once ({n})")
     cpp = transpile(src)
     # lookup counter at the top of getBlockAt
     cpp, n = re.subn(r"(\bint\s+getBlockAt\s*\([^)]*\)\s*\{)", r"\1 glsl_count_lookup();", cpp, count=1)
@@ -239,6 +250,15 @@ def build_unit(shader: str, ns: str, shader_dir: str, harness: str, entry: str =
         raise SystemExit(f"{shader}: getBlockAt not found")
     inits = file_scope_initialisers(cpp)
     reinit = " ".join(f"{name} = {expr};" for name, expr in inits)
+    if restore == "lights":
+        # update_lights() writes the file-scope light tables (structs.glsl:63-89); GLSL
+        # re-initialises them for every invocation like any other global
+        code_only = "".join(t if is_code else re.sub(r"[^\n]", " ", t) for is_code, t in split_comments(cpp))
+        tables = LIGHT_TABLE.findall(code_only)
+        if len(tables) != 3:
+            raise SystemExit(f"{shader}: expected 3 light tables, found {len(tables)}")
+        for name, size, init in tables:
+            reinit += f" {{ Light init_[{size}] = {' '.join(init.split())}; for (int i_ = 0; i_ < {size}; i_++) {name}[i_] = init_[i_]; }}"
     body = f"namespace {ns} {{\n{cpp}\n}}  // namespace {ns}\n" + harness % {"reinit": reinit, "ns": ns, "entry": entry}
     return body, seen
 
@@ -254,10 +274,14 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     head = '#include <vector>\n#include "../ref_glsl/glsl_shim.h"\n' + HARNESS_COMMON
     units = []
-    for shader, ns, harness, entry, hyst in (("probe_pass.comp", "probe_pass", HARNESS_PROBE, "ref_probe_pass", False),
-                                             ("probe_pass.comp", "probe_pass_hysteresis", HARNESS_PROBE, "ref_probe_pass_hysteresis", True),
-                                             ("compute_pass.comp", "compute_pass", HARNESS_PIXEL, "ref_compute_pass", False)):
-        body, seen = build_unit(shader, ns, shader_dir, harness, entry, hyst)
+    for shader, ns, harness, entry, restore in (
+            ("probe_pass.comp", "probe_pass", HARNESS_PROBE, "ref_probe_pass", ""),
+            ("probe_pass.comp", "probe_pass_hysteresis", HARNESS_PROBE, "ref_probe_pass_hysteresis", "hysteresis"),
+            ("probe_pass.comp", "probe_pass_lights", HARNESS_PROBE, "ref_probe_pass_lights", "lights"),
+            ("compute_pass.comp", "compute_pass", HARNESS_PIXEL, "ref_compute_pass", ""),
+            ("compute_pass.comp", "compute_pass_lights", HARNESS_PIXEL, "ref_compute_pass_lights", "lights"),
+            ("compute_pass.comp", "compute_pass_chebyshev", HARNESS_PIXEL, "ref_compute_pass_chebyshev", "chebyshev")):
+        body, seen = build_unit(shader, ns, shader_dir, harness, entry, restore)
         path = os.path.join(OUT, ns + "_ref.cpp")
         with open(path, "w") as f:
             f.write(f"// GENERATED by oracle/ref_glsl/build_ref.py from {shader} + {', '.join(seen)} — do not commit\n")

@@ -293,7 +293,15 @@ inline float glsl_atan(float x) { return (float)::atan((double)x); }
 inline float glsl_sqrt(float x) { return sqrtf(x); }
 inline float inversesqrt(float x) { return glsl::s_isqrt(x); }
 inline float glsl_pow(float a, float b) { return powf(a, b); }
-inline float glsl_pow(float a, int b) { return powf(a, (float)b); }
+// pow with a small non-negative integer exponent (pow(2.f, i), pow(0.5, i), pow(w, 3)): the product
+// in fp64 rounded once to fp32 (oracle PIN 11); exact for the powers of two the noise code asks for
+inline float glsl_pow(float a, int b)
+{
+    if (b < 0 || b > 64) return powf(a, (float)b);
+    double r = 1.0;
+    for (int i = 0; i < b; i++) r = r * (double)a;
+    return (float)r;
+}
 inline float glsl_exp(float x) { return expf(x); }
 inline float glsl_log(float x) { return logf(x); }
 inline float glsl_exp2(float x) { return exp2f(x); }

@@ -31,6 +31,8 @@ struct SimParams {
     int32_t screen_width, screen_height;
     int32_t blend_mode;
     float hysteresis;
+    int32_t render_mode, visualize_probes, weight_mode, distance_mode;
+    float distance_scale;
 };
 
 struct Built {
@@ -85,6 +87,10 @@ static void build(const SimParams* S, const float* cam, Built* B)
     P.max_bounces = S->max_bounces;
     P.screen_w = S->screen_width;
     P.screen_h = S->screen_height;
+    P.render_mode = S->render_mode;
+    P.visualize_probes = S->visualize_probes;
+    P.weight_mode = S->weight_mode;
+    P.distance_scale = S->distance_scale;
     if (cam) {
         memcpy(P.cam, cam, sizeof(P.cam));
         P.cam_w = 1.0f / (float)tan((double)(0.5f * cam[17]));
@@ -96,7 +102,7 @@ extern "C" {
 // variant 0: trace_probe_ray (reference loop order); variant 1: the wavefront
 // state machine stepped one lane at a time.
 void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32_t k0, uint32_t k1,
-                      int variant, uint32_t* albedo, float* f32, uint32_t* lookups)
+                      int variant, uint32_t* albedo, float* f32, uint32_t* lookups, uint32_t* distance)
 {
     Built B;
     build(S, nullptr, &B);
@@ -111,17 +117,26 @@ void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32
         int yp = p / tiles_x, xp = p - yp * tiles_x;
         int tx = xp * P.rx + f2i(r[9]), ty = yp * P.ry + f2i(r[10]);
         uint32_t n = 0;
-        v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n)
-                            : wavefront_trace_scalar(P, o, d, (uint32_t)k, n);
+        float first_t = 0.0f;
+        v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n, &first_t)
+                            : wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
         size_t t = (size_t)ty * W + tx;
         if (S->blend_mode) c = blend_hysteresis(albedo[t], c, S->hysteresis);
         albedo[t] = pack_rgba8(c.x, c.y, c.z, 1.0f);
+        if (distance) {
+            uint32_t moments = 0u;
+            if (S->distance_mode == 1) {
+                float dd = first_t / S->distance_scale;
+                moments = pack_rgba8(dd, dd * dd, 0.0f, 0.0f);
+            }
+            distance[t] = moments;
+        }
         if (f32) { f32[4 * t] = c.x; f32[4 * t + 1] = c.y; f32[4 * t + 2] = c.z; f32[4 * t + 3] = 1.0f; }
         if (lookups) lookups[k] = n;
     }
 }
 
-void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex, uint32_t* frame,
+void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex, const uint32_t* dist_tex, uint32_t* frame,
                       float* f32, uint32_t* lookups)
 {
     Built B;
@@ -137,7 +152,8 @@ void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex,
             v3 o, d;
             pinhole_ray(P, cx, cy, &o, &d);
             uint32_t n = 0;
-            v3 s = shade_ddgi(P, tex, W, o, d, n);
+            bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0;
+            v3 s = ext ? shade_pixel<true>(P, tex, dist_tex, W, o, d, n) : shade_pixel<false>(P, tex, dist_tex, W, o, d, n);
             s = V3(0, 0, 0) + s;
             size_t at = (size_t)gy * w + gx;
             frame[at] = pack_rgba8(s.x, s.y, s.z, 1.0f);

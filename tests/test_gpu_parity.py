@@ -259,7 +259,7 @@ def test_errors_are_reported_not_thrown():
         with pytest.raises(ddgi_b200.DDGIError) as e:
             r.probe_update()
         assert e.value.code == ddgi_b200.capi.E_STATE
-        r.render_settings.render_mode = 3
+        r.render_settings.camera_mode = 1  # ortho / spherical cameras are out of scope
         with pytest.raises(ddgi_b200.DDGIError) as e:
             r.update()
         assert e.value.code == ddgi_b200.capi.E_INVALID

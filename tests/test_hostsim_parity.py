@@ -20,7 +20,7 @@ def _sim_probe_update(sc, rays, variant, k0=0, k1=None):
     alb = np.zeros((H, W), dtype=np.uint32)
     f32 = np.zeros((H, W, 4), dtype=np.float32)
     lk = np.zeros(sc.num_rays, dtype=np.uint32)
-    hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, k0, k1, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data)
+    hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, k0, k1, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data, None)
     return alb, f32, lk
 
 
@@ -77,7 +77,7 @@ def test_frame_headers_match_oracle():
     frame = np.zeros((96, 96), dtype=np.uint32)
     f32 = np.zeros((96, 96, 4), dtype=np.float32)
     lk = np.zeros((96, 96), dtype=np.uint32)
-    hs.sim_render_frame(C.byref(sc.p), cam.ctypes.data, alb.ctypes.data, frame.ctypes.data, f32.ctypes.data, lk.ctypes.data)
+    hs.sim_render_frame(C.byref(sc.p), cam.ctypes.data, alb.ctypes.data, None, frame.ctypes.data, f32.ctypes.data, lk.ctypes.data)
     assert np.array_equal(lk, want_lk)
     assert np.array_equal(f32.view(np.uint32), want_f32.view(np.uint32))
     assert np.array_equal(frame, want)
@@ -104,7 +104,7 @@ def test_literal_colour_mode_matches_oracle_on_the_textured_cave():
     lk = np.zeros((h, w), dtype=np.uint32)
     cam = np.ascontiguousarray(g["cam"])
     tex = np.ascontiguousarray(g["albedo"])
-    hs.sim_render_frame(C.byref(sc.p), cam.ctypes.data, tex.ctypes.data, frame.ctypes.data, f32.ctypes.data, lk.ctypes.data)
+    hs.sim_render_frame(C.byref(sc.p), cam.ctypes.data, tex.ctypes.data, None, frame.ctypes.data, f32.ctypes.data, lk.ctypes.data)
     assert np.array_equal(lk, g["frame_lookups"])
     assert np.array_equal(f32.view(np.uint32), g["frame_f32"].view(np.uint32))
     assert np.array_equal(frame, g["frame"])
@@ -123,5 +123,5 @@ def test_hysteresis_blend_in_the_engine_headers():
     for variant in (0, 1):
         alb = np.zeros((H, W), dtype=np.uint32)
         for want in g["albedo_hysteresis"]:
-            hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, None, None)
+            hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, None, None, None)
             assert np.array_equal(alb, want)

@@ -70,7 +70,7 @@ def _worker(rank, world, port, name, out_path, block=0):
         alb = np.zeros((H, W), dtype=np.uint32)
         hs = util.hostsim()
         for y0, y1 in owned:
-            hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, y0 * per_row, y1 * per_row, 1, alb.ctypes.data, None, None)
+            hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, y0 * per_row, y1 * per_row, 1, alb.ctypes.data, None, None, None)
         mask = np.zeros(H, dtype=bool)
         for y0, y1 in owned:
             mask[y0 * ry:y1 * ry] = True
