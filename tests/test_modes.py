@@ -292,3 +292,80 @@ def test_cuda_distance_moments_and_checkpoint(variant, tmp_path):
         r.render_frame()
         r.sync()
         assert same(r.read_frame(capi.FMT_F32), want_frame[1])
+
+
+# ------------------------------------------------------------------ dynamic scenes (no reference text: its scene is compiled in)
+def test_update_lights_host_function_matches_oracle():
+    """ddgi_update_lights is a host-side function of the C-ABI: callable without a GPU."""
+    lib = capi.load()
+    for scene in (0, 1, 2):
+        base = oracle.default_lights(scene) if scene != 0 else oracle.cave_lights4(0.0)
+        if scene == 0:  # the 4-light table: exercises i >= 1
+            arr0 = (oracle.OrcLight * 8)()
+            oracle.load().orc_cave_lights4(arr0)
+            base = [arr0[i] for i in range(4)]
+        n = len(base)
+        arr = (capi.Light * 8)()
+        for i, l in enumerate(base):
+            arr[i].intensity = l.intensity
+            arr[i].col[:] = list(l.col)
+            arr[i].pos[:] = list(l.pos)
+        out = (capi.Light * 8)()
+        for t in (0.0, 2.0, 74.0, 12345.0):
+            assert lib.ddgi_update_lights(scene, t, arr, n, out) == 0
+            want = oracle.update_lights(scene, base, t)
+            for i in range(n):
+                assert same(np.array(list(out[i].pos), dtype=np.float32), np.array(list(want[i].pos), dtype=np.float32))
+                assert out[i].intensity == want[i].intensity
+    assert lib.ddgi_update_lights(3, 0.0, arr, 1, out) == capi.E_INVALID
+
+
+@pytest.mark.gpu
+def test_cuda_voxel_edit_matches_reupload_and_oracle(tmp_path):
+    """ddgi_edit_voxels: a pillar placed into (and a hole cut out of) the Cornell box frame by
+    frame; the occupancy bricks are rebuilt only where touched, the result must equal a full
+    re-upload and the oracle on the edited field."""
+    cfg = util.small(util.configs.CONFIGS["cornell_3x3x3"], screen=(64, 64))
+    vox, vorg = util.oracle_voxels(cfg)
+    vox = vox.copy()
+    rx, ry = cfg["tile"]
+    edits = [((-2, -9, 9), np.full((7, 13, 3), 4, dtype=np.uint8)),     # [z, y, x] blue pillar, odd sizes / offsets
+             ((-10, -3, 12), np.zeros((5, 5, 1), dtype=np.uint8)),       # a window in the red wall
+             ((16, 16, 31), np.full((1, 1, 1), 3, dtype=np.uint8))]      # last cell of the grid
+    with ddgi_b200.RVPT(64, 64) as r, ddgi_b200.RVPT(64, 64) as fresh:
+        r.set_debug(True)
+        util.configs.apply(r, cfg)
+        r.generate_probe_rays(reseed=True)
+        r.update(advance_time=False)
+        r.probe_update()  # calibrates the schedule on the unedited scene
+        for origin, box in edits:
+            r.edit_voxels(box, origin)
+            z0, y0, x0 = origin[2] - vorg[2], origin[1] - vorg[1], origin[0] - vorg[0]
+            vox[z0:z0 + box.shape[0], y0:y0 + box.shape[1], x0:x0 + box.shape[2]] = box
+            assert np.array_equal(r.read_voxels(cfg["voxels"][1]), vox)
+            sc = util.oracle_scene(cfg, voxels=vox)
+            rays = oracle.generate_probe_rays(sc, oracle.generate_samples(rx, ry, reseed=True))
+            want = oracle.probe_update(sc, rays)
+            for variant in (0, 1):
+                r.set_kernel_variant(variant)
+                r.draw()
+                r.sync()
+                assert np.array_equal(r.read_lookup_counts(0), want[3])
+                assert np.array_equal(r.read_probe_texture(0), want[0])
+            want_frame = oracle.render_frame(sc, util.camera_block(cfg), want[0])
+            assert np.array_equal(r.read_frame(), want_frame[0])
+        # out-of-field edits are refused, not clipped
+        with pytest.raises(ddgi_b200.DDGIError) as e:
+            r.edit_voxels(np.zeros((2, 2, 2), dtype=np.uint8), (16, 16, 31))
+        assert e.value.code == capi.E_INVALID
+        # voxel file round trip into a fresh context = the same texture
+        path = str(tmp_path / "scene.vox")
+        r.save_voxels(path, cfg["voxels"][1], vorg)
+        util.configs.apply(fresh, cfg)
+        dims, origin = fresh.load_voxels(path)
+        assert dims == tuple(cfg["voxels"][1]) and origin == tuple(vorg)
+        fresh.generate_probe_rays(reseed=True)
+        fresh.update(advance_time=False)
+        fresh.probe_update()
+        fresh.sync()
+        assert np.array_equal(fresh.read_probe_texture(0), r.read_probe_texture(0))
