@@ -117,8 +117,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="field_32")
-    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
-                    help="N > 1: fused = the kernel stores texels into every replica over NVLink; nccl = in-place all-gathers")
+    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused", "fused-nccl-barrier"],
+                    help="N > 1: fused = the kernel stores texels into every replica over NVLink, then a device-side epoch-flag "
+                         "barrier (no collective library on the data path); fused-nccl-barrier = the same stores with a 4-byte "
+                         "NCCL all-reduce as the barrier; nccl = in-place all-gathers")
     ap.add_argument("--sharding", default="cyclic", choices=["cyclic", "slab"],
                     help="N > 1: cyclic ownership (single probes with the fused exchange, blocks of probe rows with nccl) "
                          "or one contiguous slab of probe rows per rank")
@@ -127,6 +129,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1: after the timed run, check that every rank's replica of both texture planes equals a full "
+                         "single-GPU update of the same frame (untimed)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -173,7 +178,8 @@ def main():
     probe_owner = np.zeros(n_probes, dtype=np.int32)   # rank that updates each probe
     block = 0
     slab = sh.probe_row_shard(Y, rank, world)           # the rows a rank reads back (e2e) in any mode
-    if world > 1 and args.sharding == "cyclic" and args.exchange == "fused":
+    fused = args.exchange.startswith("fused")
+    if world > 1 and args.sharding == "cyclic" and fused:
         r.set_probes_cyclic(rank, world, 1)
         probe_owner = (np.arange(n_probes) % world).astype(np.int32)
         shard_desc = f"{n_probes} probes dealt round-robin to {world} ranks"
@@ -196,7 +202,7 @@ def main():
     planes = [tex[:nbytes], tex[nbytes:]]
     row_bytes = W * 4 * ry
 
-    if world > 1 and args.exchange == "fused":
+    if world > 1 and fused:
         handles = [None] * world
         dist.all_gather_object(handles, r.export_texture_handle())
         r.open_peers(handles, rank)
@@ -206,9 +212,12 @@ def main():
         if world == 1:
             return
         if args.exchange == "fused":
-            # texels were stored into every replica by the kernel; one tiny all-reduce is
-            # the cross-GPU completion barrier on the stream
-            dist.all_reduce(sync_flag)
+            # texels were stored into every replica by the kernel; the completion barrier is a
+            # one-warp kernel exchanging epoch flags through the same peer mappings
+            r.exchange_barrier()
+            return
+        if fused:
+            dist.all_reduce(sync_flag)  # the same, with a 4-byte NCCL all-reduce as the barrier
             return
         for pl in planes:
             if block:
@@ -379,6 +388,24 @@ def main():
                                 "h2d_bytes_per_step": int(n_rays * 48 + 160), "d2h_bytes_per_step": int(nbytes)}
             r.generate_probe_rays(reseed=True)
 
+    # ---- untimed: the exchanged replicas against a full local update of the same frame ----
+    verify = None
+    if args.verify and world > 1:
+        step()
+        barrier()
+        got = tex.clone()
+        if fused:
+            if args.exchange == "fused":
+                r.exchange_status()
+            r.close_peers()
+        r.set_probe_rows(0, Y)
+        r.probe_update()
+        barrier()
+        ok = torch.tensor([1 if torch.equal(got, tex) else 0], device=f"cuda:{local}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verify = {"replicas_equal_full_update": bool(int(ok[0])), "bytes_compared_per_rank": int(got.numel())}
+        fused = False  # peers are closed
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(r, cfg, args.workload)
@@ -402,6 +429,7 @@ def main():
                          "kernel_ms": kernel_ms, "bytes_per_ray": bytes_per_ray, "mean_lookups_per_ray": mean_lookups,
                          "note": "algorithmic bytes = rays x (4 B x voxel lookups of the reference algorithm + 8 B texel stores), SURVEY 8d"},
             "cpu_baseline": cpu,
+            "verify": verify,
             "fps": {"value": 1000.0 / frame_ms, "frame_ms": frame_ms, "pixel_pass_ms": pixel_ms,
                     "resolution": list(cfg["screen"])},
         }
@@ -416,7 +444,9 @@ def main():
                 pass
         print(json.dumps(out), flush=True)
     if world > 1:
-        if args.exchange == "fused":
+        if fused:
+            if args.exchange == "fused":
+                r.exchange_status()  # raises if any barrier timed out
             r.close_peers()
         dist.barrier()
         dist.destroy_process_group()

@@ -117,6 +117,8 @@ PROTOTYPES = {
     "ddgi_export_texture_handle": (C.c_int, [_P, _P]),
     "ddgi_open_peers": (C.c_int, [_P, _I32, _P, _I32]),
     "ddgi_close_peers": (C.c_int, [_P]),
+    "ddgi_exchange_barrier": (C.c_int, [_P, _P]),
+    "ddgi_exchange_status": (C.c_int, [_P]),
     "ddgi_probe_update": (C.c_int, [_P, _P]),
     "ddgi_render_frame": (C.c_int, [_P, _P]),
     "ddgi_sync": (C.c_int, [_P]),
@@ -125,9 +127,11 @@ PROTOTYPES = {
     "ddgi_write_probe_texture": (C.c_int, [_P, _I32, _P, _SZ]),
     "ddgi_read_frame": (C.c_int, [_P, _I32, _P, _SZ]),
     "ddgi_set_debug": (C.c_int, [_P, _I32]),
+    "ddgi_read_warp_times": (C.c_int, [_P, _P, _SZ, C.POINTER(_SZ)]),
     "ddgi_read_lookup_counts": (C.c_int, [_P, _I32, _P, _SZ]),
     "ddgi_set_kernel_variant": (C.c_int, [_P, _I32]),
     "ddgi_set_tuning": (C.c_int, [_P, _I32]),
+    "ddgi_set_grid_limit": (C.c_int, [_P, _I32]),
     "ddgi_set_auto_schedule": (C.c_int, [_P, _I32]),
     "ddgi_launch_count": (C.c_uint64, [_P]),
 }

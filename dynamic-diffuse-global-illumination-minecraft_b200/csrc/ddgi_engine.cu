@@ -27,6 +27,9 @@ struct ddgi_ctx {
     int distance_mode = 0;  // 1: the probe pass stores first-hit distance moments
     float distance_scale = 1.0f;
     int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
+    int grid_limit = 0;  // wavefront kernel: cap on resident blocks per SM (0 = what the occupancy allows)
+    unsigned long long* d_warp_times = nullptr;  // debug level 2
+    size_t warp_times_cap = 0, warp_times_n = 0;
     uint32_t* d_counter = nullptr;
 
     ddgi_render_settings rs{};
@@ -62,13 +65,14 @@ struct ddgi_ctx {
     int cyc_world = 0, cyc_rank = 0, cyc_block = 1;  // block-cyclic ownership when cyc_world > 0
     int cyc_unit = 0;                                // 0: blocks of probe rows, 1: blocks of probes
 
-    // schedule: the owned probes, most expensive first once calibrated
+    // schedule: the owned slots (groups of slot_rays consecutive rays of a probe), most expensive
+    // first once calibrated
     std::vector<uint32_t> order;
     uint32_t* d_order = nullptr;
-    uint32_t* d_probe_cost = nullptr;
+    uint32_t* d_slot_cost = nullptr;
     size_t order_cap = 0;
     bool order_dirty = true;   // ownership / field changed: rebuild the list
-    bool calibrated = false;   // per-probe costs of the current scene + rays are in `cost`
+    bool calibrated = false;   // per-slot costs of the current scene + rays are in `cost`
     int auto_schedule = 1;
     std::vector<uint32_t> cost;
 
@@ -79,6 +83,8 @@ struct ddgi_ctx {
     uint32_t* d_px_lookups = nullptr;
 
     // fused exchange
+    uint32_t epoch = 0;              // barriers issued since the textures were created
+    uint32_t* d_barrier_error = nullptr;
     int n_peers = 0, self_index = 0;
     void* peer_base[kMaxPeers] = {nullptr};
     bool peer_opened[kMaxPeers] = {false};
@@ -133,30 +139,41 @@ static bool owns_probe(const ddgi_ctx* c, int p)
     return (unit / c->cyc_block) % c->cyc_world == c->cyc_rank;
 }
 
-// Builds the list of owned probes (by the ownership mode: a slab of probe rows, block-cyclic
+// Rays per scheduling slot: one warp's fetch (32) when it divides rays/probe, else the probe.
+static uint32_t slot_rays(const ddgi_ctx* c)
+{
+    uint32_t rpp = (uint32_t)(c->rx * c->ry);
+    return rpp % 32u == 0 ? 32u : rpp;
+}
+static size_t num_slots(const ddgi_ctx* c) { return num_probes(c) * ((size_t)(c->rx * c->ry) / slot_rays(c)); }
+
+// Builds the list of owned slots (by the ownership mode: a slab of probe rows, block-cyclic
 // rows or block-cyclic probes) and uploads it.  With measured costs the list is sorted most
-// expensive first (ties by probe index): a probe ray's bounces and marches are one long
-// dependent chain, so the longest rays must start early or they ARE the kernel's tail.
+// expensive first (cost = the largest voxel-lookup count of the slot's rays; ties by index): a
+// probe ray's bounces and marches are one long dependent chain, so the longest rays must start
+// early or they ARE the kernel's tail, and the last slots taken must hold nothing but short rays.
 static int schedule(ddgi_ctx* ctx)
 {
     if (!ctx->order_dirty && ctx->d_order) return DDGI_OK;
-    size_t np = num_probes(ctx);
+    size_t np = num_probes(ctx), ns = num_slots(ctx);
+    uint32_t spp = (uint32_t)(ns / np);
     ctx->order.clear();
     for (size_t p = 0; p < np; p++)
-        if (owns_probe(ctx, (int)p)) ctx->order.push_back((uint32_t)p);
-    if (ctx->auto_schedule && ctx->calibrated && ctx->cost.size() == np) {
+        if (owns_probe(ctx, (int)p))
+            for (uint32_t j = 0; j < spp; j++) ctx->order.push_back((uint32_t)p * spp + j);
+    if (ctx->auto_schedule && ctx->calibrated && ctx->cost.size() == ns) {
         const std::vector<uint32_t>& c = ctx->cost;
         bool measured = true;
-        for (uint32_t p : ctx->order) measured = measured && c[p] != 0xffffffffu;
+        for (uint32_t q : ctx->order) measured = measured && c[q] != 0xffffffffu;
         if (measured)
             std::stable_sort(ctx->order.begin(), ctx->order.end(), [&c](uint32_t a, uint32_t b) { return c[a] > c[b]; });
     }
-    if (np > ctx->order_cap) {
+    if (ns > ctx->order_cap) {
         dfree(ctx->d_order);
-        dfree(ctx->d_probe_cost);
-        CU(cudaMalloc(&ctx->d_order, np * sizeof(uint32_t)));
-        CU(cudaMalloc(&ctx->d_probe_cost, np * sizeof(uint32_t)));
-        ctx->order_cap = np;
+        dfree(ctx->d_slot_cost);
+        CU(cudaMalloc(&ctx->d_order, ns * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->d_slot_cost, ns * sizeof(uint32_t)));
+        ctx->order_cap = ns;
     }
     if (!ctx->order.empty())
         CU(cudaMemcpy(ctx->d_order, ctx->order.data(), ctx->order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -178,8 +195,10 @@ static int resize_textures(ddgi_ctx* ctx)
     ctx->tex_w = w;
     ctx->tex_h = h;
     size_t n = tex_texels(ctx);
-    CU(cudaMalloc(&ctx->d_tex, 2 * n * sizeof(uint32_t)));
-    CU(cudaMemset(ctx->d_tex, 0, 2 * n * sizeof(uint32_t)));
+    // both planes, then the epoch flags of the fused exchange (ddgi_exchange_barrier)
+    CU(cudaMalloc(&ctx->d_tex, (2 * n + kFlagWords) * sizeof(uint32_t)));
+    CU(cudaMemset(ctx->d_tex, 0, (2 * n + kFlagWords) * sizeof(uint32_t)));
+    ctx->epoch = 0;
     return DDGI_OK;
 }
 
@@ -396,7 +415,9 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_frame_f32);
     dfree(ctx->d_px_lookups);
     dfree(ctx->d_order);
-    dfree(ctx->d_probe_cost);
+    dfree(ctx->d_slot_cost);
+    dfree(ctx->d_warp_times);
+    dfree(ctx->d_barrier_error);
     delete ctx;
 }
 
@@ -456,6 +477,7 @@ int ddgi_set_ray_tile(ddgi_ctx* ctx, int32_t rx, int32_t ry)
         ctx->ry = ry;
         ctx->ray_mode = 0;
         ctx->calibrated = false;
+        ctx->order_dirty = true;  // the slot count changed
         return resize_textures(ctx);
     }
     return DDGI_OK;
@@ -811,6 +833,42 @@ int ddgi_close_peers(ddgi_ctx* ctx)
     return DDGI_OK;
 }
 
+int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (ctx->n_peers < 1 || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no peers: call ddgi_open_peers first");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_barrier_error) {
+        CU(cudaMalloc(&ctx->d_barrier_error, sizeof(uint32_t)));
+        CU(cudaMemset(ctx->d_barrier_error, 0, sizeof(uint32_t)));
+    }
+    PeerBarrier B;
+    memset(&B, 0, sizeof(B));
+    B.n_ranks = ctx->n_peers;
+    B.self = ctx->self_index;
+    B.epoch = ++ctx->epoch;
+    B.timeout_ns = 5000000000ull;
+    size_t flags_at = 2 * tex_texels(ctx);
+    B.local_flags = ctx->d_tex + flags_at;
+    for (int g = 0; g < ctx->n_peers; g++) B.peer_flags[g] = (uint32_t*)ctx->peer_base[g] + flags_at;
+    B.error = ctx->d_barrier_error;
+    int l = 0;
+    CU(launch_peer_barrier(B, (cudaStream_t)stream, &l));
+    ctx->launches += l;
+    return DDGI_OK;
+}
+
+int ddgi_exchange_status(ddgi_ctx* ctx)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (!ctx->d_barrier_error) return DDGI_OK;
+    CU(cudaSetDevice(ctx->device));
+    uint32_t e = 0;
+    CU(cudaMemcpy(&e, ctx->d_barrier_error, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) return fail(ctx, DDGI_E_STATE, "a peer did not reach the exchange barrier within 5 s");
+    return DDGI_OK;
+}
+
 int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
 {
     if (!ctx) return DDGI_E_INVALID;
@@ -831,10 +889,10 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     bool calibrate = ctx->auto_schedule && !ctx->calibrated;
     J.order = ctx->d_order;
     J.n_owned = (uint32_t)ctx->order.size();
-    J.rays_per_probe = (uint32_t)(ctx->rx * ctx->ry);
+    J.slot_rays = slot_rays(ctx);
     if (calibrate) {
-        CU(cudaMemsetAsync(ctx->d_probe_cost, 0, num_probes(ctx) * sizeof(uint32_t), (cudaStream_t)stream));
-        J.probe_cost = ctx->d_probe_cost;
+        CU(cudaMemsetAsync(ctx->d_slot_cost, 0, num_slots(ctx) * sizeof(uint32_t), (cudaStream_t)stream));
+        J.slot_cost = ctx->d_slot_cost;
     }
     J.blend = ctx->blend_mode;
     J.hysteresis = ctx->field.hysteresis;
@@ -852,19 +910,30 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         J.peer_distance[J.n_peers] = (uint32_t*)ctx->peer_base[g] + tex_texels(ctx);
         J.n_peers++;
     }
+    ctx->warp_times_n = 0;
+    if (ctx->debug >= 2 && ctx->variant == 1 && P.max_bounces > 0) {
+        size_t warps = wavefront_warps(J.n_owned * J.slot_rays, ctx->grid_limit);
+        if (warps > ctx->warp_times_cap) {
+            dfree(ctx->d_warp_times);
+            CU(cudaMalloc(&ctx->d_warp_times, warps * 3 * sizeof(unsigned long long)));
+            ctx->warp_times_cap = warps;
+        }
+        J.warp_times = ctx->d_warp_times;
+        ctx->warp_times_n = warps;
+    }
     int l = 0;
-    CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, (cudaStream_t)stream, &l));
+    CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, ctx->grid_limit, (cudaStream_t)stream, &l));
     ctx->launches += l;
     if (calibrate) {
-        // First update after the scene / rays / field changed: this launch also summed the voxel
-        // lookups per probe.  Read them once (the only synchronising probe update) and list the
-        // owned probes most expensive first from now on.
-        size_t np = num_probes(ctx);
-        std::vector<uint32_t> c(np);
-        CU(cudaMemcpyAsync(c.data(), ctx->d_probe_cost, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        // First update after the scene / rays / field changed: this launch also recorded the largest
+        // voxel-lookup count per slot.  Read them once (the only synchronising probe update) and
+        // list the owned slots most expensive first from now on.
+        size_t ns = num_slots(ctx);
+        std::vector<uint32_t> c(ns);
+        CU(cudaMemcpyAsync(c.data(), ctx->d_slot_cost, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
         CU(cudaStreamSynchronize((cudaStream_t)stream));
-        if (ctx->cost.size() != np) ctx->cost.assign(np, 0xffffffffu);
-        for (uint32_t p : ctx->order) ctx->cost[p] = c[p];  // only the owned probes were measured
+        if (ctx->cost.size() != ns) ctx->cost.assign(ns, 0xffffffffu);
+        for (uint32_t q : ctx->order) ctx->cost[q] = c[q];  // only the owned slots were measured
         ctx->calibrated = true;
         ctx->order_dirty = true;
     }
@@ -967,7 +1036,27 @@ int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes)
 int ddgi_set_debug(ddgi_ctx* ctx, int32_t debug)
 {
     if (!ctx) return DDGI_E_INVALID;
-    ctx->debug = debug != 0;
+    ctx->debug = debug < 0 ? 0 : (debug > 2 ? 2 : debug);
+    return DDGI_OK;
+}
+
+int ddgi_read_warp_times(ddgi_ctx* ctx, uint64_t* dst, size_t count, size_t* n_warps)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(n_warps, "null n_warps");
+    *n_warps = ctx->warp_times_n;
+    if (!dst) return DDGI_OK;
+    NEED(count >= ctx->warp_times_n * 3, "expected 3 values per warp");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(dst, ctx->d_warp_times, ctx->warp_times_n * 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DDGI_OK;
+}
+
+int ddgi_set_grid_limit(ddgi_ctx* ctx, int32_t blocks_per_sm)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(blocks_per_sm >= 0 && blocks_per_sm <= 32, "blocks_per_sm in [0,32]");
+    ctx->grid_limit = blocks_per_sm;
     return DDGI_OK;
 }
 

@@ -13,14 +13,17 @@ constexpr int kMaxPeers = 8;
 struct ProbeJob {
     const float4* rays;   // literal 48-byte ProbeRay records (3 x float4) or nullptr
     const float* dirs;    // generated mode: rx*ry normalised directions (xyz)
-    // This shard updates the probes order[0 .. n_owned): the idx-th ray of the shard is ray
-    // idx % rays_per_probe of probe order[idx / rays_per_probe].  The host lists the owned
-    // probes most expensive first (ddgi_engine.cu: schedule), so the long rays start early and
-    // the persistent kernel's tail is short.  The order never changes a result.
+    // The unit of scheduling is a SLOT of slot_rays consecutive rays of one probe (32 = one
+    // warp's fetch = two rows of a 16x16 ray tile, i.e. neighbouring directions; the whole probe
+    // when rays/probe is not a multiple of 32).  This shard updates the slots order[0 .. n_owned):
+    // its idx-th ray is ray idx % slot_rays of slot order[idx / slot_rays], slot s holding the
+    // rays [s * slot_rays, (s + 1) * slot_rays) of the reference's ray list.  The host lists
+    // the owned slots most expensive first (ddgi_engine.cu: schedule), so the long rays start
+    // early and the persistent kernel's tail is short.  The order never changes a result.
     const uint32_t* order;
     uint32_t n_owned;
-    uint32_t rays_per_probe;
-    uint32_t* probe_cost;  // calibration launch: per-probe sum of voxel lookups, else nullptr
+    uint32_t slot_rays;
+    uint32_t* slot_cost;  // calibration launch: per-slot MAX of the rays' voxel lookups, else nullptr
     int tex_w, tex_h;
     uint32_t* albedo;     // W*H RGBA8
     uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)
@@ -30,10 +33,24 @@ struct ProbeJob {
     float hysteresis;
     int distance_mode;    // 1: store first-hit distance moments (d, d*d), d = t / distance_scale; 0: zeros as shipped
     float distance_scale;
+    unsigned long long* warp_times;  // debug level 2: per warp (start, last fetch, exit) globaltimer ns, or nullptr
     int n_peers;          // fused exchange: replicas to store every texel into
     uint32_t* peer_albedo[kMaxPeers];
     uint32_t* peer_distance[kMaxPeers];
 };
+
+// Fused exchange: the epoch flags live behind the two texture planes of every replica
+// (kFlagWords uint32 after them; slot g = the last epoch rank g has published here).
+constexpr int kFlagWords = 64;
+struct PeerBarrier {
+    int n_ranks, self;
+    uint32_t epoch;
+    unsigned long long timeout_ns;
+    uint32_t* local_flags;
+    uint32_t* peer_flags[kMaxPeers];  // by rank; [self] unused
+    uint32_t* error;                  // set to 1 when a peer did not arrive in time
+};
+cudaError_t launch_peer_barrier(const PeerBarrier& B, cudaStream_t s, int* launches);
 
 struct PixelJob {
     const uint32_t* albedo;    // probe texture
@@ -44,8 +61,10 @@ struct PixelJob {
     uint32_t* lookups;      // debug or nullptr
 };
 
+// grid_limit > 0 caps the resident blocks per SM the persistent kernel launches (tuning)
 cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
-                                int march_min, cudaStream_t s, int* launches);
+                                int march_min, int grid_limit, cudaStream_t s, int* launches);
+uint32_t wavefront_warps(uint32_t n_rays, int grid_limit);
 cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStream_t s, int* launches);
 cudaError_t launch_bake_scene(int scene, const int dims[3], const int org[3], uint8_t* types,
                               cudaStream_t s, int* launches);

@@ -53,9 +53,9 @@ __device__ __forceinline__ RayIn fetch_ray(const FrameParams& P, const ProbeJob&
 // Linear ray index (the reference's position in the ProbeRay list) of the idx-th ray of this shard.
 __device__ __forceinline__ uint32_t shard_ray(const ProbeJob& J, uint32_t idx)
 {
-    uint32_t slot = idx / J.rays_per_probe;
-    uint32_t i = idx - slot * J.rays_per_probe;
-    return __ldg(J.order + slot) * J.rays_per_probe + i;
+    uint32_t slot = idx / J.slot_rays;
+    uint32_t i = idx - slot * J.slot_rays;
+    return __ldg(J.order + slot) * J.slot_rays + i;
 }
 
 // `first_t`: t of the ray's first nearest-hit query (INF on a miss); only read in distance mode 1.
@@ -81,7 +81,7 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
     }
     if (J.albedo_f32) J.albedo_f32[t] = make_float4(color.x, color.y, color.z, 1.0f);
     if (J.lookups) J.lookups[k] = lookups;
-    if (J.probe_cost) atomicAdd(J.probe_cost + k / J.rays_per_probe, lookups);
+    if (J.slot_cost) atomicMax(J.slot_cost + k / J.slot_rays, lookups);
 }
 
 // ------------------------------------------------------------------ variant 0
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
                                                            const __grid_constant__ ProbeJob J)
 {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= J.n_owned * J.rays_per_probe) return;
+    if (idx >= J.n_owned * J.slot_rays) return;
     uint32_t k = shard_ray(J, idx);
     RayIn r = fetch_ray(P, J, k);
     uint32_t lookups = 0;
@@ -108,6 +108,12 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
 constexpr int kWfThreads = 128;
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #ifndef DDGI_WF_UNROLL
 #define DDGI_WF_UNROLL 1  // march steps per lane-count check
 #endif
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const uint32_t n_rays = J.n_owned * J.rays_per_probe;
+    const uint32_t n_rays = J.n_owned * J.slot_rays;
     __shared__ float s_base[kLiteral ? 3 * kWfThreads : 1];  // procedural colour of the lane's bounce hit
     __shared__ float s_first_t[kWfThreads];                  // t of the lane's first query (distance mode 1)
     float* stash = s_base + (kLiteral ? threadIdx.x : 0);
@@ -134,6 +140,14 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     int tx = 0, ty = 0;
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: ray indices already reserved
     bool exhausted = false;
+    // debug level 2: this warp's (start, last ray taken, exit) times; the slot address is
+    // recomputed at each use so that the normal kernel keeps no register for it
+#define DDGI_WARP_TIME(slot)                                                                                  \
+    do {                                                                                                      \
+        if (J.warp_times)                                                                                     \
+            J.warp_times[3 * (size_t)((blockIdx.x * kWfThreads + threadIdx.x) >> 5) + (slot)] = globaltimer_ns(); \
+    } while (0)
+    if (lane == 0) DDGI_WARP_TIME(0);
 
     for (;;) {
         // ---- march while at least march_min/32 of the lanes holding a ray are marching ----
@@ -174,23 +188,30 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                 idx = chunk_next + rank;
                 chunk_next += cnt;
             } else {
+                // Reserve ray indices for the warp: 32 at a time while plenty are left (one
+                // atomic per 32 rays, and a warp's lanes work on neighbouring rays), exactly the
+                // number asked for once fewer than two rays per resident lane remain — a warp
+                // must not sit on reserved rays while others run dry, or it alone is the tail.
+                const uint32_t more = cnt - avail;
+                const uint32_t take = (n_rays - chunk_end <= 2u * gridDim.x * kWfThreads) ? more : 32u;
                 uint32_t base = n_rays;
                 if (!exhausted) {
-                    if (lane == 0) base = atomicAdd(next_ray, 32u);
+                    if (lane == 0) base = atomicAdd(next_ray, take);
                     base = __shfl_sync(full, base, 0);
                 }
-                uint32_t nend = base + 32u < n_rays ? base + 32u : n_rays;
+                uint32_t nend = base + take < n_rays ? base + take : n_rays;
                 if (base >= n_rays) {
                     exhausted = true;
                     base = nend = n_rays;
                 }
                 idx = rank < avail ? chunk_next + rank : base + (rank - avail);
-                chunk_next = base + (cnt - avail);
+                chunk_next = base + more;
                 chunk_end = nend;
                 if (chunk_next > chunk_end) chunk_next = chunk_end;
             }
             if (need) {
                 if (idx < n_rays) {
+                    DDGI_WARP_TIME(1);  // (any lane: the last writer wins, same instant)
                     k = shard_ray(J, idx);
                     RayIn r = fetch_ray(P, J, k);
                     tx = r.tx;
@@ -207,6 +228,41 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         if (R.mode == WF_SCATTER) wf_scatter(P, R);
         if (R.mode == WF_QUERY) wf_begin_query(P, R);
     }
+    if (lane == 0) DDGI_WARP_TIME(2);
+#undef DDGI_WARP_TIME
+}
+
+// ------------------------------------------------------------------ fused-exchange barrier
+// Runs after the probe update on the same stream (so every texel this rank stored into its
+// peers' replicas has been performed): lane g publishes `epoch` in peer g's flag slot for this
+// rank, then waits until peer g's epoch has arrived in the local slot — i.e. until g's texels
+// are in the local replica.  One launch, no collective library on the data path.  A peer that
+// never arrives ends the wait after `timeout_ns` with *error set (never a hang).
+__global__ void peer_barrier_kernel(PeerBarrier B)
+{
+    const int g = threadIdx.x;
+    if (g >= B.n_ranks || g == B.self) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(B.peer_flags[g] + B.self) = B.epoch;
+    __threadfence_system();
+    const volatile uint32_t* mine = B.local_flags + g;
+    const unsigned long long t0 = globaltimer_ns();
+    // epochs only grow; the signed difference keeps the test right across a wrap
+    while ((int32_t)(*mine - B.epoch) < 0) {
+        if (globaltimer_ns() - t0 > B.timeout_ns) {
+            atomicExch(B.error, 1u);
+            return;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_peer_barrier(const PeerBarrier& B, cudaStream_t s, int* launches)
+{
+    peer_barrier_kernel<<<1, 32, 0, s>>>(B);
+    (*launches)++;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ pixel pass
@@ -320,17 +376,9 @@ __global__ void edit_voxels_kernel(int dx, int dy, int x0, int y0, int z0, int e
 }
 
 // ------------------------------------------------------------------ launchers
-cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
-                                int march_min, cudaStream_t s, int* launches)
+// Warps the wavefront kernel would launch for n rays (debug level 2 sizes its timing buffer by it).
+uint32_t wavefront_warps(uint32_t n, int grid_limit)
 {
-    uint32_t n = J.n_owned * J.rays_per_probe;
-    if (n == 0) return cudaSuccess;
-    if (variant == 0 || P.max_bounces <= 0) {
-        dim3 block(256), grid((n + 255) / 256);
-        probe_update_direct<<<grid, block, 0, s>>>(P, J);
-        (*launches)++;
-        return cudaGetLastError();
-    }
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
         int dev = 0;
@@ -339,12 +387,28 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false>, kWfThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
-    if (e != cudaSuccess) return e;
     uint32_t warps_needed = (n + 31) / 32;
     uint32_t blocks_needed = (warps_needed + kWfThreads / 32 - 1) / (kWfThreads / 32);
-    uint32_t grid = (uint32_t)(sms * blocks_per_sm);
+    int per_sm = grid_limit > 0 && grid_limit < blocks_per_sm ? grid_limit : blocks_per_sm;
+    uint32_t grid = (uint32_t)(sms * per_sm);
     if (grid > blocks_needed) grid = blocks_needed;
+    return grid * (kWfThreads / 32);
+}
+
+cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
+                                int march_min, int grid_limit, cudaStream_t s, int* launches)
+{
+    uint32_t n = J.n_owned * J.slot_rays;
+    if (n == 0) return cudaSuccess;
+    if (variant == 0 || P.max_bounces <= 0) {
+        dim3 block(256), grid((n + 255) / 256);
+        probe_update_direct<<<grid, block, 0, s>>>(P, J);
+        (*launches)++;
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    uint32_t grid = wavefront_warps(n, grid_limit) / (kWfThreads / 32);
     if (P.scene.color_mode != 0) probe_update_wavefront<true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
     else probe_update_wavefront<false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
     (*launches)++;

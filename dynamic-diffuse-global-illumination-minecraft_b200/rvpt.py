@@ -338,8 +338,21 @@ class RVPT:
                 self.write_probe_texture(plane.reshape(h, w), which)
 
     # -- instrumentation / multi-GPU ------------------------------------------------
-    def set_debug(self, on: bool):
-        self._check(self._lib.ddgi_set_debug(self._ctx, 1 if on else 0))
+    def set_debug(self, on):
+        """False / True, or 2 to also record per-warp start / last-fetch / exit times (read_warp_times)."""
+        self._check(self._lib.ddgi_set_debug(self._ctx, int(on)))
+
+    def read_warp_times(self) -> np.ndarray:
+        """uint64 [warps, 3]: %globaltimer ns at start, last ray taken, exit (debug level 2, variant 1)."""
+        n = C.c_size_t()
+        self._check(self._lib.ddgi_read_warp_times(self._ctx, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 3), dtype=np.uint64)
+        if n.value:
+            self._check(self._lib.ddgi_read_warp_times(self._ctx, out.ctypes.data, out.size, C.byref(n)))
+        return out
+
+    def set_grid_limit(self, blocks_per_sm: int):
+        self._check(self._lib.ddgi_set_grid_limit(self._ctx, blocks_per_sm))
 
     def set_kernel_variant(self, v: int):
         self._check(self._lib.ddgi_set_kernel_variant(self._ctx, v))
@@ -384,6 +397,14 @@ class RVPT:
     def open_peers(self, handles: list[bytes], self_index: int):
         blob = b"".join(handles)
         self._check(self._lib.ddgi_open_peers(self._ctx, len(handles), blob, self_index))
+
+    def exchange_barrier(self):
+        """Device-side completion barrier of the fused exchange (after probe_update, every rank)."""
+        self._check(self._lib.ddgi_exchange_barrier(self._ctx, self.stream))
+
+    def exchange_status(self):
+        """Raises if a peer missed an exchange barrier (synchronises)."""
+        self._check(self._lib.ddgi_exchange_status(self._ctx))
 
     def close_peers(self):
         self._check(self._lib.ddgi_close_peers(self._ctx))

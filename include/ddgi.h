@@ -214,6 +214,13 @@ DDGI_API int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** 
 DDGI_API int ddgi_export_texture_handle(ddgi_ctx* ctx, void* handle64);
 DDGI_API int ddgi_open_peers(ddgi_ctx* ctx, int32_t n_peers, const void* handles64, int32_t self_index);
 DDGI_API int ddgi_close_peers(ddgi_ctx* ctx);
+/* Completion barrier of the fused exchange, on `stream` after ddgi_probe_update: publishes this
+   rank's frame epoch in every peer's replica and waits (on the device) until every peer's epoch
+   has arrived here, i.e. until their texels are in the local replica.  One small kernel, no
+   collective library.  Every rank must call it once per frame.  A peer that does not arrive
+   within 5 s ends the wait (never a hang); ddgi_exchange_status reports it (synchronises). */
+DDGI_API int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream);
+DDGI_API int ddgi_exchange_status(ddgi_ctx* ctx);
 
 /* ---- the two dispatches ---- */
 /* vkCmdDispatch #1, probe_pass.comp (rvpt.cpp:1121-1129) */
@@ -234,8 +241,13 @@ DDGI_API int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* 
 DDGI_API int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes);
 
 /* ---- instrumentation ---- */
-/* debug != 0: keep fp32 copies of the outputs and per-invocation voxel-lookup counts. */
+/* debug >= 1: keep fp32 copies of the outputs and per-invocation voxel-lookup counts.
+   debug == 2: kernel variant 1 also records, per warp, the %globaltimer (ns) at which it started,
+   took its last ray and exited (ddgi_read_warp_times) — how long the persistent kernel's tail is. */
 DDGI_API int ddgi_set_debug(ddgi_ctx* ctx, int32_t debug);
+/* *n_warps = warps of the last probe update that recorded times; dst (may be NULL to query the
+   count) receives 3 values per warp. */
+DDGI_API int ddgi_read_warp_times(ddgi_ctx* ctx, uint64_t* dst, size_t count, size_t* n_warps);
 /* Per-ray (which = 0) or per-pixel (which = 1) voxel lookups of the last dispatch. */
 DDGI_API int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t count);
 /* Kernel variant: 0 = one thread per ray, reference loop order; 1 = regrouped
@@ -245,6 +257,9 @@ DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
    march_min/32 of the lanes that hold a ray are marching (1..32, default 16).  Results do
    not depend on it. */
 DDGI_API int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min);
+/* Caps the resident blocks per SM variant 1 launches (0 = as many as fit, the default).  Results
+   do not depend on it. */
+DDGI_API int ddgi_set_grid_limit(ddgi_ctx* ctx, int32_t blocks_per_sm);
 /* Cost-ordered scheduling (default on): the first ddgi_probe_update after the voxels, the
    field shape or the probe ownership changed also sums the voxel lookups per probe and
    synchronises once to read them; later updates trace the owned probes most expensive
