@@ -283,7 +283,10 @@ def main():
     ms_per_step = total_ms / args.steps
     value = n_rays / (ms_per_step * 1e-3)
 
-    # ---- FPS at the config's resolution: probe update + exchange + pixel pass ----
+    # ---- FPS at the config's resolution: probe update + exchange + pixel pass.  On N > 1 GPUs every
+    #      replica holds the whole texture after the exchange, so each rank renders 1/N of the frame's
+    #      16-pixel workgroup rows (no further collective; the bands are read back independently) ----
+    band = r.set_frame_band(rank, world)
     fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_frames = max(3, min(args.steps, 10))
     barrier()
@@ -431,7 +434,8 @@ def main():
             "cpu_baseline": cpu,
             "verify": verify,
             "fps": {"value": 1000.0 / frame_ms, "frame_ms": frame_ms, "pixel_pass_ms": pixel_ms,
-                    "resolution": list(cfg["screen"])},
+                    "resolution": list(cfg["screen"]), "pixel_rows_rank0": list(band),
+                    "note": "probe update + exchange + pixel pass; pixel rows split across ranks"},
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):

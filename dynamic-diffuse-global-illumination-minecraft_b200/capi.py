@@ -119,6 +119,8 @@ PROTOTYPES = {
     "ddgi_close_peers": (C.c_int, [_P]),
     "ddgi_exchange_barrier": (C.c_int, [_P, _P]),
     "ddgi_exchange_status": (C.c_int, [_P]),
+    "ddgi_set_frame_band": (C.c_int, [_P, _I32, _I32]),
+    "ddgi_frame_band_rows": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
     "ddgi_probe_update": (C.c_int, [_P, _P]),
     "ddgi_render_frame": (C.c_int, [_P, _P]),
     "ddgi_sync": (C.c_int, [_P]),

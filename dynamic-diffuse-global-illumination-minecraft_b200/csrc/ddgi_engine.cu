@@ -82,6 +82,8 @@ struct ddgi_ctx {
     float4* d_frame_f32 = nullptr;
     uint32_t* d_px_lookups = nullptr;
 
+    int band_rank = 0, band_world = 1;  // pixel pass: this context renders band `rank` of `world` row bands
+
     // fused exchange
     uint32_t epoch = 0;              // barriers issued since the textures were created
     uint32_t* d_barrier_error = nullptr;
@@ -957,12 +959,34 @@ int ddgi_render_frame(ddgi_ctx* ctx, void* stream)
     J.albedo = ctx->d_tex;
     J.distance = ctx->d_tex + tex_texels(ctx);
     J.tex_w = ctx->tex_w;
+    // rows of 16x16 workgroups: floor(h/16) in all (rvpt.cpp:1139-1140), split evenly over the bands
+    int groups = ctx->rs.screen_height / 16;
+    J.group_row0 = (int)((long long)groups * ctx->band_rank / ctx->band_world);
+    J.group_rows = (int)((long long)groups * (ctx->band_rank + 1) / ctx->band_world) - J.group_row0;
     J.frame = ctx->d_frame;
     J.frame_f32 = ctx->debug ? ctx->d_frame_f32 : nullptr;
     J.lookups = ctx->debug ? ctx->d_px_lookups : nullptr;
     int l = 0;
     CU(launch_render_frame(P, J, (cudaStream_t)stream, &l));
     ctx->launches += l;
+    return DDGI_OK;
+}
+
+int ddgi_set_frame_band(ddgi_ctx* ctx, int32_t rank, int32_t world)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(world >= 1 && rank >= 0 && rank < world, "bad band rank / world");
+    ctx->band_rank = rank;
+    ctx->band_world = world;
+    return DDGI_OK;
+}
+
+int ddgi_frame_band_rows(const ddgi_ctx* ctx, int32_t* y0, int32_t* y1)
+{
+    if (!ctx || !y0 || !y1) return DDGI_E_INVALID;
+    int groups = ctx->rs.screen_height / 16;
+    *y0 = 16 * (int)((long long)groups * ctx->band_rank / ctx->band_world);
+    *y1 = 16 * (int)((long long)groups * (ctx->band_rank + 1) / ctx->band_world);
     return DDGI_OK;
 }
 

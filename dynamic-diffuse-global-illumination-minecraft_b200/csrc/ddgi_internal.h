@@ -56,6 +56,7 @@ struct PixelJob {
     const uint32_t* albedo;    // probe texture
     const uint32_t* distance;  // distance texture (read only by the restored Chebyshev weight)
     int tex_w;
+    int group_row0, group_rows;  // rows of 16x16 workgroups this context renders (all of them by default)
     uint32_t* frame;        // w*h RGBA8
     float4* frame_f32;      // debug or nullptr
     uint32_t* lookups;      // debug or nullptr

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) render_frame_kernel(const __grid_constant
                                                            const __grid_constant__ PixelJob J)
 {
     int gx = blockIdx.x * 16 + (threadIdx.x & 15);
-    int gy = blockIdx.y * 16 + (threadIdx.x >> 4);
+    int gy = (J.group_row0 + blockIdx.y) * 16 + (threadIdx.x >> 4);
     float cx = (float)gx / (float)P.screen_w;
     float cy = (float)gy / (float)P.screen_h;
     cy = 1.0f - cy;
@@ -417,7 +417,7 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
 
 cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStream_t s, int* launches)
 {
-    dim3 grid(P.screen_w / 16, P.screen_h / 16);
+    dim3 grid(P.screen_w / 16, J.group_rows);  // the reference dispatches floor(w/16) x floor(h/16) groups
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0;
     if (ext) render_frame_kernel<true><<<grid, 256, 0, s>>>(P, J);

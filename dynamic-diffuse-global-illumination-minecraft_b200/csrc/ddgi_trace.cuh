@@ -8,6 +8,7 @@
 //   march / nearest_hit      assets/shaders/intersection.glsl:1051-1100, :1244-1301
 //   probe_direct_lighting    assets/shaders/probe_pass.comp:180-215
 #pragma once
+#include "ddgi_fastmath.cuh"
 #include "ddgi_texture.cuh"
 
 namespace ddgi {
@@ -145,8 +146,8 @@ DDGI_HD v3 hemisphere_dir(v3 normal, uint32_t& st, bool axis_normal = false)
 // ray scaled by 1/0.1.  Returns t (INF on a miss) and the unnormalised normal.
 DDGI_HD float light_sphere(v3 origin, v3 direction, const Light& l, float maxt, v3* normal)
 {
-    v3 o = (origin - lpos(l)) / 0.1f;
-    v3 d = direction / 0.1f;
+    v3 o = div_tenth(origin - lpos(l));  // x / 0.1f, exact (ddgi_fastmath.cuh)
+    v3 d = div_tenth(direction);
     float A = dot(d, d);
     float B = -dot(d, o);
     float C = dot(o, o) - 1.0f;
@@ -214,26 +215,55 @@ DDGI_HD void march_advance(v3 origin, v3 dir, float& t, v3& p)
 
 // Marches at most 125 cells.  On a hit fills t, the (un-normalised) axis normal and
 // the albedo.  `lookups` counts voxel queries (the reference's getBlockAt calls).
+// Regular directions and origins (every component passes ddgi_fastmath.cuh's range checks —
+// all but axis-parallel / degenerate rays) take the exact one-division step of the wavefront
+// kernel: max((-f)/d, (1-f)/d) = (sel - f)/d with sel = 1 for d > 0 else 0, the division by the
+// FMA-corrected reciprocal, floor / ceil by directed-rounding adds.  Bit-identical to the literal
+// form below (tests/hostsim on the CPU, tests/selftest_div.cu exhaustively on the GPU).
 DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32_t& lookups)
 {
     v3 dir = normalize(direction);
     v3 p = origin;
     float t = 0.0f;
-    for (int i = 0; i < kMarchSteps; i++) {
-        march_advance(origin, dir, t, p);
-        v3 cell = V3(ceilf(p.x), ceilf(p.y), ceilf(p.z));
-        lookups++;
-        int type = scene_lookup(S, cell);
-        if (type > 0) {
-            out.t = t;
-            v3 n = face_normal(p, cell);
-            out.normal = normalize(n);
-            out.base_color = scene_color(S, p, type, out.normal);
-            out.emissive = V3(0, 0, 0);
-            return true;
+    const bool fast = regular_component(dir.x) && regular_component(dir.y) && regular_component(dir.z) &&
+                      regular_origin(origin.x) && regular_origin(origin.y) && regular_origin(origin.z);
+    bool hit = false;
+    if (fast) {
+        const v3 inv = V3(rcp_regular(dir.x), rcp_regular(dir.y), rcp_regular(dir.z));
+        const v3 sel = V3(dir.x > 0 ? 1.0f : 0.0f, dir.y > 0 ? 1.0f : 0.0f, dir.z > 0 ? 1.0f : 0.0f);
+        for (int i = 0; i < kMarchSteps; i++) {
+            float tx = div_markstein(sel.x - (p.x - floor_small(p.x)), dir.x, inv.x);
+            float ty = div_markstein(sel.y - (p.y - floor_small(p.y)), dir.y, inv.y);
+            float tz = div_markstein(sel.z - (p.z - floor_small(p.z)), dir.z, inv.z);
+            t += gmin(gmin(tx, ty), tz) + 0.0001f;
+            p = origin + dir * t;
+            lookups++;
+            // |p| < 2^22: p + 1.5*2^23 rounded up IS ceil(p) + 1.5*2^23
+            if (cell_solid(S, float_bits(add_round_up(p.x, kCellMagic)), float_bits(add_round_up(p.y, kCellMagic)),
+                           float_bits(add_round_up(p.z, kCellMagic)))) {
+                hit = true;
+                break;
+            }
+        }
+    } else {
+        for (int i = 0; i < kMarchSteps; i++) {
+            march_advance(origin, dir, t, p);
+            lookups++;
+            if (cell_solid(S, cell_bits(ceilf(p.x)), cell_bits(ceilf(p.y)), cell_bits(ceilf(p.z)))) {
+                hit = true;
+                break;
+            }
         }
     }
-    return false;
+    if (!hit) return false;
+    v3 cell = V3(ceilf(p.x), ceilf(p.y), ceilf(p.z));
+    int type = scene_type_at(S, cell);
+    out.t = t;
+    v3 n = face_normal(p, cell);
+    out.normal = normalize(n);
+    out.base_color = scene_color(S, p, type, out.normal);
+    out.emissive = V3(0, 0, 0);
+    return true;
 }
 
 // Nearest of {light spheres, voxel march}.

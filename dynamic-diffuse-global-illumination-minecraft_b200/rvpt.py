@@ -398,6 +398,13 @@ class RVPT:
         blob = b"".join(handles)
         self._check(self._lib.ddgi_open_peers(self._ctx, len(handles), blob, self_index))
 
+    def set_frame_band(self, rank: int, world: int):
+        """This context renders band `rank` of `world` bands of 16-pixel rows; returns its pixel rows (y0, y1)."""
+        self._check(self._lib.ddgi_set_frame_band(self._ctx, rank, world))
+        y0, y1 = C.c_int32(), C.c_int32()
+        self._check(self._lib.ddgi_frame_band_rows(self._ctx, C.byref(y0), C.byref(y1)))
+        return y0.value, y1.value
+
     def exchange_barrier(self):
         """Device-side completion barrier of the fused exchange (after probe_update, every rank)."""
         self._check(self._lib.ddgi_exchange_barrier(self._ctx, self.stream))

@@ -222,6 +222,13 @@ DDGI_API int ddgi_close_peers(ddgi_ctx* ctx);
 DDGI_API int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream);
 DDGI_API int ddgi_exchange_status(ddgi_ctx* ctx);
 
+/* Pixel pass across GPUs: every replica holds the whole probe texture after the exchange, so the
+   frame splits into `world` bands of 16-pixel workgroup rows with no further collective; this
+   context's ddgi_render_frame writes only band `rank` (pixel rows [y0, y1) of
+   ddgi_frame_band_rows) of its frame buffer.  Default (0, 1): the whole frame. */
+DDGI_API int ddgi_set_frame_band(ddgi_ctx* ctx, int32_t rank, int32_t world);
+DDGI_API int ddgi_frame_band_rows(const ddgi_ctx* ctx, int32_t* y0, int32_t* y1);
+
 /* ---- the two dispatches ---- */
 /* vkCmdDispatch #1, probe_pass.comp (rvpt.cpp:1121-1129) */
 DDGI_API int ddgi_probe_update(ddgi_ctx* ctx, void* stream);
