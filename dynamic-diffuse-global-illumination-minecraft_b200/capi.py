@@ -134,6 +134,7 @@ PROTOTYPES = {
     "ddgi_set_kernel_variant": (C.c_int, [_P, _I32]),
     "ddgi_set_tuning": (C.c_int, [_P, _I32]),
     "ddgi_set_grid_limit": (C.c_int, [_P, _I32]),
+    "ddgi_set_schedule_slot": (C.c_int, [_P, _I32]),
     "ddgi_set_auto_schedule": (C.c_int, [_P, _I32]),
     "ddgi_launch_count": (C.c_uint64, [_P]),
 }

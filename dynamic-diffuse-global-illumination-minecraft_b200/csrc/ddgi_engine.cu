@@ -28,6 +28,7 @@ struct ddgi_ctx {
     float distance_scale = 1.0f;
     int march_min = 16;  // wavefront kernel: keep stepping while >= march_min/32 of the live lanes march
     int grid_limit = 0;  // wavefront kernel: cap on resident blocks per SM (0 = what the occupancy allows)
+    int slot_pref = 32;  // schedule granularity in rays (0 = a whole probe): one warp's fetch measured best
     unsigned long long* d_warp_times = nullptr;  // debug level 2
     size_t warp_times_cap = 0, warp_times_n = 0;
     uint32_t* d_counter = nullptr;
@@ -141,11 +142,13 @@ static bool owns_probe(const ddgi_ctx* c, int p)
     return (unit / c->cyc_block) % c->cyc_world == c->cyc_rank;
 }
 
-// Rays per scheduling slot: one warp's fetch (32) when it divides rays/probe, else the probe.
+// Rays per scheduling slot: ctx->slot_pref (a multiple of 32) when it divides rays/probe, else the
+// whole probe.
 static uint32_t slot_rays(const ddgi_ctx* c)
 {
     uint32_t rpp = (uint32_t)(c->rx * c->ry);
-    return rpp % 32u == 0 ? 32u : rpp;
+    uint32_t want = (uint32_t)c->slot_pref;
+    return want >= 32u && want <= rpp && rpp % want == 0 ? want : rpp;
 }
 static size_t num_slots(const ddgi_ctx* c) { return num_probes(c) * ((size_t)(c->rx * c->ry) / slot_rays(c)); }
 
@@ -1073,6 +1076,16 @@ int ddgi_read_warp_times(ddgi_ctx* ctx, uint64_t* dst, size_t count, size_t* n_w
     NEED(count >= ctx->warp_times_n * 3, "expected 3 values per warp");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpy(dst, ctx->d_warp_times, ctx->warp_times_n * 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DDGI_OK;
+}
+
+int ddgi_set_schedule_slot(ddgi_ctx* ctx, int32_t rays)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(rays == 0 || (rays >= 32 && rays % 32 == 0), "slot must be 0 (a whole probe) or a multiple of 32 rays");
+    ctx->slot_pref = rays;
+    ctx->order_dirty = true;
+    ctx->calibrated = false;
     return DDGI_OK;
 }
 

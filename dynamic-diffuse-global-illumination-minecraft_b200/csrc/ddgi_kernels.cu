@@ -121,7 +121,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 #define DDGI_WF_MIN_BLOCKS 7  // 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
 
-template <bool kLiteral>
+template <bool kLiteral, bool kTimed>
 __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_wavefront(const __grid_constant__ FrameParams P,
                                                                      const __grid_constant__ ProbeJob J,
                                                                      uint32_t* __restrict__ next_ray,
@@ -140,11 +140,12 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     int tx = 0, ty = 0;
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: ray indices already reserved
     bool exhausted = false;
-    // debug level 2: this warp's (start, last ray taken, exit) times; the slot address is
-    // recomputed at each use so that the normal kernel keeps no register for it
+    // debug level 2 (kTimed instantiation only — measured: even a never-taken test of
+    // J.warp_times in the fetch path costs the normal kernel 1.6 %): this warp's (start, last
+    // ray taken, exit) times
 #define DDGI_WARP_TIME(slot)                                                                                  \
     do {                                                                                                      \
-        if (J.warp_times)                                                                                     \
+        if (kTimed)                                                                                           \
             J.warp_times[3 * (size_t)((blockIdx.x * kWfThreads + threadIdx.x) >> 5) + (slot)] = globaltimer_ns(); \
     } while (0)
     if (lane == 0) DDGI_WARP_TIME(0);
@@ -384,7 +385,7 @@ uint32_t wavefront_warps(uint32_t n, int grid_limit)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false>, kWfThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false, false>, kWfThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     uint32_t warps_needed = (n + 31) / 32;
@@ -409,8 +410,11 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     uint32_t grid = wavefront_warps(n, grid_limit) / (kWfThreads / 32);
-    if (P.scene.color_mode != 0) probe_update_wavefront<true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
-    else probe_update_wavefront<false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    const bool literal = P.scene.color_mode != 0, timed = J.warp_times != nullptr;
+    if (literal && timed) probe_update_wavefront<true, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    else if (literal) probe_update_wavefront<true, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    else if (timed) probe_update_wavefront<false, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    else probe_update_wavefront<false, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
     (*launches)++;
     return cudaGetLastError();
 }

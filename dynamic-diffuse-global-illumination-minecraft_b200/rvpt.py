@@ -351,6 +351,9 @@ class RVPT:
             self._check(self._lib.ddgi_read_warp_times(self._ctx, out.ctypes.data, out.size, C.byref(n)))
         return out
 
+    def set_schedule_slot(self, rays: int):
+        self._check(self._lib.ddgi_set_schedule_slot(self._ctx, rays))
+
     def set_grid_limit(self, blocks_per_sm: int):
         self._check(self._lib.ddgi_set_grid_limit(self._ctx, blocks_per_sm))
 

@@ -34,6 +34,7 @@ def timed(reps=10):
     ts = []
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(1)  # cold L2, as bench.py times it
         a.record(stream)
         r.probe_update()
         b.record(stream)
@@ -42,10 +43,12 @@ def timed(reps=10):
     return float(np.median(ts))
 
 
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for w in (1, world):
-    for sched in (1, 0):
+    for sched, slot in ((1, 0), (1, 128), (1, 64), (1, 32), (0, 0)):
         for limit in (0,):
             r.set_auto_schedule(bool(sched))
+            r.set_schedule_slot(slot)
             r.set_probes_cyclic(0, w, 1)
             r.set_grid_limit(limit)
             r.set_debug(False)
@@ -58,7 +61,7 @@ for w in (1, world):
             t0 = t[:, 0].min()
             start, last, exit_ = (t[:, 0] - t0) / 1e6, (t[:, 1] - t0) / 1e6, (t[:, 2] - t0) / 1e6
             q = lambda a, p: float(np.percentile(a, p))
-            print(f"world {w} sched {sched} blocks/SM {limit or 'max'}: {ms:7.3f} ms ({n / w / ms / 1e3:7.1f} Mrays/s) warps {len(t)} | "
+            print(f"world {w} sched {sched} slot {slot or 'probe'}: {ms:7.3f} ms ({n / w / ms / 1e3:7.1f} Mrays/s) warps {len(t)} | "
                   f"start p50 {q(start, 50):.3f} max {start.max():.3f} | last fetch p10 {q(last, 10):.3f} p50 {q(last, 50):.3f} max {last.max():.3f} | "
                   f"exit p10 {q(exit_, 10):.3f} p50 {q(exit_, 50):.3f} p90 {q(exit_, 90):.3f} max {exit_.max():.3f} | "
                   f"mean busy {float((exit_ - start).mean()):.3f}")
