@@ -20,6 +20,7 @@ COLOR_PALETTE, COLOR_LITERAL = 0, 1
 BLEND_OVERWRITE, BLEND_HYSTERESIS = 0, 1
 WEIGHT_LITERAL, WEIGHT_CHEBYSHEV = 0, 1
 DISTANCE_ZERO, DISTANCE_MOMENTS = 0, 1
+LAYOUT_RAY_TILE, LAYOUT_OCTAHEDRAL = 0, 1
 RENDER_DDGI, RENDER_DIRECT, RENDER_INDIRECT, RENDER_COLOR, RENDER_NORMAL, RENDER_DEPTH = range(6)  # rvpt.h:25-31
 MAX_LIGHTS = 8
 
@@ -105,6 +106,8 @@ PROTOTYPES = {
     "ddgi_edit_voxels": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), _P, _P]),
     "ddgi_read_voxels": (C.c_int, [_P, _P, _SZ]),
     "ddgi_generate_probe_rays": (C.c_int, [_P, _I32]),
+    "ddgi_generate_fibonacci_rays": (C.c_int, [_P]),
+    "ddgi_set_layout": (C.c_int, [_P, _I32, _I32]),
     "ddgi_set_ray_samples": (C.c_int, [_P, _P, _SZ]),
     "ddgi_get_ray_samples": (C.c_int, [_P, _P, _SZ]),
     "ddgi_set_probe_rays": (C.c_int, [_P, _P, _SZ]),

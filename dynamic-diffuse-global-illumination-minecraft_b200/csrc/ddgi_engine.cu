@@ -23,6 +23,12 @@ struct ddgi_ctx {
     int variant = 1;
     int color_mode = 0;  // 0 flat palette, 1 the reference's procedural colours
     int blend_mode = 0;  // 1: hysteresis blend into the previous texel (field.hysteresis)
+    int layout = 0, oct = 8;  // probe-texture layout: 0 the reference's ray tile, 1 octahedral oct x oct tiles
+    float4* d_ray_out = nullptr;     // octahedral layout: per-ray (radiance, first-hit t)
+    size_t ray_out_cap = 0;
+    uint32_t* d_owned = nullptr;     // octahedral layout: the owned probes
+    size_t owned_cap = 0;
+    std::vector<uint32_t> owned;
     int weight_mode = 0;    // 1: Chebyshev visibility weight restored in the cage sample
     int distance_mode = 0;  // 1: the probe pass stores first-hit distance moments
     float distance_scale = 1.0f;
@@ -122,6 +128,8 @@ static void dfree(T*& p)
 }
 
 static size_t tex_texels(const ddgi_ctx* c) { return (size_t)c->tex_w * c->tex_h; }
+static int tile_w(const ddgi_ctx* c) { return c->layout == 1 ? c->oct : c->rx; }
+static int tile_h(const ddgi_ctx* c) { return c->layout == 1 ? c->oct : c->ry; }
 static size_t num_rays(const ddgi_ctx* c)
 {
     if (!c->have_field) return 0;
@@ -163,9 +171,19 @@ static int schedule(ddgi_ctx* ctx)
     size_t np = num_probes(ctx), ns = num_slots(ctx);
     uint32_t spp = (uint32_t)(ns / np);
     ctx->order.clear();
+    ctx->owned.clear();
     for (size_t p = 0; p < np; p++)
-        if (owns_probe(ctx, (int)p))
+        if (owns_probe(ctx, (int)p)) {
+            ctx->owned.push_back((uint32_t)p);
             for (uint32_t j = 0; j < spp; j++) ctx->order.push_back((uint32_t)p * spp + j);
+        }
+    if (ctx->owned.size() > ctx->owned_cap) {
+        dfree(ctx->d_owned);
+        CU(cudaMalloc(&ctx->d_owned, ctx->owned.size() * sizeof(uint32_t)));
+        ctx->owned_cap = ctx->owned.size();
+    }
+    if (!ctx->owned.empty())
+        CU(cudaMemcpy(ctx->d_owned, ctx->owned.data(), ctx->owned.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (ctx->auto_schedule && ctx->calibrated && ctx->cost.size() == ns) {
         const std::vector<uint32_t>& c = ctx->cost;
         bool measured = true;
@@ -190,8 +208,8 @@ static int schedule(ddgi_ctx* ctx)
 // does when probe counts or rays/probe change (src/rvpt/rvpt.cpp:661-755).
 static int resize_textures(ddgi_ctx* ctx)
 {
-    int w = ctx->field.probe_count[0] * ctx->field.probe_count[2] * ctx->rx;
-    int h = ctx->field.probe_count[1] * ctx->ry;
+    int w = ctx->field.probe_count[0] * ctx->field.probe_count[2] * tile_w(ctx);
+    int h = ctx->field.probe_count[1] * tile_h(ctx);
     if (w == ctx->tex_w && h == ctx->tex_h && ctx->d_tex) return DDGI_OK;
     if (ctx->n_peers) return fail(ctx, DDGI_E_STATE, "close peers before resizing the probe textures");
     dfree(ctx->d_tex);
@@ -279,6 +297,10 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
     P->visualize_probes = c->rs.visualize_probes != 0;
     P->weight_mode = c->weight_mode;
     P->distance_scale = c->distance_scale;
+    P->layout = c->layout;
+    P->oct = c->oct;
+    P->tile_w = tile_w(c);
+    P->tile_h = tile_h(c);
 }
 
 // The flat-colour table of the reference's block types: 2-5 are getColorAt's own flat
@@ -423,6 +445,8 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_slot_cost);
     dfree(ctx->d_warp_times);
     dfree(ctx->d_barrier_error);
+    dfree(ctx->d_ray_out);
+    dfree(ctx->d_owned);
     delete ctx;
 }
 
@@ -679,6 +703,44 @@ int ddgi_generate_probe_rays(ddgi_ctx* ctx, int32_t reseed)
     return upload_dirs(ctx);
 }
 
+// Spherical Fibonacci set (the north star's ray generator; the reference's is the stratified
+// libc-rand() set above): direction i of n has cos(theta) = 1 - (2i + 1)/n and azimuth
+// 2 pi frac(i (phi - 1)), phi the golden ratio, evaluated in fp64 and rounded once to fp32.
+int ddgi_generate_fibonacci_rays(ddgi_ctx* ctx)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    CU(cudaSetDevice(ctx->device));
+    const int n = ctx->rx * ctx->ry;
+    const double golden = 0.61803398874989484820;  // phi - 1
+    ctx->samples.resize((size_t)n * 3);
+    for (int i = 0; i < n; i++) {
+        double f = (double)i * golden;
+        double az = 6.283185307179586476925 * (f - floor(f));
+        double z = 1.0 - (2.0 * (double)i + 1.0) / (double)n;
+        double ring = sqrt(1.0 - z * z);
+        ctx->samples[3 * (size_t)i] = (float)(cos(az) * ring);
+        ctx->samples[3 * (size_t)i + 1] = (float)(sin(az) * ring);
+        ctx->samples[3 * (size_t)i + 2] = (float)z;
+    }
+    return upload_dirs(ctx);
+}
+
+int ddgi_set_layout(ddgi_ctx* ctx, int32_t layout, int32_t oct)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->have_field, "set the irradiance field first");
+    NEED(layout == DDGI_LAYOUT_RAY_TILE || layout == DDGI_LAYOUT_OCTAHEDRAL, "layout must be DDGI_LAYOUT_RAY_TILE or DDGI_LAYOUT_OCTAHEDRAL");
+    if (layout == DDGI_LAYOUT_OCTAHEDRAL) {
+        NEED(oct >= 2 && oct <= 64, "octahedral tile size in [2,64]");
+        NEED(ctx->rx * ctx->ry <= 4096, "the octahedral layout stages a probe's rays in shared memory: at most 4096 rays/probe");
+    }
+    CU(cudaSetDevice(ctx->device));
+    ctx->layout = layout;
+    if (layout == DDGI_LAYOUT_OCTAHEDRAL) ctx->oct = oct;
+    return resize_textures(ctx);
+}
+
 int ddgi_set_ray_samples(ddgi_ctx* ctx, const float* samples, size_t count)
 {
     if (!ctx) return DDGI_E_INVALID;
@@ -915,6 +977,16 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         J.peer_distance[J.n_peers] = (uint32_t*)ctx->peer_base[g] + tex_texels(ctx);
         J.n_peers++;
     }
+    if (ctx->layout == 1) {
+        if (ctx->ray_mode != 1)
+            return fail(ctx, DDGI_E_STATE, "the octahedral layout needs a generated ray set (ddgi_generate_probe_rays / _fibonacci_rays / ddgi_set_ray_samples)");
+        if (num_rays(ctx) > ctx->ray_out_cap) {
+            dfree(ctx->d_ray_out);
+            CU(cudaMalloc(&ctx->d_ray_out, num_rays(ctx) * sizeof(float4)));
+            ctx->ray_out_cap = num_rays(ctx);
+        }
+        J.ray_out = ctx->d_ray_out;
+    }
     ctx->warp_times_n = 0;
     if (ctx->debug >= 2 && ctx->variant == 1 && P.max_bounces > 0) {
         size_t warps = wavefront_warps(J.n_owned * J.slot_rays, ctx->grid_limit);
@@ -928,6 +1000,27 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     }
     int l = 0;
     CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, ctx->grid_limit, (cudaStream_t)stream, &l));
+    if (ctx->layout == 1) {
+        OctJob O;
+        memset(&O, 0, sizeof(O));
+        O.probes = ctx->d_owned;
+        O.n_probes = (uint32_t)ctx->owned.size();
+        O.n_rays = ctx->rx * ctx->ry;
+        O.dirs = ctx->d_dirs;
+        O.ray_out = ctx->d_ray_out;
+        O.tex_w = ctx->tex_w;
+        O.albedo = J.albedo;
+        O.distance = J.distance;
+        O.blend = ctx->blend_mode;
+        O.hysteresis = ctx->field.hysteresis;
+        O.distance_scale = ctx->distance_scale;
+        O.n_peers = J.n_peers;
+        for (int g = 0; g < J.n_peers; g++) {
+            O.peer_albedo[g] = J.peer_albedo[g];
+            O.peer_distance[g] = J.peer_distance[g];
+        }
+        CU(launch_probe_blend_octahedral(P, O, (cudaStream_t)stream, &l));
+    }
     ctx->launches += l;
     if (calibrate) {
         // First update after the scene / rays / field changed: this launch also recorded the largest

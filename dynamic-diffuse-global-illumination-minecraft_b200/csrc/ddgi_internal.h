@@ -33,6 +33,7 @@ struct ProbeJob {
     float hysteresis;
     int distance_mode;    // 1: store first-hit distance moments (d, d*d), d = t / distance_scale; 0: zeros as shipped
     float distance_scale;
+    float4* ray_out;      // octahedral layout: per-ray (radiance rgb, first-hit t) instead of a texel store, or nullptr
     unsigned long long* warp_times;  // debug level 2: per warp (start, last fetch, exit) globaltimer ns, or nullptr
     int n_peers;          // fused exchange: replicas to store every texel into
     uint32_t* peer_albedo[kMaxPeers];
@@ -51,6 +52,25 @@ struct PeerBarrier {
     uint32_t* error;                  // set to 1 when a peer did not arrive in time
 };
 cudaError_t launch_peer_barrier(const PeerBarrier& B, cudaStream_t s, int* launches);
+
+// Octahedral layout, second kernel of the probe update: ray results -> tile texels.
+struct OctJob {
+    const uint32_t* probes;  // owned probes
+    uint32_t n_probes;
+    int n_rays;              // rays per probe
+    const float* dirs;       // n_rays normalised directions
+    const float4* ray_out;   // all rays of the field, linear ray index
+    int tex_w;
+    uint32_t* albedo;
+    uint32_t* distance;
+    int blend;
+    float hysteresis;
+    float distance_scale;
+    int n_peers;
+    uint32_t* peer_albedo[kMaxPeers];
+    uint32_t* peer_distance[kMaxPeers];
+};
+cudaError_t launch_probe_blend_octahedral(const FrameParams& P, const OctJob& J, cudaStream_t s, int* launches);
 
 struct PixelJob {
     const uint32_t* albedo;    // probe texture

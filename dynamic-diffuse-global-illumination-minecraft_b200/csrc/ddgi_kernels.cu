@@ -62,6 +62,14 @@ __device__ __forceinline__ uint32_t shard_ray(const ProbeJob& J, uint32_t idx)
 __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v3 color, uint32_t k,
                                             uint32_t lookups, float first_t)
 {
+    if (J.ray_out) {
+        // octahedral layout: the ray's radiance and first-hit t go to the ray buffer; the tile
+        // texels are made from all rays of the probe by probe_blend_octahedral
+        J.ray_out[k] = make_float4(color.x, color.y, color.z, first_t);
+        if (J.lookups) J.lookups[k] = lookups;
+        if (J.slot_cost) atomicMax(J.slot_cost + k / J.slot_rays, lookups);
+        return;
+    }
     size_t t = (size_t)ty * J.tex_w + tx;
     if (J.blend) color = blend_hysteresis(J.albedo[t], color, J.hysteresis);
     uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     __shared__ float s_base[kLiteral ? 3 * kWfThreads : 1];  // procedural colour of the lane's bounce hit
     __shared__ float s_first_t[kWfThreads];                  // t of the lane's first query (distance mode 1)
     float* stash = s_base + (kLiteral ? threadIdx.x : 0);
-    const bool want_first_t = J.distance_mode == 1;
+    const bool want_first_t = J.distance_mode == 1 || J.ray_out != nullptr;
     WfRay R;
     R.mode = WF_FETCH;
     uint32_t k = 0xffffffffu;  // no ray yet
@@ -231,6 +239,77 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     }
     if (lane == 0) DDGI_WARP_TIME(2);
 #undef DDGI_WARP_TIME
+}
+
+// ------------------------------------------------------------------ octahedral blend
+// One block per owned probe.  The probe's ray directions and ray results are staged in shared
+// memory; each warp takes texels of the oct x oct tile in turn: lanes accumulate their share of
+// the rays (ddgi_octahedral.cuh: oct_lane_partial), the partial sums meet in an xor-butterfly
+// of warp shuffles — the north star's "warp-shuffle reduction of ray radiance into texels" — and
+// lane 0 blends and stores the two texels (into every replica under the fused exchange).
+constexpr int kOctThreads = 128;
+__device__ __forceinline__ OctAcc oct_shuffle_xor(OctAcc a, int off)
+{
+    OctAcc b;
+    b.r = __shfl_xor_sync(0xffffffffu, a.r, off);
+    b.g = __shfl_xor_sync(0xffffffffu, a.g, off);
+    b.b = __shfl_xor_sync(0xffffffffu, a.b, off);
+    b.d = __shfl_xor_sync(0xffffffffu, a.d, off);
+    b.d2 = __shfl_xor_sync(0xffffffffu, a.d2, off);
+    b.w = __shfl_xor_sync(0xffffffffu, a.w, off);
+    return b;
+}
+__global__ void __launch_bounds__(kOctThreads) probe_blend_octahedral(const __grid_constant__ FrameParams P,
+                                                                      const __grid_constant__ OctJob J)
+{
+    extern __shared__ float s_oct[];
+    float* s_dirs = s_oct;                 // n x 3
+    float* s_rad = s_oct + 3 * J.n_rays;   // n x 4
+    const uint32_t p = J.probes[blockIdx.x];
+    for (int i = threadIdx.x; i < 3 * J.n_rays; i += kOctThreads) s_dirs[i] = J.dirs[i];
+    const float4* mine = J.ray_out + (size_t)p * J.n_rays;
+    for (int i = threadIdx.x; i < J.n_rays; i += kOctThreads) {
+        float4 v = mine[i];
+        s_rad[4 * i] = v.x;
+        s_rad[4 * i + 1] = v.y;
+        s_rad[4 * i + 2] = v.z;
+        s_rad[4 * i + 3] = v.w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cx, cy;
+    tile_origin(P, (int)p, &cx, &cy);
+    for (int t = warp; t < P.oct * P.oct; t += kOctThreads / 32) {
+        int u = t % P.oct, v = t / P.oct;
+        v3 dir_t = oct_texel_dir(u, v, P.oct);
+        OctAcc a = oct_lane_partial(dir_t, s_dirs, s_rad, J.n_rays, lane, J.distance_scale);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) a = oct_add(a, oct_shuffle_xor(a, off));
+        if (lane == 0) {
+            size_t at = (size_t)(cy + v) * J.tex_w + (cx + u);
+            uint32_t alb, dist;
+            oct_finalize(a, J.blend, J.hysteresis, J.albedo[at], J.distance[at], &alb, &dist);
+            J.albedo[at] = alb;
+            J.distance[at] = dist;
+            for (int g = 0; g < J.n_peers; g++) {
+                J.peer_albedo[g][at] = alb;
+                J.peer_distance[g][at] = dist;
+            }
+        }
+    }
+}
+
+cudaError_t launch_probe_blend_octahedral(const FrameParams& P, const OctJob& J, cudaStream_t s, int* launches)
+{
+    if (J.n_probes == 0) return cudaSuccess;
+    size_t smem = (size_t)7 * J.n_rays * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(probe_blend_octahedral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    probe_blend_octahedral<<<J.n_probes, kOctThreads, smem, s>>>(P, J);
+    (*launches)++;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ fused-exchange barrier
@@ -423,7 +502,7 @@ cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStr
 {
     dim3 grid(P.screen_w / 16, J.group_rows);  // the reference dispatches floor(w/16) x floor(h/16) groups
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-    bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0;
+    bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0 || P.layout != 0;
     if (ext) render_frame_kernel<true><<<grid, 256, 0, s>>>(P, J);
     else render_frame_kernel<false><<<grid, 256, 0, s>>>(P, J);
     (*launches)++;

@@ -8,6 +8,7 @@
 //   shade_pixel                 assets/shaders/compute_pass.comp:58-87 (eval_integrator)
 //   pinhole_ray                 assets/shaders/camera.glsl:29-51
 #pragma once
+#include "ddgi_octahedral.cuh"
 #include "ddgi_trace.cuh"
 
 namespace ddgi {
@@ -23,8 +24,17 @@ DDGI_HD void tile_origin(const FrameParams& P, int p, int* ox, int* oy)
     int col = f2i(gmod((float)p, (float)x_dim));
     int row = p / x_dim;
     if (row >= P.probe_count[1]) return;
-    *ox = col * P.rx;
-    *oy = row * P.ry;
+    *ox = col * P.tile_w;
+    *oy = row * P.tile_h;
+}
+
+// Octahedral layout: bilinear fetch of probe p's tile of `tex` at octEncode(dir).
+DDGI_HD v3 sample_tile_oct(const FrameParams& P, const uint32_t* tex, int W, int p, v3 dir)
+{
+    int cx, cy;
+    tile_origin(P, p, &cx, &cy);
+    if (cx == -1 && cy == -1) return V3(1, 0, 1);
+    return oct_sample_tile(tex, W, cx, cy, P.oct, dir);
 }
 
 // Direction -> texel of the probe tile, then the mean of the centre texel plus the
@@ -101,7 +111,8 @@ DDGI_HD v3 cage_irradiance(const FrameParams& P, const uint32_t* tex, const uint
         // (intersection.glsl:1367-1383); weight_mode 1 restores `weight *= chebyshevWeight`
         if (kExt && P.weight_mode == 1) {
             float probe_dist = length(pos - probe_pos) / P.distance_scale;
-            v3 mms = sample_tile(P, tex, dist_tex, W, p, V3(-dir.x, -dir.y, -dir.z));
+            v3 to_pos = V3(-dir.x, -dir.y, -dir.z);
+            v3 mms = P.layout == 1 ? sample_tile_oct(P, dist_tex, W, p, to_pos) : sample_tile(P, tex, dist_tex, W, p, to_pos);
             float mean = mms.x;
             float variance = fabsf(mean * mean - mms.y);
             float over = gmax(probe_dist - mean, 0.0f);
@@ -113,7 +124,8 @@ DDGI_HD v3 cage_irradiance(const FrameParams& P, const uint32_t* tex, const uint
         const float crush = 0.2f;
         if (w < crush) w *= w * w * (1.f / (crush * crush));
         w *= tri.x * tri.y * tri.z;
-        irradiance = irradiance + sample_tile(P, tex, tex, W, p, N) * w;
+        v3 e = (kExt && P.layout == 1) ? sample_tile_oct(P, tex, W, p, N) : sample_tile(P, tex, tex, W, p, N);
+        irradiance = irradiance + e * w;
         sum_w += w;
     }
     return irradiance / sum_w;

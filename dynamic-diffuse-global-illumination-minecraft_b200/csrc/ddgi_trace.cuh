@@ -48,6 +48,10 @@ struct FrameParams {
     int weight_mode;
     // distance moments are stored and compared in units of distance_scale (1 = the reference's text)
     float distance_scale;
+    // probe-texture layout: 0 = the reference's ray tile (one texel per ray, rx x ry), 1 = octahedral
+    // tile of oct x oct texels (ddgi_octahedral.cuh); tile_w x tile_h is the tile either way
+    int layout, oct;
+    int tile_w, tile_h;
 };
 
 struct Hit {

@@ -220,6 +220,16 @@ class RVPT:
         self._apply_field()
         self._check(self._lib.ddgi_generate_probe_rays(self._ctx, 1 if reseed else 0))
 
+    def generate_fibonacci_rays(self):
+        """Spherical-Fibonacci ray set (north-star generator; deterministic)."""
+        self._apply_field()
+        self._check(self._lib.ddgi_generate_fibonacci_rays(self._ctx))
+
+    def set_layout(self, layout: int, oct: int = 8):
+        """capi.LAYOUT_RAY_TILE (the reference) or capi.LAYOUT_OCTAHEDRAL (oct x oct tile per probe)."""
+        self._apply_field()
+        self._check(self._lib.ddgi_set_layout(self._ctx, layout, oct))
+
     def set_ray_samples(self, samples: np.ndarray):
         self._apply_field()
         s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 3)

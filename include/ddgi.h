@@ -175,6 +175,19 @@ DDGI_API int ddgi_set_distance_mode(ddgi_ctx* ctx, int32_t mode, float scale);
    Ordered on `stream` with the dispatches; returns when `types` may be reused.  The cost-ordered
    schedule keeps its last calibration (results never depend on it). */
 DDGI_API int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[3], const uint8_t* types, void* stream);
+/* Probe-texture layout.  DDGI_LAYOUT_RAY_TILE (default) is the reference: one texel per ray, tile
+   rx x ry (probe_pass.comp:269-271).  DDGI_LAYOUT_OCTAHEDRAL is the textbook layout the north star
+   names: an oct x oct octahedral tile per probe (mapping = the reference's unused
+   assets/shaders/octahedral.glsl:16-35); texel = cosine-weighted mean over ALL the probe's rays of
+   the ray radiance (albedo plane) and of the first-hit distance moments (d, d^2), d = min(t /
+   distance_scale, 1) (distance plane), reduced with warp shuffles, blended by the hysteresis rule
+   when DDGI_BLEND_HYSTERESIS is on; the pixel pass fetches tiles bilinearly at octEncode(dir).
+   The reference has no code that fills or reads such a tile, so this mode has no reference
+   output: parity for it is engine vs oracle only.  Re-creates the probe textures
+   (W = X*Z*oct, H = Y*oct); needs a generated ray set. */
+#define DDGI_LAYOUT_RAY_TILE 0
+#define DDGI_LAYOUT_OCTAHEDRAL 1
+DDGI_API int ddgi_set_layout(ddgi_ctx* ctx, int32_t layout, int32_t oct);
 /* Copies the block types back (dims product bytes). */
 DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
 
@@ -184,6 +197,10 @@ DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
    kernel derives origin / direction / tile offset of ray k itself (no 48 B/ray read).
    reseed != 0 calls srand(1) first (the state of a fresh process). */
 DDGI_API int ddgi_generate_probe_rays(ddgi_ctx* ctx, int32_t reseed);
+/* Spherical-Fibonacci set of rx*ry directions (north-star ray generator; no reference counterpart —
+   the reference draws the stratified rand() set above): cos(theta_i) = 1 - (2i+1)/n, azimuth
+   2 pi frac(i (phi - 1)).  Deterministic, no rand(). */
+DDGI_API int ddgi_generate_fibonacci_rays(ddgi_ctx* ctx);
 /* Same, from a caller-supplied table of rx*ry un-normalised sphere samples (xyz). */
 DDGI_API int ddgi_set_ray_samples(ddgi_ctx* ctx, const float* samples, size_t count);
 /* Reads the current rx*ry sample table back (3 floats each). */

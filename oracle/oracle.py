@@ -45,6 +45,8 @@ class OrcParams(C.Structure):
         ("weight_mode", C.c_int32),
         ("distance_mode", C.c_int32),
         ("distance_scale", C.c_float),
+        ("layout", C.c_int32),
+        ("oct", C.c_int32),
     ]
 
 
@@ -86,6 +88,7 @@ def load() -> C.CDLL:
     lib.orc_generate_probe_rays.argtypes = [P, vp, vp]
     lib.orc_probe_update.argtypes = [P, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, C.c_int]
     lib.orc_render_frame.argtypes = [P, vp, vp, vp, vp, vp, vp, C.c_int]
+    lib.orc_probe_update_oct.argtypes = [P, vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_int]
     lib.orc_update_lights.argtypes = [C.c_int, C.POINTER(OrcLight), C.c_int, C.c_float, C.POINTER(OrcLight)]
     lib.orc_sample_probe.argtypes = [P, vp, C.c_int, vp, vp]
     lib.orc_get_block_at.restype = C.c_int
@@ -136,7 +139,7 @@ class Scene:
     def __init__(self, *, probe_count, side_length, field_origin, rx, ry=None, lights, scene=1,
                  voxels=None, vorg=(0, 0, 0), palette=None, max_bounces=8, screen=(0, 0), procedural=False,
                  literal_colors=False, hysteresis=None, render_mode=0, visualize_probes=False, chebyshev=False,
-                 distance_scale=None):
+                 distance_scale=None, oct=None):
         self.p = OrcParams()
         p = self.p
         p.scene_mode = 0 if procedural else 1
@@ -171,6 +174,8 @@ class Scene:
         p.weight_mode = 1 if chebyshev else 0           # 1: `weight *= chebyshevWeight` restored (G:1382)
         p.distance_mode = 0 if distance_scale is None else 1  # None = the reference as shipped: distances = vec2(0)
         p.distance_scale = 1.0 if distance_scale is None else float(distance_scale)
+        p.layout = 0 if oct is None else 1   # None = the reference's one-texel-per-ray tile
+        p.oct = 0 if oct is None else int(oct)
 
     @property
     def num_rays(self):
@@ -180,7 +185,8 @@ class Scene:
     @property
     def tex_size(self):
         p = self.p
-        return p.probe_count[0] * p.probe_count[2] * p.rx, p.probe_count[1] * p.ry
+        tw, th = (p.oct, p.oct) if p.layout == 1 else (p.rx, p.ry)
+        return p.probe_count[0] * p.probe_count[2] * tw, p.probe_count[1] * th
 
 
 def generate_samples(rx: int, ry: int, reseed: bool = True) -> np.ndarray:
@@ -208,6 +214,29 @@ def probe_update(sc: Scene, rays: np.ndarray, k0: int = 0, k1: int | None = None
     r = np.ascontiguousarray(rays, dtype=np.float32)
     load().orc_probe_update(C.byref(sc.p), _ptr(r), k0, k1, _ptr(alb), _ptr(dist), _ptr(f32), _ptr(steps), _ptr(oob), threads)
     return alb, dist, f32, steps, oob
+
+
+def probe_update_oct(sc: Scene, rays: np.ndarray, tex=None, dist=None, p0: int = 0, p1: int | None = None, threads: int = 0):
+    """Octahedral layout (no reference output exists for it).  Returns (albedo [H,W], distance [H,W], lookups [R])."""
+    W, H = sc.tex_size
+    n_probes = sc.p.probe_count[0] * sc.p.probe_count[1] * sc.p.probe_count[2]
+    p1 = n_probes if p1 is None else p1
+    alb = np.zeros((H, W), dtype=np.uint32) if tex is None else tex
+    dst = np.zeros((H, W), dtype=np.uint32) if dist is None else dist
+    steps = np.zeros(sc.num_rays, dtype=np.uint32)
+    r = np.ascontiguousarray(rays, dtype=np.float32)
+    load().orc_probe_update_oct(C.byref(sc.p), _ptr(r), p0, p1, _ptr(alb), _ptr(dst), _ptr(steps), threads)
+    return alb, dst, steps
+
+
+def fibonacci_samples(n: int) -> np.ndarray:
+    """The spherical-Fibonacci set of ddgi_generate_fibonacci_rays, restated independently (fp64, rounded once)."""
+    i = np.arange(n, dtype=np.float64)
+    f = i * 0.61803398874989484820
+    az = 6.283185307179586476925 * (f - np.floor(f))
+    z = 1.0 - (2.0 * i + 1.0) / n
+    ring = np.sqrt(1.0 - z * z)
+    return np.stack([np.cos(az) * ring, np.sin(az) * ring, z], axis=1).astype(np.float32)
 
 
 def render_frame(sc: Scene, cam: np.ndarray, tex_albedo: np.ndarray, threads: int = 0, tex_distances=None):

@@ -33,6 +33,7 @@ struct SimParams {
     float hysteresis;
     int32_t render_mode, visualize_probes, weight_mode, distance_mode;
     float distance_scale;
+    int32_t layout, oct;
 };
 
 struct Built {
@@ -91,6 +92,10 @@ static void build(const SimParams* S, const float* cam, Built* B)
     P.visualize_probes = S->visualize_probes;
     P.weight_mode = S->weight_mode;
     P.distance_scale = S->distance_scale;
+    P.layout = S->layout;
+    P.oct = S->oct;
+    P.tile_w = S->layout == 1 ? S->oct : S->rx;
+    P.tile_h = S->layout == 1 ? S->oct : S->ry;
     if (cam) {
         memcpy(P.cam, cam, sizeof(P.cam));
         P.cam_w = 1.0f / (float)tan((double)(0.5f * cam[17]));
@@ -142,7 +147,7 @@ void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex,
     Built B;
     build(S, cam, &B);
     const FrameParams& P = B.P;
-    int W = P.probe_count[0] * P.probe_count[2] * P.rx;
+    int W = P.probe_count[0] * P.probe_count[2] * P.tile_w;
     int w = P.screen_w, h = P.screen_h;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int gy = 0; gy < (h / 16) * 16; gy++)
@@ -152,7 +157,7 @@ void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex,
             v3 o, d;
             pinhole_ray(P, cx, cy, &o, &d);
             uint32_t n = 0;
-            bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0;
+            bool ext = (P.render_mode >= 1 && P.render_mode <= 5) || P.visualize_probes != 0 || P.weight_mode != 0 || P.layout != 0;
             v3 s = ext ? shade_pixel<true>(P, tex, dist_tex, W, o, d, n) : shade_pixel<false>(P, tex, dist_tex, W, o, d, n);
             s = V3(0, 0, 0) + s;
             size_t at = (size_t)gy * w + gx;
@@ -160,6 +165,49 @@ void sim_render_frame(const SimParams* S, const float* cam, const uint32_t* tex,
             if (f32) { f32[4 * at] = s.x; f32[4 * at + 1] = s.y; f32[4 * at + 2] = s.z; f32[4 * at + 3] = 1.0f; }
             if (lookups) lookups[at] = n;
         }
+}
+
+// Octahedral layout: the trace (either variant) into a ray buffer, then the blend with the warp's
+// 32 lanes and its xor-butterfly emulated in order (ddgi_kernels.cu: probe_blend_octahedral).
+void sim_probe_update_oct(const SimParams* S, const float* rays /* R x 12 */, int variant, uint32_t* albedo, uint32_t* distance,
+                          uint32_t* lookups)
+{
+    Built B;
+    build(S, nullptr, &B);
+    const FrameParams& P = B.P;
+    const int n = P.rx * P.ry, oct = P.oct;
+    const int W = P.probe_count[0] * P.probe_count[2] * oct;
+    const int64_t probes = (int64_t)P.probe_count[0] * P.probe_count[1] * P.probe_count[2];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t p = 0; p < probes; p++) {
+        std::vector<float> dirs(3 * (size_t)n), rad(4 * (size_t)n);
+        for (int i = 0; i < n; i++) {
+            int64_t k = p * n + i;
+            const float* r = rays + 12 * k;
+            v3 o = V3(r[0], r[1], r[2]), d = V3(r[4], r[5], r[6]);
+            uint32_t cnt = 0;
+            float first_t = 0.0f;
+            v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, cnt, &first_t)
+                                : wavefront_trace_scalar(P, o, d, (uint32_t)k, cnt, &first_t);
+            dirs[3 * i] = d.x; dirs[3 * i + 1] = d.y; dirs[3 * i + 2] = d.z;
+            rad[4 * i] = c.x; rad[4 * i + 1] = c.y; rad[4 * i + 2] = c.z; rad[4 * i + 3] = first_t;
+            if (lookups) lookups[k] = cnt;
+        }
+        int cx, cy;
+        tile_origin(P, (int)p, &cx, &cy);
+        for (int t = 0; t < oct * oct; t++) {
+            int u = t % oct, v = t / oct;
+            v3 dir_t = oct_texel_dir(u, v, oct);
+            OctAcc lane[32], next[32];
+            for (int l = 0; l < 32; l++) lane[l] = oct_lane_partial(dir_t, dirs.data(), rad.data(), n, l, S->distance_scale);
+            for (int off = 16; off >= 1; off >>= 1) {
+                for (int l = 0; l < 32; l++) next[l] = oct_add(lane[l], lane[l ^ off]);
+                memcpy(lane, next, sizeof(lane));
+            }
+            size_t at = (size_t)(cy + v) * W + (cx + u);
+            oct_finalize(lane[0], S->blend_mode, S->hysteresis, albedo[at], distance[at], &albedo[at], &distance[at]);
+        }
+    }
 }
 
 void sim_bake_scene(int scene, const int32_t* org, const int32_t* dim, uint8_t* out)

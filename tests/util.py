@@ -28,6 +28,7 @@ def hostsim():
         vp = C.c_void_p
         lib.sim_probe_update.argtypes = [P, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, vp, vp]
         lib.sim_render_frame.argtypes = [P, vp, vp, vp, vp, vp, vp]
+        lib.sim_probe_update_oct.argtypes = [P, vp, C.c_int, vp, vp, vp]
         lib.sim_bake_scene.argtypes = [C.c_int, vp, vp, vp]
         lib.sim_pin_sincos.argtypes = [vp, C.c_int, vp, vp]
         lib.sim_pin_acos.argtypes = [vp, C.c_int, vp]
