@@ -335,6 +335,14 @@ def main():
         h2d = pinned_samples.numel() * 4 + 32 + 48 + 80 + 4 * 28
         d2h = nbytes if world == 1 else (slab[1] - slab[0]) * row_bytes
 
+        # 1 GPU: the texture is double-buffered in the engine, so the D2H of step i (asynchronous, on the
+        # engine's copy stream, into one of two pinned buffers) overlaps the trace of step i+1; every
+        # step's whole albedo plane is still read back inside the timed region (read_wait at its end)
+        pipelined = world == 1
+        host_pair = [host_tex, torch.empty(nbytes, dtype=torch.uint8).pin_memory()] if pipelined else [host_tex]
+        if pipelined:
+            r.set_double_buffer(True)
+
         def e2e_step():
             frame_no[0] += 1
             r.render_settings.time = 2.0 * frame_no[0]
@@ -344,9 +352,8 @@ def main():
             assert rc == 0
             r.probe_update()
             exchange()
-            if world == 1:
-                rc = lib.ddgi_read_probe_texture(r._ctx, 0, 0, host_tex.data_ptr(), nbytes)
-                assert rc == 0
+            if pipelined:
+                r.read_probe_texture_async(host_pair[frame_no[0] & 1].data_ptr(), nbytes, 0)
             else:
                 # every replica is complete after the exchange: each rank reads back 1/N of the albedo plane
                 host_tex[:d2h].copy_(planes[0][slab[0] * row_bytes:slab[1] * row_bytes], non_blocking=True)
@@ -354,17 +361,24 @@ def main():
 
         for _ in range(3):
             e2e_step()
+        if pipelined:
+            r.read_wait()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
+        if pipelined:
+            r.read_wait()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local}", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if pipelined:
+            r.set_double_buffer(False)
         e2e = {"value": n_rays * args.steps / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "inputs": "ray-sample table + uniforms + lights (pinned host)",
-               "result": "albedo probe texture rows of this rank (pinned host)"}
+               "result": "albedo probe texture rows of this rank (pinned host)",
+               "pipelining": "double-buffered texture: the D2H of step i overlaps the trace of step i+1" if pipelined else "none"}
         # literal storage-buffer mode: the whole ProbeRay array re-uploaded every frame, as
         # RVPT::update does (rvpt.cpp:285)
         if world == 1:

@@ -59,13 +59,22 @@ struct ddgi_ctx {
     // rays
     std::vector<float> samples;  // rx*ry raw sphere samples (xyz)
     float* d_dirs = nullptr;     // normalised, generated mode
+    size_t dirs_cap = 0;
+    cudaEvent_t ev_update = nullptr;  // recorded after every probe update: what a new ray table must wait for
     float4* d_rays = nullptr;    // literal storage-buffer mode
     size_t n_rays_ssbo = 0;
     int ray_mode = 0;  // 0 none, 1 generated, 2 storage buffer
 
     // probe textures: one allocation, albedo then distance
     int tex_w = 0, tex_h = 0;
-    uint32_t* d_tex = nullptr;
+    uint32_t* d_tex = nullptr;  // the current texture allocation (= d_tex_pair[cur_tex] under double buffering)
+    // double buffering (ddgi_set_double_buffer): probe updates alternate between two allocations so
+    // that frame i can be copied out (ddgi_read_probe_texture_async) while frame i+1 is traced
+    bool double_buffer = false;
+    uint32_t* d_tex_pair[2] = {nullptr, nullptr};
+    int cur_tex = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // last asynchronous read of each buffer
     float4* d_tex_f32 = nullptr;
     uint32_t* d_ray_lookups = nullptr;
     int row0 = 0, row1 = 0;  // probe rows owned by this context (contiguous ownership)
@@ -212,15 +221,22 @@ static int resize_textures(ddgi_ctx* ctx)
     int h = ctx->field.probe_count[1] * tile_h(ctx);
     if (w == ctx->tex_w && h == ctx->tex_h && ctx->d_tex) return DDGI_OK;
     if (ctx->n_peers) return fail(ctx, DDGI_E_STATE, "close peers before resizing the probe textures");
-    dfree(ctx->d_tex);
+    if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+    dfree(ctx->d_tex_pair[0]);
+    dfree(ctx->d_tex_pair[1]);
+    ctx->d_tex = nullptr;
     dfree(ctx->d_tex_f32);
     dfree(ctx->d_ray_lookups);
     ctx->tex_w = w;
     ctx->tex_h = h;
     size_t n = tex_texels(ctx);
     // both planes, then the epoch flags of the fused exchange (ddgi_exchange_barrier)
-    CU(cudaMalloc(&ctx->d_tex, (2 * n + kFlagWords) * sizeof(uint32_t)));
-    CU(cudaMemset(ctx->d_tex, 0, (2 * n + kFlagWords) * sizeof(uint32_t)));
+    for (int b = 0; b < (ctx->double_buffer ? 2 : 1); b++) {
+        CU(cudaMalloc(&ctx->d_tex_pair[b], (2 * n + kFlagWords) * sizeof(uint32_t)));
+        CU(cudaMemset(ctx->d_tex_pair[b], 0, (2 * n + kFlagWords) * sizeof(uint32_t)));
+    }
+    ctx->cur_tex = 0;
+    ctx->d_tex = ctx->d_tex_pair[0];
     ctx->epoch = 0;
     return DDGI_OK;
 }
@@ -390,8 +406,14 @@ static int upload_dirs(ddgi_ctx* ctx)
         dirs[3 * i + 1] = d.y;
         dirs[3 * i + 2] = d.z;
     }
-    dfree(ctx->d_dirs);
-    CU(cudaMalloc(&ctx->d_dirs, n * 3 * sizeof(float)));
+    // the last probe update may still be reading the table (a cudaFree here used to hide that by
+    // stalling the whole device every frame): wait for exactly that launch
+    if (ctx->ev_update) CU(cudaEventSynchronize(ctx->ev_update));
+    if (n > ctx->dirs_cap) {
+        dfree(ctx->d_dirs);
+        CU(cudaMalloc(&ctx->d_dirs, n * 3 * sizeof(float)));
+        ctx->dirs_cap = n;
+    }
     CU(cudaMemcpy(ctx->d_dirs, dirs.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
     ctx->ray_mode = 1;
     return DDGI_OK;
@@ -435,7 +457,11 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_palette);
     dfree(ctx->d_dirs);
     dfree(ctx->d_rays);
-    dfree(ctx->d_tex);
+    dfree(ctx->d_tex_pair[0]);
+    dfree(ctx->d_tex_pair[1]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int b = 0; b < 2; b++)
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
     dfree(ctx->d_tex_f32);
     dfree(ctx->d_ray_lookups);
     dfree(ctx->d_frame);
@@ -447,6 +473,7 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_barrier_error);
     dfree(ctx->d_ray_out);
     dfree(ctx->d_owned);
+    if (ctx->ev_update) cudaEventDestroy(ctx->ev_update);
     delete ctx;
 }
 
@@ -766,6 +793,7 @@ int ddgi_set_probe_rays(ddgi_ctx* ctx, const ddgi_probe_ray* rays, size_t count)
     NEED(ctx->have_field, "set the irradiance field first");
     NEED(rays && count == num_rays(ctx), "expected probes*rx*ry rays");
     CU(cudaSetDevice(ctx->device));
+    if (ctx->ev_update) CU(cudaEventSynchronize(ctx->ev_update));  // the last update may still read the old list
     if (ctx->n_rays_ssbo != count) {
         dfree(ctx->d_rays);
         CU(cudaMalloc(&ctx->d_rays, count * sizeof(ddgi_probe_ray)));
@@ -871,6 +899,7 @@ int ddgi_open_peers(ddgi_ctx* ctx, int32_t n_peers, const void* handles64, int32
     if (!ctx) return DDGI_E_INVALID;
     NEED(ctx->d_tex, "no probe texture");
     NEED(n_peers >= 1 && n_peers <= kMaxPeers && handles64 && self_index >= 0 && self_index < n_peers, "bad peers");
+    NEED(!ctx->double_buffer, "the fused exchange maps one allocation per rank: turn double buffering off");
     CU(cudaSetDevice(ctx->device));
     ddgi_close_peers(ctx);
     for (int g = 0; g < n_peers; g++) {
@@ -967,8 +996,17 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     J.distance_scale = ctx->distance_scale;
     J.tex_w = ctx->tex_w;
     J.tex_h = ctx->tex_h;
+    const uint32_t* old_tex = ctx->d_tex;
+    if (ctx->double_buffer) {
+        // write the other allocation; the last asynchronous read of it must have finished
+        int next = ctx->cur_tex ^ 1;
+        if (ctx->ev_copied[next]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_copied[next], 0));
+        ctx->cur_tex = next;
+        ctx->d_tex = ctx->d_tex_pair[next];
+    }
     J.albedo = ctx->d_tex;
     J.distance = ctx->d_tex + tex_texels(ctx);
+    J.albedo_old = old_tex;
     J.albedo_f32 = ctx->debug ? ctx->d_tex_f32 : nullptr;
     J.lookups = ctx->debug ? ctx->d_ray_lookups : nullptr;
     for (int g = 0; g < ctx->n_peers; g++) {
@@ -1011,6 +1049,8 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         O.tex_w = ctx->tex_w;
         O.albedo = J.albedo;
         O.distance = J.distance;
+        O.albedo_old = old_tex;
+        O.distance_old = old_tex + tex_texels(ctx);
         O.blend = ctx->blend_mode;
         O.hysteresis = ctx->field.hysteresis;
         O.distance_scale = ctx->distance_scale;
@@ -1022,6 +1062,8 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         CU(launch_probe_blend_octahedral(P, O, (cudaStream_t)stream, &l));
     }
     ctx->launches += l;
+    if (!ctx->ev_update) CU(cudaEventCreateWithFlags(&ctx->ev_update, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_update, (cudaStream_t)stream));
     if (calibrate) {
         // First update after the scene / rays / field changed: this launch also recorded the largest
         // voxel-lookup count per slot.  Read them once (the only synchronising probe update) and
@@ -1121,6 +1163,51 @@ int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, void* dst
         return DDGI_OK;
     }
     return fail(ctx, DDGI_E_INVALID, "unknown format");
+}
+
+int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->n_peers == 0, "close peers first: the fused exchange maps one allocation per rank");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    bool want = on != 0;
+    if (want == ctx->double_buffer) return DDGI_OK;
+    ctx->double_buffer = want;
+    if (!ctx->d_tex) return DDGI_OK;  // no field yet: resize_textures allocates the pair
+    size_t bytes = (2 * tex_texels(ctx) + kFlagWords) * sizeof(uint32_t);
+    if (want) {
+        int other = ctx->cur_tex ^ 1;
+        CU(cudaMalloc(&ctx->d_tex_pair[other], bytes));
+        CU(cudaMemcpy(ctx->d_tex_pair[other], ctx->d_tex, bytes, cudaMemcpyDeviceToDevice));
+    } else {
+        dfree(ctx->d_tex_pair[ctx->cur_tex ^ 1]);
+    }
+    return DDGI_OK;
+}
+
+int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex, "no probe texture");
+    NEED(dst && (which == 0 || which == 1) && bytes == tex_texels(ctx) * 4, "expected width*height*4 bytes");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int b = ctx->cur_tex;
+    if (!ctx->ev_copied[b]) CU(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+    // after the probe update that produced this buffer, on the engine's own copy stream
+    if (ctx->ev_update) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_update, 0));
+    CU(cudaMemcpyAsync(dst, ctx->d_tex + (which ? tex_texels(ctx) : 0), bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    return DDGI_OK;
+}
+
+int ddgi_read_wait(ddgi_ctx* ctx)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+    return DDGI_OK;
 }
 
 int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size_t bytes)

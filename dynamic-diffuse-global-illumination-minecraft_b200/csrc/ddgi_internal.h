@@ -27,6 +27,7 @@ struct ProbeJob {
     int tex_w, tex_h;
     uint32_t* albedo;     // W*H RGBA8
     uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)
+    const uint32_t* albedo_old;  // what the hysteresis blend reads: the same plane, or the previous frame's under double buffering
     float4* albedo_f32;   // debug: pre-quantisation values, or nullptr
     uint32_t* lookups;    // debug: per-ray voxel lookups, or nullptr
     int blend;            // 1: blend into the old texel with `hysteresis` (probe_pass.comp:298-299 restored)
@@ -63,6 +64,8 @@ struct OctJob {
     int tex_w;
     uint32_t* albedo;
     uint32_t* distance;
+    const uint32_t* albedo_old;    // blend sources: the same planes, or the previous frame's under double buffering
+    const uint32_t* distance_old;
     int blend;
     float hysteresis;
     float distance_scale;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
         return;
     }
     size_t t = (size_t)ty * J.tex_w + tx;
-    if (J.blend) color = blend_hysteresis(J.albedo[t], color, J.hysteresis);
+    if (J.blend) color = blend_hysteresis(J.albedo_old[t], color, J.hysteresis);
     uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);
     J.albedo[t] = rgba;
     // probe_pass.comp:276,302: distances = vec2(0) as shipped; distance mode 1 stores the
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kOctThreads) probe_blend_octahedral(const __gr
         if (lane == 0) {
             size_t at = (size_t)(cy + v) * J.tex_w + (cx + u);
             uint32_t alb, dist;
-            oct_finalize(a, J.blend, J.hysteresis, J.albedo[at], J.distance[at], &alb, &dist);
+            oct_finalize(a, J.blend, J.hysteresis, J.albedo_old[at], J.distance_old[at], &alb, &dist);
             J.albedo[at] = alb;
             J.distance[at] = dist;
             for (int g = 0; g < J.n_peers; g++) {

@@ -305,6 +305,16 @@ class RVPT:
         self._check(self._lib.ddgi_read_probe_texture(self._ctx, which, fmt, out.ctypes.data, out.nbytes))
         return out
 
+    def set_double_buffer(self, on: bool):
+        self._check(self._lib.ddgi_set_double_buffer(self._ctx, 1 if on else 0))
+
+    def read_probe_texture_async(self, out_ptr: int, nbytes: int, which: int = 0):
+        """Enqueues the copy of the latest frame into (pinned) host memory at out_ptr; valid after read_wait()."""
+        self._check(self._lib.ddgi_read_probe_texture_async(self._ctx, which, out_ptr, nbytes))
+
+    def read_wait(self):
+        self._check(self._lib.ddgi_read_wait(self._ctx))
+
     def write_probe_texture(self, tex: np.ndarray, which: int = 0):
         t = np.ascontiguousarray(tex, dtype=np.uint32)
         self._check(self._lib.ddgi_write_probe_texture(self._ctx, which, t.ctypes.data, t.nbytes))

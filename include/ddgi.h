@@ -260,6 +260,18 @@ DDGI_API int ddgi_sync(ddgi_ctx* ctx);
                             only kept when ddgi_set_debug(ctx, 1) */
 DDGI_API int ddgi_probe_texture_size(const ddgi_ctx* ctx, int32_t* width, int32_t* height);
 DDGI_API int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, void* dst, size_t bytes);
+/* Double buffering (default off): probe updates alternate between two texture allocations, the
+   hysteresis blend reads the previous frame's, ddgi_render_frame and the reads use the latest.
+   With it frame i can be copied to the host while frame i+1 is traced:
+   ddgi_read_probe_texture_async enqueues the copy of the latest frame on the engine's own copy
+   stream, ordered after the update that produced it (dst should be pinned; it is valid after
+   ddgi_read_wait, or once a later ddgi_read_wait / ddgi_sync returns); the next update but one
+   waits, on the device, for that copy before it overwrites the buffer.  Not with the fused
+   exchange (one mapped allocation per rank).  With partial probe ownership and no exchange the
+   texels a context does not own are one frame older in every other buffer. */
+DDGI_API int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on);
+DDGI_API int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes);
+DDGI_API int ddgi_read_wait(ddgi_ctx* ctx);
 /* Uploads texture contents (checkpoint / resume, and pixel-pass tests). */
 DDGI_API int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size_t bytes);
 DDGI_API int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes);

@@ -307,3 +307,45 @@ def test_frame_bands_compose_to_the_whole_frame():
         got = r.read_frame()
         y0, y1 = rows[1]
         assert np.array_equal(got[y0:y1], whole[y0:y1]) and (got[:y0] == 0).all() and (got[y1:] == 0).all()
+
+
+def test_double_buffered_async_reads_match_single_buffered_frames():
+    """ddgi_set_double_buffer + ddgi_read_probe_texture_async: four frames with moving lights and
+    the hysteresis blend (which must read the PREVIOUS frame's buffer) give the same textures as
+    the single-buffered engine, each read back while the next frame is being traced."""
+    cfg = CFG["field_8"]
+    frames = 4
+
+    def run(double):
+        out = []
+        with make_engine(cfg, debug=False) as r:
+            r.ir.hysteresis = 0.6
+            r.set_blend_mode(ddgi_b200.capi.BLEND_HYSTERESIS)
+            r.set_double_buffer(double)
+            W, H = r.probe_texture_size
+            bufs = [np.zeros((H, W), dtype=np.uint32) for _ in range(frames)]
+            for f in range(frames):
+                r.render_settings.time = 2.0 * (f + 1)
+                r.lights = util.configs.lights_for(cfg, r.render_settings.time)
+                r.update(advance_time=False)
+                r.probe_update()
+                if double:
+                    r.read_probe_texture_async(bufs[f].ctypes.data, bufs[f].nbytes, 0)
+                else:
+                    r.sync()
+                    bufs[f][:] = r.read_probe_texture(0)
+            r.read_wait()
+            r.sync()
+            out = [b.copy() for b in bufs]
+            last = r.read_probe_texture(0)
+            assert np.array_equal(last, out[-1])   # the synchronous read sees the latest buffer
+            r.render_frame()
+            r.sync()
+            return out, r.read_frame().copy()
+
+    single, frame_s = run(False)
+    double, frame_d = run(True)
+    for f in range(frames):
+        assert np.array_equal(single[f], double[f]), f"frame {f}"
+    assert not np.array_equal(single[0], single[-1])
+    assert np.array_equal(frame_s, frame_d)
