@@ -1,5 +1,6 @@
+"""A/B timing of the probe-update kernel on field_32 (1 GPU, cold L2, median of 15): run with DDGI_LIB=<alternative build> to compare builds.  Not a bench value."""
 import importlib, os, sys, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddgi_b200
 configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
 cfg = configs.CONFIGS["field_32"]
