@@ -349,3 +349,68 @@ def test_double_buffered_async_reads_match_single_buffered_frames():
         assert np.array_equal(single[f], double[f]), f"frame {f}"
     assert not np.array_equal(single[0], single[-1])
     assert np.array_equal(frame_s, frame_d)
+
+
+def test_field_32_full_size_sampled_parity_and_properties():
+    """BASELINE configs[3] at its FULL size (32^3 probes x 256 rays = 8 388 608 probe rays, 512^3
+    voxels, 4 moving lights).  The oracle cannot trace the whole field in seconds, so:
+      * 48 probes drawn at random (plus the field's corners and centre) are traced by the oracle
+        on the engine's own baked voxels and compared texel for texel and lookup for lookup;
+      * idempotence: a second update gives the same bytes; schedule / slot independence;
+      * composition: 4 round-robin probe shards tile the full texture (what 4 GPUs compute);
+      * a checksum of per-row checksums over all 16 384 x 512 texels pins the frame for the record.
+    The baker itself is checked against its numpy restatement on field_8 (test_bake_matches_oracle)."""
+    cfg = CFG["field_32"]
+    X, Y, Z = cfg["probe_count"]
+    rx, ry = cfg["tile"]
+    n = rx * ry
+    with make_engine(cfg, debug=True, time=6.0) as r:
+        r.probe_update()
+        r.sync()
+        full = r.read_probe_texture(0).copy()
+        lk = r.read_lookup_counts(0).reshape(X * Y * Z, n)
+        vox = r.read_voxels(cfg["voxels"][1])
+        # --- sampled oracle parity on the engine's voxels
+        sc = util.oracle_scene(cfg, time=6.0, voxels=vox)
+        rays = oracle_rays(sc, cfg)
+        rng = np.random.default_rng(32)
+        probes = sorted(set(rng.integers(0, X * Y * Z, size=48).tolist()) | {0, X * Y * Z - 1, (Y // 2 * Z + Z // 2) * X + X // 2})
+        tiles = full.reshape(Y, ry, X * Z, rx).transpose(0, 2, 1, 3).reshape(X * Y * Z, ry, rx)
+        W, H = sc.tex_size
+        want_tex = np.zeros((H, W), dtype=np.uint32)
+        open_probes = 0
+        for p in probes:
+            _, _, _, steps, _ = oracle.probe_update(sc, rays, p * n, (p + 1) * n, tex=want_tex)
+            assert np.array_equal(lk[p], steps[p * n:(p + 1) * n]), f"probe {p}: lookup counts differ"
+            open_probes += int(steps[p * n:(p + 1) * n].max() > 16)
+        want_tiles = want_tex.reshape(Y, ry, X * Z, rx).transpose(0, 2, 1, 3).reshape(X * Y * Z, ry, rx)
+        assert np.array_equal(tiles[probes], want_tiles[probes])
+        assert open_probes >= 5, "the sample must include probes in the open cavity, not only rock"
+        mean_lookups = lk.mean()
+        assert 100.0 < mean_lookups < 115.0   # the figure bench.py's algorithmic bytes are built on (~106.4)
+        # --- idempotence, schedule independence
+        r.set_debug(False)
+        for slot, sched in ((32, True), (0, True), (32, False)):
+            r.set_schedule_slot(slot)
+            r.set_auto_schedule(sched)
+            for _ in range(2):
+                r.probe_update()
+            r.sync()
+            assert np.array_equal(r.read_probe_texture(0), full)
+        # --- 4 round-robin shards compose to the full texture
+        acc = np.zeros_like(tiles)
+        owner = np.arange(X * Y * Z) % 4
+        for rank in range(4):
+            r.write_probe_texture(np.zeros_like(full))
+            r.set_probes_cyclic(rank, 4, 1)
+            r.probe_update()
+            r.sync()
+            t = r.read_probe_texture(0).reshape(Y, ry, X * Z, rx).transpose(0, 2, 1, 3).reshape(X * Y * Z, ry, rx)
+            assert (t[owner != rank] == 0).all()
+            acc[owner == rank] = t[owner == rank]
+        assert np.array_equal(acc, tiles)
+    # --- checksum of checksums (size-independent record of the frame)
+    row_sums = full.astype(np.uint64).sum(axis=1)
+    total = int((row_sums * (np.arange(H, dtype=np.uint64) + 1)).sum() % (1 << 61))
+    print(f"field_32 t=6: mean lookups/ray {mean_lookups:.3f}, checksum of row checksums {total}")
+    assert (full >> 24 == 255).all()   # every texel was written (alpha = 1)
