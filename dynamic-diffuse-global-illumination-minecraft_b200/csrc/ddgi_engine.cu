@@ -70,6 +70,11 @@ struct ddgi_ctx {
     uint32_t* d_tex = nullptr;  // the current texture allocation (= d_tex_pair[cur_tex] under double buffering)
     // double buffering (ddgi_set_double_buffer): probe updates alternate between two allocations so
     // that frame i can be copied out (ddgi_read_probe_texture_async) while frame i+1 is traced
+    // The reference stores vec4(0) into the distance image every frame (probe_pass.comp:276,302).
+    // While nothing else has written the plane it already holds those zeros, in every replica, and
+    // the stores (one local + one per peer and ray) are skipped.  Set by anything that may leave
+    // other bytes there; never cleared (a re-created texture starts clean again).
+    bool distance_dirty[2] = {false, false};
     bool double_buffer = false;
     uint32_t* d_tex_pair[2] = {nullptr, nullptr};
     int cur_tex = 0;
@@ -238,6 +243,7 @@ static int resize_textures(ddgi_ctx* ctx)
     ctx->cur_tex = 0;
     ctx->d_tex = ctx->d_tex_pair[0];
     ctx->epoch = 0;
+    ctx->distance_dirty[0] = ctx->distance_dirty[1] = false;
     return DDGI_OK;
 }
 
@@ -1006,6 +1012,10 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     }
     J.albedo = ctx->d_tex;
     J.distance = ctx->d_tex + tex_texels(ctx);
+    if (ctx->distance_mode == DDGI_DISTANCE_MOMENTS || ctx->layout == DDGI_LAYOUT_OCTAHEDRAL) ctx->distance_dirty[ctx->cur_tex] = true;
+    // peers run the same sequence of modes, so their replicas are clean exactly when this one is;
+    // an uploaded plane (ddgi_write_probe_texture) or a double-buffer copy marks it dirty below
+    const bool skip_distance = !ctx->distance_dirty[ctx->cur_tex];
     J.albedo_old = old_tex;
     J.albedo_f32 = ctx->debug ? ctx->d_tex_f32 : nullptr;
     J.lookups = ctx->debug ? ctx->d_ray_lookups : nullptr;
@@ -1036,8 +1046,10 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         J.warp_times = ctx->d_warp_times;
         ctx->warp_times_n = warps;
     }
+    if (skip_distance && ctx->layout != DDGI_LAYOUT_OCTAHEDRAL) J.distance = nullptr;
     int l = 0;
     CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, ctx->grid_limit, (cudaStream_t)stream, &l));
+    if (!J.distance) J.distance = ctx->d_tex + tex_texels(ctx);
     if (ctx->layout == 1) {
         OctJob O;
         memset(&O, 0, sizeof(O));
@@ -1180,6 +1192,7 @@ int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on)
         int other = ctx->cur_tex ^ 1;
         CU(cudaMalloc(&ctx->d_tex_pair[other], bytes));
         CU(cudaMemcpy(ctx->d_tex_pair[other], ctx->d_tex, bytes, cudaMemcpyDeviceToDevice));
+        ctx->distance_dirty[other] = ctx->distance_dirty[ctx->cur_tex];
     } else {
         dfree(ctx->d_tex_pair[ctx->cur_tex ^ 1]);
     }
@@ -1217,6 +1230,7 @@ int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size
     NEED(src && (which == 0 || which == 1) && bytes == tex_texels(ctx) * 4, "expected width*height*4 bytes");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpy(ctx->d_tex + (which ? tex_texels(ctx) : 0), src, bytes, cudaMemcpyHostToDevice));
+    if (which == 1) ctx->distance_dirty[ctx->cur_tex] = true;
     return DDGI_OK;
 }
 

@@ -26,7 +26,7 @@ struct ProbeJob {
     uint32_t* slot_cost;  // calibration launch: per-slot MAX of the rays' voxel lookups, else nullptr
     int tex_w, tex_h;
     uint32_t* albedo;     // W*H RGBA8
-    uint32_t* distance;   // W*H RGBA8 (the reference stores zeros)
+    uint32_t* distance;   // W*H RGBA8 (the reference stores zeros); nullptr = already all zero, skip the stores
     const uint32_t* albedo_old;  // what the hysteresis blend reads: the same plane, or the previous frame's under double buffering
     float4* albedo_f32;   // debug: pre-quantisation values, or nullptr
     uint32_t* lookups;    // debug: per-ray voxel lookups, or nullptr

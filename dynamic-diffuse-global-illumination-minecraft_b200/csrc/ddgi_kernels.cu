@@ -81,11 +81,12 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
         float d = first_t / J.distance_scale;
         moments = pack_rgba8(d, d * d, 0.0f, 0.0f);
     }
-    J.distance[t] = moments;
+    // (J.distance == nullptr: the plane is known to hold the zeros the reference would store again)
+    if (J.distance) J.distance[t] = moments;
 #pragma unroll 1
     for (int g = 0; g < J.n_peers; g++) {
         J.peer_albedo[g][t] = rgba;
-        J.peer_distance[g][t] = moments;
+        if (J.distance) J.peer_distance[g][t] = moments;
     }
     if (J.albedo_f32) J.albedo_f32[t] = make_float4(color.x, color.y, color.z, 1.0f);
     if (J.lookups) J.lookups[k] = lookups;

@@ -44,6 +44,13 @@ def timed(reps=10):
 
 
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+if len(sys.argv) > 3 and sys.argv[3] == "march_min":   # sweep of the scheduling knob on both shares
+    for w in (1, world):
+        r.set_probes_cyclic(0, w, 1)
+        for mm in (8, 12, 14, 16, 18, 20, 24):
+            r.set_tuning(mm)
+            print(f"world {w} march_min {mm:2d}: {timed():7.3f} ms")
+    sys.exit(0)
 for w in (1, world):
     for sched, slot in ((1, 0), (1, 128), (1, 64), (1, 32), (0, 0)):
         for limit in (0,):
