@@ -343,11 +343,16 @@ def main():
         if pipelined:
             r.set_double_buffer(True)
 
-        def e2e_step():
+        def e2e_prep():
+            # host side of a step: move the lights, rebuild and hand over the uniforms (no device work)
             frame_no[0] += 1
             r.render_settings.time = 2.0 * frame_no[0]
             r.lights = configs.lights_for(cfg, r.render_settings.time)
             r.update(advance_time=False)
+
+        def e2e_step():
+            if pipelined:
+                e2e_prep()   # overlaps the previous step's trace; set_ray_samples then waits for that trace
             rc = lib.ddgi_set_ray_samples(r._ctx, pinned_samples.data_ptr(), rx * ry)
             assert rc == 0
             r.probe_update()
@@ -355,10 +360,14 @@ def main():
             if pipelined:
                 r.read_probe_texture_async(host_pair[frame_no[0] & 1].data_ptr(), nbytes, 0)
             else:
-                # every replica is complete after the exchange: each rank reads back 1/N of the albedo plane
+                # every replica is complete after the exchange: each rank reads back 1/N of the albedo plane;
+                # the next step's host-side uniforms are prepared while this step runs on the device
                 host_tex[:d2h].copy_(planes[0][slab[0] * row_bytes:slab[1] * row_bytes], non_blocking=True)
+                e2e_prep()
                 torch.cuda.current_stream().synchronize()
 
+        if not pipelined:
+            e2e_prep()
         for _ in range(3):
             e2e_step()
         if pipelined:
