@@ -5,8 +5,10 @@
 
 One step = one frame's probe update over the whole probe field: 4 dynamic lights are
 moved (host), every probe ray is traced (ddgi_probe_update) and, on N > 1 GPUs, the
-probe-row shards are exchanged (NCCL all-gather or the fused peer-store kernel).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+shards are exchanged (default: the kernel stores its texels into every replica over NVLink and a
+one-warp epoch-flag kernel is the completion barrier; --exchange nccl: in-place all-gathers).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field; --verify (N > 1)
+checks every replica against a full single-GPU update.
 """
 from __future__ import annotations
 

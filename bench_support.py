@@ -72,8 +72,45 @@ def _time_oracle(cfg, voxels, steps, warmup, time0=0.0):
             "mean_lookups": float(lookups.mean()), "tex": tex, "k": (k0, k1)}
 
 
+def _reference_shaders_available(cfg):
+    """oracle/_ref (the reference's own shaders transpiled to C++) has the reference's scenes, light
+    tables and square ray tiles compiled in: it can run a workload only if that is what the workload is
+    (the Cornell configs; the cave workloads use flat colours and field_32 a synthetic voxel field)."""
+    from oracle import ref
+
+    return ref.available() and cfg["scene"] == 1 and cfg["lights"] == "default" and cfg["tile"][0] == cfg["tile"][1]
+
+
+def _time_reference_shaders(cfg, steps, warmup):
+    """probe_pass.comp itself (transpiled, 1 thread: the shader's globals are process-wide) over ALL
+    probe rays of the workload."""
+    from oracle import oracle, ref
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+
+    s = cfg["tile"][0]
+    sc = util.oracle_scene(cfg, procedural=True)
+    rays = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = ref.probe_pass(scene=cfg["scene"], probe_count=cfg["probe_count"], side_length=cfg["side_length"],
+                             field_origin=cfg["field_origin"], s=s, rays=rays, max_bounces=cfg.get("max_bounces", 8))
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return {"rays": rays.shape[0], "seconds": float(np.mean(times)), "mean_lookups": float(out[3].mean())}
+
+
 def cpu_baseline(rvpt, cfg, name):
-    """Oracle ("port") timed on the host cores over a bounded sample of the workload."""
+    """The CPU side of the comparison on the host cores: the reference's own shaders (oracle/_ref,
+    kind "reference") where they can run the workload, else the oracle ("port") over a bounded sample."""
+    if _reference_shaders_available(cfg):
+        res = _time_reference_shaders(cfg, steps=3, warmup=1)
+        return {"value": res["rays"] / res["seconds"], "unit": "probe-rays/s", "cores": 1, "kind": "reference",
+                "sample": f"all {res['rays']} probe rays per step, mean of 3 steps: the reference's probe_pass.comp transpiled "
+                          f"to C++ (oracle/_ref), single thread",
+                "mean_lookups_per_ray_in_sample": res["mean_lookups"]}
     X, Y, Z = cfg["probe_count"]
     vox = rvpt.read_voxels(cfg["voxels"][1])
     res = _time_oracle(cfg, vox, steps=2, warmup=1)
@@ -92,12 +129,21 @@ def reference_arm(args, name):
 
     X, Y, Z = cfg["probe_count"]
     rx, ry = cfg["tile"]
-    vox, _ = util.oracle_voxels(cfg)
-    res = _time_oracle(cfg, vox, steps=max(1, min(args.steps, 5)), warmup=1)
-    y0, y1 = res["rows"]
+    kind, cores = "port", None
+    if _reference_shaders_available(cfg):
+        res = _time_reference_shaders(cfg, steps=max(1, min(args.steps, 5)), warmup=1)
+        kind, cores = "reference", 1
+        sample = (f"all {res['rays']} probe rays per step: the reference's own probe_pass.comp transpiled to C++ "
+                  f"(oracle/_ref), single thread (its globals are process-wide)")
+    else:
+        vox, _ = util.oracle_voxels(cfg)
+        res = _time_oracle(cfg, vox, steps=max(1, min(args.steps, 5)), warmup=1)
+        y0, y1 = res["rows"]
+        cores = res["threads"]
+        sample = (f"probe rows [{y0},{y1}) of {Y} = {res['rays']} rays per step (the GLSL reference cannot be built: "
+                  f"no glslang/Vulkan/lavapipe, and its transpiled shaders (oracle/_ref) have the reference's own scenes "
+                  f"compiled in, not this workload's voxel field; this is the CPU oracle port, OpenMP, all host threads)")
     value = res["rays"] / res["seconds"]
-    sample = (f"probe rows [{y0},{y1}) of {Y} = {res['rays']} rays per step (the GLSL reference cannot be built: "
-              f"no glslang/Vulkan/lavapipe; this is the CPU oracle port, OpenMP, all host threads)")
     return {
         "impl": "reference", "metric": "probe_rays_per_s", "value": value, "unit": "probe-rays/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": max(1, min(args.steps, 5)), "warmup": 1,
@@ -106,7 +152,7 @@ def reference_arm(args, name):
         "config": {"workload": name, "probes": [X, Y, Z], "rays_per_probe": rx * ry, "probe_rays": X * Y * Z * rx * ry,
                    "voxels": list(cfg["voxels"][1]), "lights": 4 if cfg["lights"] == "cave4" else 1,
                    "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"])},
-        "cpu_baseline": {"value": value, "unit": "probe-rays/s", "cores": res["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "probe-rays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "probe-rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

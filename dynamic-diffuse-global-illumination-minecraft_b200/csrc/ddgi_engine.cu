@@ -375,7 +375,7 @@ static int finish_voxels(ddgi_ctx* ctx)
     CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, b0, ctx->nb, ctx->d_types, ctx->d_occ, 0, &l));
     ctx->launches += l;
     CU(cudaDeviceSynchronize());
-    ctx->calibrated = false;  // a new scene: measure the per-probe costs again
+    ctx->calibrated = false;  // a new scene: measure the per-slot costs again
     return DDGI_OK;
 }
 

@@ -1,9 +1,14 @@
 // ddgi_kernels.cu — sm_100a kernels of the DDGI probe-field engine.
 //
-//   probe_update_direct   one thread per probe ray, reference loop order
-//                         (assets/shaders/probe_pass.comp:253-303)
-//   render_frame_kernel   one thread per pixel (assets/shaders/compute_pass.comp:162-191)
-//   bake_* / build_occupancy   scene preparation
+//   probe_update_wavefront   persistent warps, one probe ray per lane as a state machine
+//                            (ddgi_wavefront.cuh); the default probe update
+//   probe_update_direct      one thread per probe ray, reference loop order
+//                            (assets/shaders/probe_pass.comp:253-303)
+//   probe_blend_octahedral   optional textbook layout: ray results -> octahedral tile texels,
+//                            warp-shuffle reduction (ddgi_octahedral.cuh)
+//   peer_barrier_kernel      completion barrier of the fused multi-GPU exchange
+//   render_frame_kernel      one thread per pixel (assets/shaders/compute_pass.comp:162-191)
+//   bake_* / build_occupancy / edit_voxels   scene preparation and per-frame edits
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (see csrc/Makefile).
 #include "ddgi_internal.h"

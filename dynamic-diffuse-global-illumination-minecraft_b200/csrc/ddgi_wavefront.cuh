@@ -28,7 +28,7 @@
 //     the second, for d < 0 the other way round (f in [0,1]); zero / NaN / tiny
 //     components take the literal two-division form (WfRay::slow).
 //   * that division and x/0.1f use the FMA-corrected reciprocal of ddgi_fastmath.cuh.
-//   * the voxel test reads one bit of the 4x4x4-brick occupancy word (16 MiB for 512^3
+//   * the voxel test reads one bit of the 4x4x2-brick occupancy word (16 MiB for 512^3
 //     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
 //     (intersection.glsl:100-113), so the two root divisions are skipped for it; and the
