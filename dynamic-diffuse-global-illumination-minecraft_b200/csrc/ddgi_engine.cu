@@ -977,6 +977,8 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     if (!ctx->have_field || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no irradiance field");
     if (!ctx->d_occ) return fail(ctx, DDGI_E_STATE, "no voxel field");
     if (ctx->ray_mode == 0) return fail(ctx, DDGI_E_STATE, "no probe rays: call ddgi_generate_probe_rays or ddgi_set_probe_rays");
+    if (ctx->layout == DDGI_LAYOUT_OCTAHEDRAL && ctx->ray_mode != 1)
+        return fail(ctx, DDGI_E_STATE, "the octahedral layout needs a generated ray set (ddgi_generate_probe_rays / _fibonacci_rays / ddgi_set_ray_samples)");
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_debug_buffers(ctx);
     if (rc) return rc;
@@ -1003,12 +1005,13 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     J.tex_w = ctx->tex_w;
     J.tex_h = ctx->tex_h;
     const uint32_t* old_tex = ctx->d_tex;
-    if (ctx->double_buffer) {
-        // write the other allocation; the last asynchronous read of it must have finished
-        int next = ctx->cur_tex ^ 1;
-        if (ctx->ev_copied[next]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_copied[next], 0));
-        ctx->cur_tex = next;
-        ctx->d_tex = ctx->d_tex_pair[next];
+    {
+        // the allocation this update writes (the other one under double buffering): the last
+        // asynchronous read of it must have finished before the kernel may overwrite it
+        int target = ctx->double_buffer ? ctx->cur_tex ^ 1 : ctx->cur_tex;
+        if (ctx->ev_copied[target]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_copied[target], 0));
+        ctx->cur_tex = target;
+        ctx->d_tex = ctx->d_tex_pair[target];
     }
     J.albedo = ctx->d_tex;
     J.distance = ctx->d_tex + tex_texels(ctx);
@@ -1026,8 +1029,6 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         J.n_peers++;
     }
     if (ctx->layout == 1) {
-        if (ctx->ray_mode != 1)
-            return fail(ctx, DDGI_E_STATE, "the octahedral layout needs a generated ray set (ddgi_generate_probe_rays / _fibonacci_rays / ddgi_set_ray_samples)");
         if (num_rays(ctx) > ctx->ray_out_cap) {
             dfree(ctx->d_ray_out);
             CU(cudaMalloc(&ctx->d_ray_out, num_rays(ctx) * sizeof(float4)));

@@ -265,8 +265,9 @@ DDGI_API int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, 
    With it frame i can be copied to the host while frame i+1 is traced:
    ddgi_read_probe_texture_async enqueues the copy of the latest frame on the engine's own copy
    stream, ordered after the update that produced it (dst should be pinned; it is valid after
-   ddgi_read_wait, or once a later ddgi_read_wait / ddgi_sync returns); the next update but one
-   waits, on the device, for that copy before it overwrites the buffer.  Not with the fused
+   ddgi_read_wait); an update that is about to overwrite a buffer first waits, on the device, for
+   the last asynchronous read of it (the next update but one; without double buffering the very
+   next update, so the asynchronous read is then correct but overlaps nothing).  Not with the fused
    exchange (one mapped allocation per rank).  With partial probe ownership and no exchange the
    texels a context does not own are one frame older in every other buffer. */
 DDGI_API int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on);
