@@ -230,3 +230,186 @@ void sim_pin_acos(const float* x, int n, float* out)
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Scheduling-policy model of probe_update_wavefront (profiles/policy_sim.py): the kernel's
+// warp loop re-enacted on the host with the same per-lane state functions, `n_warps` warps
+// advanced in order of their accumulated cost (so the dynamic ray fetch behaves as on the
+// device), counting how often each state's code runs and with how many lanes.  Not a test:
+// a tool for comparing scheduling rules without a GPU.
+//   policy 0: the kernel's rule (march while >= march_min/32 of the live lanes march, else the
+//             fullest other state, ties to the later stage)
+//   policy 1: always the fullest state, MARCH counted like any other (ties: march)
+//   policy 2: as 0, but a non-march state runs only with >= min_other lanes unless no lane marches
+//   policy 3: hysteresis: start marching at >= min_other/32 of the live lanes, keep marching down to march_min/32
+//   policy 4: drain: below the march threshold run the other states until none of them holds
+//             min_other or more lanes (re-ranked after each), only then look at the march count again
+struct PolicyOut {
+    uint64_t exec[8];    // executions of each state's code (warp passes)
+    uint64_t lanes[8];   // lanes active over those executions
+    uint64_t passes;     // outer-loop passes (scheduler rounds)
+    double makespan;     // largest accumulated warp cost
+    double busy;         // sum of warp costs
+};
+// `group` > 1 models ideal regrouping inside a block of `group` warps: the scheduling unit holds
+// 32 * group rays and a state's code is issued ceil(count / 32) times (moving ray state between
+// lanes is taken as free: an upper bound on what block-level compaction could give).
+template <int kGroup>
+static void wavefront_policy(const SimParams* S, const float* rays, const uint32_t* order, uint32_t n_rays, int n_warps, int policy,
+                             int march_min, int min_other, const double* cost, PolicyOut* out);
+
+extern "C" void sim_wavefront_policy(const SimParams* S, const float* rays, const uint32_t* order, uint32_t n_rays, int n_warps,
+                                     int policy, int march_min, int min_other, const double* cost /* [8] + scheduler */,
+                                     PolicyOut* out, int group)
+{
+    if (group == 2) wavefront_policy<2>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
+    else if (group == 4) wavefront_policy<4>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
+    else if (group == 8) wavefront_policy<8>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
+    else wavefront_policy<1>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
+}
+
+template <int kGroup>
+static void wavefront_policy(const SimParams* S, const float* rays, const uint32_t* order, uint32_t n_rays, int n_warps, int policy,
+                             int march_min, int min_other, const double* cost, PolicyOut* out)
+{
+    constexpr int kLanes = 32 * kGroup;
+    Built B;
+    build(S, nullptr, &B);
+    const FrameParams& P = B.P;
+    struct Warp {
+        WfRay R[kLanes];
+        double t = 0;
+        bool done = false;
+        bool marching = false;  // policy 3
+        bool draining = false;  // policy 4
+    };
+    std::vector<Warp> warps((size_t)n_warps);
+    for (auto& w : warps)
+        for (int l = 0; l < kLanes; l++) w.R[l].mode = WF_FETCH;
+    memset(out, 0, sizeof(*out));
+    uint32_t next = 0;
+    float stash[3];
+    size_t live = (size_t)n_warps;
+    while (live) {
+        // the warp that is furthest behind runs its next pass
+        Warp* w = nullptr;
+        for (auto& c : warps)
+            if (!c.done && (!w || c.t < w->t)) w = &c;
+        int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int l = 0; l < kLanes; l++) count[w->R[l].mode]++;
+        int n_live = kLanes - count[WF_IDLE];
+        if (n_live == 0) {
+            w->done = true;
+            live--;
+            continue;
+        }
+        out->passes++;
+        w->t += cost[8];
+        auto run = [&](int state) {
+            const int issues = (count[state] + 31) / 32;
+            out->exec[state] += (uint64_t)issues;
+            out->lanes[state] += (uint64_t)count[state];
+            w->t += cost[state] * issues;
+            // regrouping is not free: moving a ray's state between the pool and a lane's registers
+            // costs `cost[7]` instructions per issue (a quarter of it per march step: a warp keeps
+            // its rays in registers over a run of steps)
+            if (kGroup > 1) w->t += (state == WF_MARCH ? 0.25 : 1.0) * cost[7] * issues;
+            int n_scatter = 0, n_query = 0;
+            for (int l = 0; l < kLanes; l++) {
+                WfRay& R = w->R[l];
+                if (R.mode != state) continue;
+                switch (state) {
+                    case WF_MARCH: wf_step(P, R); break;
+                    case WF_MARCH_SLOW: wf_step_literal(P, R); break;
+                    case WF_BOUNCE_HIT: wf_resolve_bounce<false>(P, R, stash, 1); break;
+                    case WF_FEELER_HIT: wf_resolve_feeler<false>(P, R, stash, 1); break;
+                    case WF_FETCH:
+                        if (next < n_rays) {
+                            uint32_t k = order[next++];
+                            const float* r = rays + 12 * (size_t)k;
+                            wf_init(R, V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), k);
+                        } else {
+                            R.mode = WF_IDLE;
+                        }
+                        break;
+                }
+                // scatter and query are armed in the same pass, as in the kernel
+                if (R.mode == WF_SCATTER) {
+                    wf_scatter(P, R);
+                    n_scatter++;
+                }
+                if (R.mode == WF_QUERY) {
+                    wf_begin_query(P, R);
+                    n_query++;
+                }
+            }
+            if (n_scatter) {
+                out->exec[WF_SCATTER] += (uint64_t)((n_scatter + 31) / 32);
+                out->lanes[WF_SCATTER] += (uint64_t)n_scatter;
+                w->t += cost[WF_SCATTER] * ((n_scatter + 31) / 32);
+            }
+            if (n_query) {
+                out->exec[WF_QUERY] += (uint64_t)((n_query + 31) / 32);
+                out->lanes[WF_QUERY] += (uint64_t)n_query;
+                w->t += cost[WF_QUERY] * ((n_query + 31) / 32);
+            }
+        };
+        auto fullest_other = [&]() {
+            int best = -1, bc = 0;
+            for (int s : {WF_BOUNCE_HIT, WF_FEELER_HIT, WF_FETCH, WF_MARCH_SLOW})
+                if (count[s] > bc || (count[s] == bc && bc > 0 && s > best)) {
+                    best = s;
+                    bc = count[s];
+                }
+            return best;
+        };
+        if (policy == 1) {
+            int o = fullest_other();
+            if (count[WF_MARCH] > 0 && (o < 0 || count[WF_MARCH] >= count[o])) run(WF_MARCH);
+            else if (o >= 0) run(o);
+            continue;
+        }
+        if (policy == 3) {
+            int lo = n_live * march_min > 32 ? n_live * march_min : 32, hi = n_live * min_other > 32 ? n_live * min_other : 32;
+            int m32 = count[WF_MARCH] * 32;
+            if (w->marching ? m32 >= lo : m32 >= hi) {
+                w->marching = true;
+                run(WF_MARCH);
+                w->t -= cost[8];
+                out->passes--;
+                continue;
+            }
+            w->marching = false;
+            int o = fullest_other();
+            if (o >= 0) run(o);
+            else if (count[WF_MARCH] > 0) run(WF_MARCH);
+            continue;
+        }
+        if (policy == 4 && w->draining) {
+            int o = fullest_other();
+            if (o >= 0 && count[o] >= min_other) {
+                run(o);
+                continue;
+            }
+            w->draining = false;
+        }
+        const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // march_min/32 of the live lanes
+        if (count[WF_MARCH] * 32 >= enough) {
+            run(WF_MARCH);  // (one step per pass here; the kernel's inner loop re-checks the same condition)
+            w->t -= cost[8];  // the inner march loop does not pay a scheduler round
+            out->passes--;
+            continue;
+        }
+        int o = fullest_other();
+        if (o < 0 || (policy == 2 && count[o] < min_other && count[WF_MARCH] > 0)) {
+            if (count[WF_MARCH] > 0) run(WF_MARCH);
+            continue;
+        }
+        if (policy == 4) w->draining = true;
+        run(o);
+    }
+    for (auto& c : warps) {
+        out->busy += c.t;
+        if (c.t > out->makespan) out->makespan = c.t;
+    }
+}
