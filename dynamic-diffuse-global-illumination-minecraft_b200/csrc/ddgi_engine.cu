@@ -164,13 +164,12 @@ static bool owns_probe(const ddgi_ctx* c, int p)
     return (unit / c->cyc_block) % c->cyc_world == c->cyc_rank;
 }
 
-// Rays per scheduling slot: ctx->slot_pref (a multiple of 32) when it divides rays/probe, else the
-// whole probe.
+// Rays per scheduling slot: ctx->slot_pref when it divides rays/probe, else the whole probe.
 static uint32_t slot_rays(const ddgi_ctx* c)
 {
     uint32_t rpp = (uint32_t)(c->rx * c->ry);
     uint32_t want = (uint32_t)c->slot_pref;
-    return want >= 32u && want <= rpp && rpp % want == 0 ? want : rpp;
+    return want >= 1u && want <= rpp && rpp % want == 0 ? want : rpp;
 }
 static size_t num_slots(const ddgi_ctx* c) { return num_probes(c) * ((size_t)(c->rx * c->ry) / slot_rays(c)); }
 
@@ -1277,7 +1276,7 @@ int ddgi_read_warp_times(ddgi_ctx* ctx, uint64_t* dst, size_t count, size_t* n_w
 int ddgi_set_schedule_slot(ddgi_ctx* ctx, int32_t rays)
 {
     if (!ctx) return DDGI_E_INVALID;
-    NEED(rays == 0 || (rays >= 32 && rays % 32 == 0), "slot must be 0 (a whole probe) or a multiple of 32 rays");
+    NEED(rays >= 0 && rays <= 4096, "slot must be 0 (a whole probe) or a ray count that divides rays/probe");
     ctx->slot_pref = rays;
     ctx->order_dirty = true;
     ctx->calibrated = false;

@@ -294,9 +294,9 @@ DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
    march_min/32 of the lanes that hold a ray are marching (1..32, default 16).  Results do
    not depend on it. */
 DDGI_API int ddgi_set_tuning(ddgi_ctx* ctx, int32_t march_min);
-/* Granularity of the cost-ordered schedule: slots of `rays` consecutive rays of a probe (a multiple
-   of 32 that divides rays/probe; default 32 = one warp's fetch, two rows of a 16x16 ray tile), 0 =
-   whole probes.  Results do not depend on it. */
+/* Granularity of the cost-ordered schedule: slots of `rays` consecutive rays of a probe (any count
+   that divides rays/probe; default 32 = one warp's fetch, two rows of a 16x16 ray tile; 1 = every
+   ray ranked on its own), 0 = whole probes.  Results do not depend on it. */
 DDGI_API int ddgi_set_schedule_slot(ddgi_ctx* ctx, int32_t rays);
 /* Caps the resident blocks per SM variant 1 launches (0 = as many as fit, the default).  Results
    do not depend on it. */

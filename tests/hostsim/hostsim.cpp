@@ -413,3 +413,34 @@ static void wavefront_policy(const SimParams* S, const float* rays, const uint32
         if (c.t > out->makespan) out->makespan = c.t;
     }
 }
+
+// Per-ray work profile for schedule experiments (profiles/policy_sim.py): counts[4k..4k+3] =
+// voxel lookups, nearest-hit queries, bounce resolves, feeler resolves of ray k.
+extern "C" void sim_ray_profile(const SimParams* S, const float* rays, uint32_t n_rays, uint32_t* counts)
+{
+    Built B;
+    build(S, nullptr, &B);
+    const FrameParams& P = B.P;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t k = 0; k < (int64_t)n_rays; k++) {
+        const float* r = rays + 12 * k;
+        WfRay R;
+        float stash[3] = {0, 0, 0};
+        wf_init(R, V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), (uint32_t)k);
+        uint32_t q = 0, b = 0, f = 0;
+        while (R.mode != WF_FETCH) {
+            switch (R.mode) {
+                case WF_MARCH: wf_step(P, R); break;
+                case WF_MARCH_SLOW: wf_step_literal(P, R); break;
+                case WF_QUERY: wf_begin_query(P, R); q++; break;
+                case WF_BOUNCE_HIT: wf_resolve_bounce<false>(P, R, stash, 1); b++; break;
+                case WF_FEELER_HIT: wf_resolve_feeler<false>(P, R, stash, 1); f++; break;
+                default: wf_scatter(P, R); break;
+            }
+        }
+        counts[4 * k] = R.lookups;
+        counts[4 * k + 1] = q;
+        counts[4 * k + 2] = b;
+        counts[4 * k + 3] = f;
+    }
+}
