@@ -51,6 +51,25 @@ def probe_row_blocks(probe_rows: int, rank: int, world: int, block: int = 1) -> 
     return out
 
 
+def probe_owner(probe: int, world: int, block: int = 1) -> int:
+    """Rank that updates `probe` under probe-cyclic ownership (ddgi_set_probes_cyclic): probes dealt
+    round-robin in blocks of `block` — the finest balance; paired with the fused exchange because a
+    rank's texels are then scattered tiles, not a byte range."""
+    if world < 1 or block < 1:
+        raise ValueError(f"world {world}, block {block}")
+    return (probe // block) % world
+
+
+def frame_band_rows(screen_height: int, rank: int, world: int) -> tuple[int, int]:
+    """Pixel rows [y0, y1) of the frame band `rank` renders (ddgi_set_frame_band): the reference
+    dispatches floor(h/16) rows of 16x16 workgroups (src/rvpt/rvpt.cpp:1139-1140); they are split as
+    evenly as integer arithmetic allows, in order."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} of world {world}")
+    groups = screen_height // 16
+    return 16 * (groups * rank // world), 16 * (groups * (rank + 1) // world)
+
+
 def allgather_probe_rows_cyclic(plane, probe_rows: int, row_bytes: int, rank: int, world: int, block: int = 1, group=None):
     """In-place exchange of one texture plane under block-cyclic ownership: every group of
     world*block consecutive probe rows is one all_gather_into_tensor (rank r's block is the

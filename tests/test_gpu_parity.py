@@ -289,6 +289,7 @@ def test_frame_bands_compose_to_the_whole_frame():
         rows = []
         for band in range(3):
             y0, y1 = r.set_frame_band(band, 3)
+            assert (y0, y1) == ddgi_b200.sharding.frame_band_rows(112, band, 3)   # the host-side mirror agrees
             rows.append((y0, y1))
             r.render_frame()
             r.sync()

@@ -48,6 +48,77 @@ def test_block_cyclic_ownership_partitions_exactly():
     assert sh.cyclic_block(32, 8) == 1 and sh.cyclic_block(32, 2) == 2 and sh.cyclic_block(8, 2) == 1
 
 
+def test_probe_cyclic_ownership_and_frame_bands_partition_exactly():
+    sh = ddgi_b200.sharding
+    for world in (1, 2, 3, 8):
+        for block in (1, 5):
+            owners = [sh.probe_owner(p, world, block) for p in range(100)]
+            assert set(owners) == set(range(min(world, -(-100 // block))))
+            assert all(owners[p] == owners[(p // block) * block] for p in range(100))
+            counts = np.bincount(owners, minlength=world)
+            assert counts.max() - counts.min() <= block
+    for h in (8, 16, 112, 900, 1080):
+        for world in (1, 2, 3, 8):
+            bands = [sh.frame_band_rows(h, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == (h // 16) * 16
+            assert all(a[1] == b[0] and a[0] % 16 == 0 for a, b in zip(bands, bands[1:]))
+            sizes = [(b - a) // 16 for a, b in bands]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _fused_worker(rank, world, port, name, out_path):
+    """The fused exchange's host logic on CPU: probes dealt round-robin, every rank's texels "stored
+    into every replica" (here: one sum all-reduce of the disjoint planes), then each rank renders
+    its frame band from the complete replica."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg, sc, rays = _scene_and_rays(name)
+        X, Y, Z = cfg["probe_count"]
+        rx, ry = cfg["tile"]
+        n = rx * ry
+        W, H = sc.tex_size
+        sh = ddgi_b200.sharding
+        alb = np.zeros((H, W), dtype=np.uint32)
+        hs = util.hostsim()
+        for p in range(X * Y * Z):
+            if sh.probe_owner(p, world) == rank:
+                hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, p * n, (p + 1) * n, 1, alb.ctypes.data, None, None, None)
+        plane = torch.from_numpy(alb.view(np.int32).reshape(-1))
+        dist.all_reduce(plane)  # disjoint non-zero texels: the sum is the union
+        screen = (64, 112)      # 7 workgroup rows over 2 ranks: uneven bands
+        sc.p.screen_width, sc.p.screen_height = screen
+        cam = util.camera_block(util.small(cfg, screen=screen))
+        frame = np.zeros((screen[1], screen[0]), dtype=np.uint32)
+        hs.sim_render_frame(C.byref(sc.p), cam.ctypes.data, alb.ctypes.data, None, frame.ctypes.data, None, None)
+        y0, y1 = sh.frame_band_rows(screen[1], rank, world)
+        band = torch.from_numpy(np.ascontiguousarray(frame[y0:y1]).view(np.int32))
+        np.save(f"{out_path}.tex.{rank}.npy", alb)
+        np.save(f"{out_path}.band.{rank}.npy", band.numpy().view(np.uint32))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_fused_exchange_and_frame_bands(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "fused")
+    name = "cornell_3x3x3"
+    mp.spawn(_fused_worker, args=(2, port, name, out), nprocs=2, join=True)
+    cfg, sc, rays = _scene_and_rays(name)
+    want = oracle.probe_update(sc, rays)[0]
+    screen = (64, 112)
+    sc.p.screen_width, sc.p.screen_height = screen
+    frame = oracle.render_frame(sc, util.camera_block(util.small(cfg, screen=screen)), want)[0]
+    bands = []
+    for rank in range(2):
+        assert np.array_equal(np.load(f"{out}.tex.{rank}.npy"), want), f"rank {rank}: replica differs"
+        bands.append(np.load(f"{out}.band.{rank}.npy"))
+    assert np.array_equal(np.concatenate(bands, axis=0), frame[:112])
+
+
 def _scene_and_rays(name):
     cfg = CFG[name]
     sc = util.oracle_scene(cfg)
