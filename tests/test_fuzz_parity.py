@@ -42,13 +42,19 @@ def random_case(seed):
     tile = (int(rng.integers(1, 7)), int(rng.integers(1, 7)))
     bounces = int(rng.integers(1, 9))
     screen = (48, 32)
+    # every third seed also draws the optional modes: hysteresis blend, distance moments, Chebyshev
+    # weight, a debug integrator, probe markers
+    modes = dict(hysteresis=None, distance_scale=None, chebyshev=False, render_mode=0, visualize_probes=False)
+    if seed % 3 == 2:
+        modes = dict(hysteresis=float(rng.uniform(0.1, 0.95)), distance_scale=float(rng.choice([1.0, 4.0, side * 1.7])),
+                     chebyshev=bool(rng.integers(0, 2)), render_mode=int(rng.integers(0, 6)), visualize_probes=bool(rng.integers(0, 2)))
     sc = oracle.Scene(probe_count=probe_count, side_length=side, field_origin=tuple(float(np.float32(v)) for v in fo), rx=tile[0], ry=tile[1],
-                      lights=lights, scene=1, voxels=vox, vorg=vorg, max_bounces=bounces, screen=screen)
+                      lights=lights, scene=1, voxels=vox, vorg=vorg, max_bounces=bounces, screen=screen, **modes)
     rays = np.ascontiguousarray(oracle.generate_probe_rays(sc, rng.normal(size=(tile[0] * tile[1], 3)).astype(np.float32)))
     cam_o = centre + rng.normal(size=3) * np.array(dims) * 0.8
     cam = ddgi_b200.Camera(screen[0] / float(screen[1]), tuple(float(v) for v in cam_o), tuple(float(v) for v in rng.uniform(-60, 60, size=3))).get_data()
     return dict(sc=sc, rays=rays, vox=vox, vorg=vorg, lights=lights, probe_count=probe_count, side=side, fo=fo, tile=tile, bounces=bounces,
-                screen=screen, cam=cam, cam_o=cam_o)
+                screen=screen, cam=cam, cam_o=cam_o, modes=modes)
 
 
 SEEDS = list(range(1, 25))
@@ -58,19 +64,25 @@ SEEDS = list(range(1, 25))
 def test_engine_headers_on_random_scenes(seed):
     c = random_case(seed)
     sc, rays = c["sc"], c["rays"]
+    W, H = sc.tex_size
     with np.errstate(all="ignore"):
-        want = oracle.probe_update(sc, rays)
-        frame = oracle.render_frame(sc, c["cam"], want[0])
+        tex = np.zeros((H, W), dtype=np.uint32)
+        for _ in range(2):   # two frames: the second blends into the first when the hysteresis mode is drawn
+            want = oracle.probe_update(sc, rays, tex=tex)
+        frame = oracle.render_frame(sc, c["cam"], want[0], tex_distances=want[1])
     hs = util.hostsim()
     for variant in (0, 1):
-        alb, f32, lk = np.zeros_like(want[0]), np.zeros_like(want[2]), np.zeros_like(want[3])
-        hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data, None)
+        alb, f32, lk, dist = np.zeros_like(want[0]), np.zeros_like(want[2]), np.zeros_like(want[3]), np.zeros_like(want[1])
+        for _ in range(2):
+            hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data,
+                                dist.ctypes.data)
         assert np.array_equal(lk, want[3]), f"seed {seed} variant {variant}: lookup counts"
         assert np.array_equal(f32.view(np.uint32), want[2].view(np.uint32)), f"seed {seed} variant {variant}: fp32 texels"
-        assert np.array_equal(alb, want[0])
+        assert np.array_equal(alb, want[0]) and np.array_equal(dist, want[1])
     w, h = c["screen"]
     got, gf32, glk = np.zeros((h, w), dtype=np.uint32), np.zeros((h, w, 4), dtype=np.float32), np.zeros((h, w), dtype=np.uint32)
-    hs.sim_render_frame(C.byref(sc.p), c["cam"].ctypes.data, want[0].ctypes.data, None, got.ctypes.data, gf32.ctypes.data, glk.ctypes.data)
+    hs.sim_render_frame(C.byref(sc.p), c["cam"].ctypes.data, want[0].ctypes.data, want[1].ctypes.data, got.ctypes.data, gf32.ctypes.data,
+                        glk.ctypes.data)
     assert np.array_equal(glk, frame[2]), f"seed {seed}: pixel lookup counts"
     assert np.array_equal(gf32.view(np.uint32), frame[1].view(np.uint32)) and np.array_equal(got, frame[0])
 
@@ -80,12 +92,20 @@ def test_engine_headers_on_random_scenes(seed):
 def test_cuda_engine_on_random_scenes(seed):
     c = random_case(seed)
     sc, rays = c["sc"], c["rays"]
+    W, H = sc.tex_size
     with np.errstate(all="ignore"):
-        want = oracle.probe_update(sc, rays)
-        frame = oracle.render_frame(sc, c["cam"], want[0])
+        tex = np.zeros((H, W), dtype=np.uint32)
+        for _ in range(2):
+            want = oracle.probe_update(sc, rays, tex=tex)
+        frame = oracle.render_frame(sc, c["cam"], want[0], tex_distances=want[1])
     w, h = c["screen"]
+    m = c["modes"]
     with ddgi_b200.RVPT(w, h) as r:
         r.set_debug(True)
+        r.render_settings.render_mode = m["render_mode"]
+        r.render_settings.visualize_probes = 1 if m["visualize_probes"] else 0
+        if m["hysteresis"] is not None:
+            r.ir.hysteresis = m["hysteresis"]
         r.render_settings.scene = 1
         r.render_settings.max_bounces = c["bounces"]
         r.ir.probe_count[:] = c["probe_count"]
@@ -96,6 +116,12 @@ def test_cuda_engine_on_random_scenes(seed):
         r.lights = [capi.Light(l.intensity, tuple(l.col), tuple(l.pos)) for l in c["lights"]]
         r.upload_voxels(c["vox"], c["vorg"])
         r.set_probe_rays(rays)
+        if m["hysteresis"] is not None:
+            r.set_blend_mode(capi.BLEND_HYSTERESIS)
+        if m["distance_scale"] is not None:
+            r.set_distance_mode(capi.DISTANCE_MOMENTS, m["distance_scale"])
+        if m["chebyshev"]:
+            r.set_weight_mode(capi.WEIGHT_CHEBYSHEV)
 
         class FixedCamera:
             def get_data(self_inner):
@@ -105,11 +131,13 @@ def test_cuda_engine_on_random_scenes(seed):
         for variant in (0, 1):
             r.set_kernel_variant(variant)
             r.update(advance_time=False)
+            r.write_probe_texture(np.zeros((H, W), dtype=np.uint32), 0)
+            r.probe_update()
             r.draw()
             r.sync()
             assert np.array_equal(r.read_lookup_counts(0), want[3]), f"seed {seed} variant {variant}: lookup counts"
             assert np.array_equal(r.read_probe_texture(0, capi.FMT_F32).view(np.uint32), want[2].view(np.uint32))
-            assert np.array_equal(r.read_probe_texture(0), want[0])
+            assert np.array_equal(r.read_probe_texture(0), want[0]) and np.array_equal(r.read_probe_texture(1), want[1])
             assert np.array_equal(r.read_lookup_counts(1).reshape(h, w), frame[2])
             assert np.array_equal(r.read_frame(capi.FMT_F32).view(np.uint32), frame[1].view(np.uint32))
             assert np.array_equal(r.read_frame(), frame[0])
