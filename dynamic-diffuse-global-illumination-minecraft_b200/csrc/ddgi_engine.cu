@@ -1309,7 +1309,7 @@ int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t 
 int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant)
 {
     if (!ctx) return DDGI_E_INVALID;
-    NEED(variant == 0 || variant == 1, "variant must be 0 or 1");
+    NEED(variant == 0 || variant == 1 || variant == 2, "variant must be 0, 1 or 2");
     ctx->variant = variant;
     return DDGI_OK;
 }

@@ -288,7 +288,9 @@ DDGI_API int ddgi_read_warp_times(ddgi_ctx* ctx, uint64_t* dst, size_t count, si
 /* Per-ray (which = 0) or per-pixel (which = 1) voxel lookups of the last dispatch. */
 DDGI_API int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t count);
 /* Kernel variant: 0 = one thread per ray, reference loop order; 1 = regrouped
-   state-machine kernel (default).  Results are identical. */
+   state-machine kernel (default); 2 = EXPERIMENTAL: the same state machine with a block's rays
+   pooled in shared memory so that a warp gathers any 32 rays in the same state (palette colour
+   mode only, otherwise variant 1 runs).  Results are identical. */
 DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
 /* Scheduling knob of variant 1: a warp keeps stepping its marches while at least
    march_min/32 of the lanes that hold a ray are marching (1..32, default 16).  Results do

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_shade.cuh"
+#include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_pooled.cuh"
 #include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_wavefront.cuh"
 
 using namespace ddgi;
@@ -102,6 +103,63 @@ static void build(const SimParams* S, const float* cam, Built* B)
     }
 }
 
+// Variant 2 (ddgi_pooled.cuh) for one ray: the state machine with the ray living in its packed
+// pool record — after every state execution it is packed, and the next execution unpacks it into
+// a WfRay whose every byte was poisoned first, the march through its own smaller record and in
+// sessions of at most 3 steps.  A field missing from a record cannot go unnoticed.
+static v3 pooled_trace_scalar(const FrameParams& P, v3 origin, v3 direction, uint32_t ray_index, uint32_t& lookups, float* first_t_out)
+{
+    if (P.max_bounces <= 0) return wavefront_trace_scalar(P, origin, direction, ray_index, lookups, first_t_out);  // the engine runs variant 0 then
+    PoolVec rec[kPoolVecs];
+    memset(rec, 0xFF, sizeof(rec));
+    int mode;
+    {
+        WfRay R;
+        memset(&R, 0xFF, sizeof(R));
+        wf_init(R, origin, direction, ray_index);
+        wf_begin_query(P, R);
+        pool_pack(R, ray_index, 0.0f, rec);
+        mode = R.mode;
+    }
+    float stash[3] = {0, 0, 0};
+    for (;;) {
+        WfRay R;
+        memset(&R, 0xFF, sizeof(R));
+        if (mode == WF_MARCH || mode == WF_MARCH_SLOW) {
+            pool_unpack_march(rec, R);
+            R.mode = mode;
+            for (int i = 0; i < 3 && R.mode == mode; i++) {
+                if (mode == WF_MARCH) wf_step(P, R);
+                else wf_step_literal(P, R);
+            }
+            pool_pack_march(R, rec);
+            mode = R.mode;
+            continue;
+        }
+        uint32_t k;
+        float first_t;
+        pool_unpack(rec, R, k, first_t);
+        R.mode = mode;
+        if (mode == WF_FETCH) {
+            lookups += R.lookups;
+            if (first_t_out) *first_t_out = first_t;
+            return R.color;
+        }
+        if (mode == WF_BOUNCE_HIT) {
+            float nearest = 0.0f;
+            bool first = R.bounce == 0;
+            wf_resolve_bounce<false>(P, R, stash, 1, &nearest);
+            if (first) first_t = nearest;
+        } else {
+            wf_resolve_feeler<false>(P, R, stash, 1);
+        }
+        if (R.mode == WF_SCATTER) wf_scatter(P, R);
+        if (R.mode == WF_QUERY) wf_begin_query(P, R);
+        pool_pack(R, k, first_t, rec);
+        mode = R.mode;
+    }
+}
+
 extern "C" {
 
 // variant 0: trace_probe_ray (reference loop order); variant 1: the wavefront
@@ -123,8 +181,9 @@ void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32
         int tx = xp * P.rx + f2i(r[9]), ty = yp * P.ry + f2i(r[10]);
         uint32_t n = 0;
         float first_t = 0.0f;
-        v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n, &first_t)
-                            : wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
+        v3 c = variant == 0   ? trace_probe_ray(P, o, d, (uint32_t)k, n, &first_t)
+               : variant == 1 ? wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t)
+                              : pooled_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
         size_t t = (size_t)ty * W + tx;
         if (S->blend_mode) c = blend_hysteresis(albedo[t], c, S->hysteresis);
         albedo[t] = pack_rgba8(c.x, c.y, c.z, 1.0f);
@@ -443,4 +502,155 @@ extern "C" void sim_ray_profile(const SimParams* S, const float* rays, uint32_t 
         counts[4 * k + 2] = b;
         counts[4 * k + 3] = f;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host re-enactment of probe_update_pooled's BLOCK logic (ddgi_kernels.cu) — queues, claims,
+// march sessions, fetch / retire accounting — with the block's warps taking turns.  It cannot show
+// races, but a slot that is lost or a pool that never drains shows up here, not as a hung GPU.
+// Writes the same texels as sim_probe_update; returns the number of loop passes (0 = did not end).
+extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
+                                            uint32_t* albedo, uint32_t* lookups_out)
+{
+    Built B;
+    build(S, nullptr, &B);
+    const FrameParams& P = B.P;
+    const int W = P.probe_count[0] * P.probe_count[2] * P.rx;
+    const int tiles_x = P.probe_count[0] * P.probe_count[2];
+    constexpr int N = 128, WARPS = 4;
+    struct Block {
+        PoolVec ray[N][kPoolVecs];
+        int queue[PQ_COUNT][N];
+        unsigned head[PQ_COUNT], tail[PQ_COUNT];
+        int live;
+        bool warp_done[WARPS];
+    };
+    std::vector<Block> blocks((size_t)n_blocks);
+    for (auto& b : blocks) {
+        memset(&b, 0, sizeof(b));
+        for (int i = 0; i < N; i++) {
+            b.queue[PQ_FETCH][i] = i;
+            b.ray[i][6].w = pool_bits_f(0xffffffffu);
+        }
+        b.tail[PQ_FETCH] = N;
+        b.live = N;
+    }
+    uint32_t next = 0;
+    uint64_t passes = 0;
+    float stash[3] = {0, 0, 0};
+    size_t running = (size_t)n_blocks * WARPS;
+    const uint64_t limit = 64ull * (uint64_t)n_rays * 400ull / 32ull + 100000ull;
+    while (running) {
+        if (++passes > limit) return 0;
+        Block& b = blocks[(passes / WARPS) % blocks.size()];
+        int w = (int)(passes % WARPS);
+        if (b.warp_done[w]) continue;
+        unsigned bestc = 0;
+        int q = -1;
+        const int order[PQ_COUNT] = {PQ_MARCH, PQ_FETCH, PQ_FEELER, PQ_BOUNCE, PQ_SLOW};
+        for (int qi : order) {
+            unsigned c = b.tail[qi] - b.head[qi];
+            unsigned cc = c < 32u ? c : 32u;
+            if (cc > bestc) {
+                bestc = cc;
+                q = qi;
+            }
+        }
+        if (q < 0) {
+            if (b.live <= 0) {
+                b.warp_done[w] = true;
+                running--;
+            }
+            continue;
+        }
+        unsigned old = b.head[q], n = bestc;
+        b.head[q] += n;
+        int slots[32], newq[32];
+        bool push[32];
+        for (unsigned l = 0; l < n; l++) slots[l] = b.queue[q][(old + l) % N];
+        if (q == PQ_MARCH || q == PQ_SLOW) {
+            const int run_mode = q == PQ_MARCH ? WF_MARCH : WF_MARCH_SLOW;
+            WfRay R[32];
+            for (unsigned l = 0; l < n; l++) {
+                memset(&R[l], 0xFF, sizeof(WfRay));
+                pool_unpack_march(b.ray[slots[l]], R[l]);
+                R[l].mode = run_mode;
+            }
+            unsigned active;
+            do {
+                active = 0;
+                for (unsigned l = 0; l < n; l++) {
+                    if (R[l].mode == run_mode) {
+                        if (q == PQ_MARCH) wf_step(P, R[l]);
+                        else wf_step_literal(P, R[l]);
+                    }
+                    active += R[l].mode == run_mode;
+                }
+            } while (active && active * 32u >= n * (unsigned)march_keep);
+            for (unsigned l = 0; l < n; l++) {
+                pool_pack_march(R[l], b.ray[slots[l]]);
+                newq[l] = pool_queue_of(R[l].mode);
+                push[l] = true;
+            }
+        } else if (q == PQ_FETCH) {
+            uint32_t base = next;
+            next += n;
+            for (unsigned l = 0; l < n; l++) {
+                PoolVec* r = b.ray[slots[l]];
+                uint32_t k = pool_f_bits(r[6].w);
+                if (k != 0xffffffffu) {
+                    const float* ry = rays + 12 * (size_t)k;
+                    int p = f2i(ry[8]);
+                    int yp = p / tiles_x, xp = p - yp * tiles_x;
+                    size_t t = (size_t)(yp * P.ry + f2i(ry[10])) * W + (xp * P.rx + f2i(ry[9]));
+                    albedo[t] = pack_rgba8(r[8].x, r[8].y, r[8].z, 1.0f);
+                    if (lookups_out) lookups_out[k] = pool_f_bits(r[2].w);
+                }
+                uint32_t idx = base + l;
+                push[l] = idx < n_rays;
+                newq[l] = PQ_FETCH;
+                if (push[l]) {
+                    const float* ry = rays + 12 * (size_t)idx;
+                    WfRay R;
+                    memset(&R, 0xFF, sizeof(R));
+                    wf_init(R, V3(ry[0], ry[1], ry[2]), V3(ry[4], ry[5], ry[6]), idx);
+                    wf_begin_query(P, R);
+                    pool_pack(R, idx, 0.0f, r);
+                    newq[l] = pool_queue_of(R.mode);
+                } else {
+                    b.live--;
+                }
+            }
+        } else {
+            for (unsigned l = 0; l < n; l++) {
+                PoolVec* r = b.ray[slots[l]];
+                WfRay R;
+                memset(&R, 0xFF, sizeof(R));
+                uint32_t k;
+                float first_t;
+                pool_unpack(r, R, k, first_t);
+                R.mode = q == PQ_BOUNCE ? WF_BOUNCE_HIT : WF_FEELER_HIT;
+                if (q == PQ_BOUNCE) {
+                    bool first = R.bounce == 0;
+                    float nearest = 0.0f;
+                    wf_resolve_bounce<false>(P, R, stash, 1, &nearest);
+                    if (first) first_t = nearest;
+                } else {
+                    wf_resolve_feeler<false>(P, R, stash, 1);
+                }
+                if (R.mode == WF_SCATTER) wf_scatter(P, R);
+                if (R.mode == WF_QUERY) wf_begin_query(P, R);
+                pool_pack(R, k, first_t, r);
+                newq[l] = pool_queue_of(R.mode);
+                push[l] = true;
+            }
+        }
+        for (unsigned l = 0; l < n; l++)
+            if (push[l]) {
+                int qi = newq[l];
+                b.queue[qi][b.tail[qi] % N] = slots[l];
+                b.tail[qi]++;
+            }
+    }
+    return passes;
 }

@@ -110,7 +110,7 @@ def test_engine_headers_edge_cases(case):
         assert (want[3] == 125).all() and (want[0] == 0xFF000000).all()   # every ray: one march of 125 empty cells, black
     hs = util.hostsim()
     rays = np.ascontiguousarray(rays)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         alb = np.zeros_like(want[0])
         f32 = np.zeros_like(want[2])
         lk = np.zeros_like(want[3])

@@ -71,7 +71,7 @@ def test_engine_headers_on_random_scenes(seed):
             want = oracle.probe_update(sc, rays, tex=tex)
         frame = oracle.render_frame(sc, c["cam"], want[0], tex_distances=want[1])
     hs = util.hostsim()
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         alb, f32, lk, dist = np.zeros_like(want[0]), np.zeros_like(want[2]), np.zeros_like(want[3]), np.zeros_like(want[1])
         for _ in range(2):
             hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data,

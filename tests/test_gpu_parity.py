@@ -415,3 +415,23 @@ def test_field_32_full_size_sampled_parity_and_properties():
     total = int((row_sums * (np.arange(H, dtype=np.uint64) + 1)).sum() % (1 << 61))
     print(f"field_32 t=6: mean lookups/ray {mean_lookups:.3f}, checksum of row checksums {total}")
     assert (full >> 24 == 255).all()   # every texel was written (alpha = 1)
+
+
+@pytest.mark.parametrize("name", ["cornell_3x3x3", "field_8"])
+def test_experimental_pooled_variant_is_bit_identical(name):
+    """Kernel variant 2 (csrc/ddgi_pooled.cuh: the state machine with a block's rays pooled in shared
+    memory) runs the same per-ray functions as variant 1 and must give the same bytes, fp32 values
+    and lookup counts; it is not the default (slower in its first form, profiles/r1_policy_model.md)."""
+    cfg = CFG[name]
+    sc = util.oracle_scene(cfg)
+    alb, _, f32, steps, _ = oracle.probe_update(sc, oracle_rays(sc, cfg))
+    with make_engine(cfg) as r:
+        r.set_kernel_variant(2)
+        for keep in (16, 4, 32):
+            r.set_tuning(keep)
+            r.write_probe_texture(np.zeros_like(alb))
+            r.probe_update()
+            r.sync()
+            assert np.array_equal(r.read_lookup_counts(0), steps)
+            assert np.array_equal(r.read_probe_texture(0, ddgi_b200.capi.FMT_F32).view(np.uint32), f32.view(np.uint32))
+            assert np.array_equal(r.read_probe_texture(0), alb)

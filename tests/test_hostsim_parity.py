@@ -24,7 +24,7 @@ def _sim_probe_update(sc, rays, variant, k0=0, k1=None):
     return alb, f32, lk
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", ["cornell_2x2x2", "cornell_3x3x3", "field_8"])
 def test_probe_update_headers_match_oracle(name, variant):
     cfg = CFG[name]
@@ -59,7 +59,7 @@ def test_wavefront_on_axis_parallel_and_degenerate_rays():
             i += 1
     with np.errstate(all="ignore"):
         want = oracle.probe_update(sc, rays, 0, n)
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             alb, f32, lk = _sim_probe_update(sc, rays, variant, 0, n)
             assert np.array_equal(lk[:n], want[3][:n])
             assert np.array_equal(f32.view(np.uint32), want[2].view(np.uint32))
@@ -92,7 +92,7 @@ def test_literal_colour_mode_matches_oracle_on_the_textured_cave():
     sc = oracle.Scene(probe_count=(3, 3, 3), side_length=7, field_origin=(0.0, 0.0, 0.0), rx=8, lights=oracle.default_lights(0),
                       scene=0, voxels=vox, vorg=(-64, -64, -64), literal_colors=True, screen=tuple(int(v) for v in g["screen"]))
     rays = g["rays"]
-    for variant in (0, 1):
+    for variant in (0, 1):   # (variant 2 carries no procedural-colour stash: the engine runs variant 1 for it)
         alb, f32, lk = _sim_probe_update(sc, rays, variant)
         assert np.array_equal(lk, g["lookups"])
         assert np.array_equal(f32.view(np.uint32), g["albedo_f32"].view(np.uint32))
@@ -120,7 +120,7 @@ def test_hysteresis_blend_in_the_engine_headers():
     hs = util.hostsim()
     W, H = sc.tex_size
     rays = np.ascontiguousarray(g["rays"])
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         alb = np.zeros((H, W), dtype=np.uint32)
         for want in g["albedo_hysteresis"]:
             hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, None, None, None)
