@@ -509,30 +509,46 @@ extern "C" void sim_ray_profile(const SimParams* S, const float* rays, uint32_t 
 // march sessions, fetch / retire accounting — with the block's warps taking turns.  It cannot show
 // races, but a slot that is lost or a pool that never drains shows up here, not as a hung GPU.
 // Writes the same texels as sim_probe_update; returns the number of loop passes (0 = did not end).
+// stats (optional, 16 values): [q] issues per queue, [5 + q] lanes over those issues, [10] march iterations,
+// [11] lanes over march iterations, [12] passes that found no work.
+// pool_slots: ray slots per block (the kernel has 128 = one per thread); lockstep != 0: the block's
+// warps all claim before any of them appends (every warp is always holding the rays it works on, as
+// on the device) instead of taking turns.
+extern "C" uint64_t sim_probe_update_pooled_stats(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
+                                                  uint32_t* albedo, uint32_t* lookups_out, uint64_t* stats, int pool_slots, int lockstep);
 extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
                                             uint32_t* albedo, uint32_t* lookups_out)
 {
+    return sim_probe_update_pooled_stats(S, rays, n_rays, n_blocks, march_keep, albedo, lookups_out, nullptr, 128, 0);
+}
+extern "C" uint64_t sim_probe_update_pooled_stats(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
+                                                  uint32_t* albedo, uint32_t* lookups_out, uint64_t* stats, int pool_slots, int lockstep)
+{
+    uint64_t local_stats[16] = {0};
+    if (!stats) stats = local_stats;
     Built B;
     build(S, nullptr, &B);
     const FrameParams& P = B.P;
     const int W = P.probe_count[0] * P.probe_count[2] * P.rx;
     const int tiles_x = P.probe_count[0] * P.probe_count[2];
-    constexpr int N = 128, WARPS = 4;
+    constexpr int WARPS = 4;
+    const int N = pool_slots;
     struct Block {
-        PoolVec ray[N][kPoolVecs];
-        int queue[PQ_COUNT][N];
-        unsigned head[PQ_COUNT], tail[PQ_COUNT];
-        int live;
-        bool warp_done[WARPS];
+        std::vector<PoolVec> ray;        // N x kPoolVecs
+        std::vector<int> queue[PQ_COUNT];  // rings of N
+        unsigned head[PQ_COUNT] = {0, 0, 0, 0, 0}, tail[PQ_COUNT] = {0, 0, 0, 0, 0};
+        int live = 0;
+        bool warp_done[WARPS] = {false, false, false, false};
     };
     std::vector<Block> blocks((size_t)n_blocks);
     for (auto& b : blocks) {
-        memset(&b, 0, sizeof(b));
+        b.ray.assign((size_t)N * kPoolVecs, PoolVec{0, 0, 0, 0});
+        for (int qi = 0; qi < PQ_COUNT; qi++) b.queue[qi].assign((size_t)N, 0);
         for (int i = 0; i < N; i++) {
             b.queue[PQ_FETCH][i] = i;
-            b.ray[i][6].w = pool_bits_f(0xffffffffu);
+            b.ray[(size_t)i * kPoolVecs + 6].w = pool_bits_f(0xffffffffu);
         }
-        b.tail[PQ_FETCH] = N;
+        b.tail[PQ_FETCH] = (unsigned)N;
         b.live = N;
     }
     uint32_t next = 0;
@@ -540,47 +556,52 @@ extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* ray
     float stash[3] = {0, 0, 0};
     size_t running = (size_t)n_blocks * WARPS;
     const uint64_t limit = 64ull * (uint64_t)n_rays * 400ull / 32ull + 100000ull;
-    while (running) {
-        if (++passes > limit) return 0;
-        Block& b = blocks[(passes / WARPS) % blocks.size()];
-        int w = (int)(passes % WARPS);
-        if (b.warp_done[w]) continue;
-        unsigned bestc = 0;
+    struct Claim {
         int q = -1;
+        unsigned n = 0;
+        int slots[32];
+    };
+    auto claim = [&](Block& b, Claim& c) {
+        unsigned bestc = 0;
+        c.q = -1;
         const int order[PQ_COUNT] = {PQ_MARCH, PQ_FETCH, PQ_FEELER, PQ_BOUNCE, PQ_SLOW};
         for (int qi : order) {
-            unsigned c = b.tail[qi] - b.head[qi];
-            unsigned cc = c < 32u ? c : 32u;
+            unsigned cnt = b.tail[qi] - b.head[qi];
+            unsigned cc = cnt < 32u ? cnt : 32u;
             if (cc > bestc) {
                 bestc = cc;
-                q = qi;
+                c.q = qi;
             }
         }
-        if (q < 0) {
-            if (b.live <= 0) {
-                b.warp_done[w] = true;
-                running--;
-            }
-            continue;
-        }
-        unsigned old = b.head[q], n = bestc;
-        b.head[q] += n;
-        int slots[32], newq[32];
+        if (c.q < 0) return;
+        unsigned old = b.head[c.q];
+        c.n = bestc;
+        b.head[c.q] += c.n;
+        for (unsigned l = 0; l < c.n; l++) c.slots[l] = b.queue[c.q][(old + l) % (unsigned)N];
+        stats[c.q]++;
+        stats[5 + c.q] += c.n;
+    };
+    auto work = [&](Block& b, const Claim& c) {
+        const int q = c.q;
+        const unsigned n = c.n;
+        int newq[32];
         bool push[32];
-        for (unsigned l = 0; l < n; l++) slots[l] = b.queue[q][(old + l) % N];
+        auto rec = [&](unsigned l) { return &b.ray[(size_t)c.slots[l] * kPoolVecs]; };
         if (q == PQ_MARCH || q == PQ_SLOW) {
             const int run_mode = q == PQ_MARCH ? WF_MARCH : WF_MARCH_SLOW;
             WfRay R[32];
             for (unsigned l = 0; l < n; l++) {
                 memset(&R[l], 0xFF, sizeof(WfRay));
-                pool_unpack_march(b.ray[slots[l]], R[l]);
+                pool_unpack_march(rec(l), R[l]);
                 R[l].mode = run_mode;
             }
             unsigned active;
             do {
                 active = 0;
+                stats[10]++;
                 for (unsigned l = 0; l < n; l++) {
                     if (R[l].mode == run_mode) {
+                        stats[11]++;
                         if (q == PQ_MARCH) wf_step(P, R[l]);
                         else wf_step_literal(P, R[l]);
                     }
@@ -588,7 +609,7 @@ extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* ray
                 }
             } while (active && active * 32u >= n * (unsigned)march_keep);
             for (unsigned l = 0; l < n; l++) {
-                pool_pack_march(R[l], b.ray[slots[l]]);
+                pool_pack_march(R[l], rec(l));
                 newq[l] = pool_queue_of(R[l].mode);
                 push[l] = true;
             }
@@ -596,7 +617,7 @@ extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* ray
             uint32_t base = next;
             next += n;
             for (unsigned l = 0; l < n; l++) {
-                PoolVec* r = b.ray[slots[l]];
+                PoolVec* r = rec(l);
                 uint32_t k = pool_f_bits(r[6].w);
                 if (k != 0xffffffffu) {
                     const float* ry = rays + 12 * (size_t)k;
@@ -618,12 +639,13 @@ extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* ray
                     pool_pack(R, idx, 0.0f, r);
                     newq[l] = pool_queue_of(R.mode);
                 } else {
+                    r[6].w = pool_bits_f(0xffffffffu);
                     b.live--;
                 }
             }
         } else {
             for (unsigned l = 0; l < n; l++) {
-                PoolVec* r = b.ray[slots[l]];
+                PoolVec* r = rec(l);
                 WfRay R;
                 memset(&R, 0xFF, sizeof(R));
                 uint32_t k;
@@ -648,9 +670,45 @@ extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* ray
         for (unsigned l = 0; l < n; l++)
             if (push[l]) {
                 int qi = newq[l];
-                b.queue[qi][b.tail[qi] % N] = slots[l];
+                b.queue[qi][b.tail[qi] % (unsigned)N] = c.slots[l];
                 b.tail[qi]++;
             }
+    };
+    size_t turn = 0;
+    while (running) {
+        if (++passes > limit) return 0;
+        Block& b = blocks[turn++ % blocks.size()];
+        Claim claims[WARPS];
+        if (lockstep) {
+            for (int w = 0; w < WARPS; w++)
+                if (!b.warp_done[w]) claim(b, claims[w]);
+            for (int w = 0; w < WARPS; w++) {
+                if (b.warp_done[w]) continue;
+                if (claims[w].q >= 0) work(b, claims[w]);
+            }
+            for (int w = 0; w < WARPS; w++) {
+                if (b.warp_done[w] || claims[w].q >= 0) continue;
+                if (b.live <= 0) {
+                    b.warp_done[w] = true;
+                    running--;
+                } else {
+                    stats[12]++;
+                }
+            }
+        } else {
+            for (int w = 0; w < WARPS; w++) {
+                if (b.warp_done[w]) continue;
+                claim(b, claims[w]);
+                if (claims[w].q >= 0) {
+                    work(b, claims[w]);
+                } else if (b.live <= 0) {
+                    b.warp_done[w] = true;
+                    running--;
+                } else {
+                    stats[12]++;
+                }
+            }
+        }
     }
     return passes;
 }
