@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     lib.orc_rand_sequence.argtypes = [C.c_uint32, C.c_int, vp]
     lib.orc_hemisphere.argtypes = [vp, C.c_uint32, vp]
     lib.orc_generate_samples.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+    lib.orc_generate_samples_order.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.orc_generate_probe_rays.argtypes = [P, vp, vp]
     lib.orc_probe_update.argtypes = [P, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, C.c_int]
     lib.orc_render_frame.argtypes = [P, vp, vp, vp, vp, vp, vp, C.c_int]
@@ -189,9 +190,11 @@ class Scene:
         return p.probe_count[0] * p.probe_count[2] * tw, p.probe_count[1] * th
 
 
-def generate_samples(rx: int, ry: int, reseed: bool = True) -> np.ndarray:
+def generate_samples(rx: int, ry: int, reseed: bool = True, y_first: bool = False) -> np.ndarray:
+    """y_first=False: PIN 5 (x jitter drawn first), what every fixture and the engine use.  y_first=True: the order
+    g++ gives the reference's own text (oracle/_ref: ref_generate_probe_rays)."""
     out = np.zeros((rx * ry, 3), dtype=np.float32)
-    load().orc_generate_samples(rx, ry, 1 if reseed else 0, _ptr(out))
+    load().orc_generate_samples_order(rx, ry, 1 if reseed else 0, 1 if y_first else 0, _ptr(out))
     return out
 
 

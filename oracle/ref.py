@@ -47,6 +47,9 @@ def load() -> C.CDLL:
         lib.ref_probe_pass_lights.argtypes = lib.ref_probe_pass.argtypes
         lib.ref_compute_pass.argtypes = [C.POINTER(RefSettings), C.POINTER(RefField), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
         lib.ref_compute_pass_lights.argtypes = lib.ref_compute_pass.argtypes
+        if hasattr(lib, "ref_generate_probe_rays"):
+            lib.ref_generate_probe_rays.restype = C.c_uint32
+            lib.ref_generate_probe_rays.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, vp, C.c_uint32]
         lib.ref_compute_pass_chebyshev.argtypes = lib.ref_compute_pass.argtypes
         _lib = lib
     return _lib
@@ -62,6 +65,17 @@ def _params(scene, probe_count, side_length, field_origin, s, screen=(0, 0), max
     f.sqrt_rays_per_probe = s
     f.field_origin[:] = tuple(field_origin)
     return rs, f
+
+
+def generate_probe_rays(*, probe_count, side_length, field_origin, s, reseed=True) -> np.ndarray:
+    """The reference's HOST ray generator — generate_samples + RVPT::generate_probe_rays, src/rvpt/rvpt.cpp:1145-1224,
+    and struct ProbeRay, src/rvpt/probe.h — compiled from its own text against a glm stand-in.  float32 [R, 12]."""
+    n = probe_count[0] * probe_count[1] * probe_count[2] * s * s
+    out = np.zeros((n, 12), dtype=np.float32)
+    got = load().ref_generate_probe_rays((C.c_int * 3)(*probe_count), side_length, s, (C.c_float * 3)(*field_origin), 1 if reseed else 0,
+                                         out.ctypes.data, n)
+    assert got == n
+    return out
 
 
 def probe_pass(*, scene, probe_count, side_length, field_origin, s, rays, max_bounces=8, hysteresis=None, previous=None,

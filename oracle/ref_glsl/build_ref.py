@@ -20,6 +20,11 @@ grammar — and touches only what differs:
     every invocation (GLSL evaluates them per invocation, probe_pass.comp:55-57);
   * `glsl_count_lookup();` is inserted at the top of getBlockAt so the harness can report the
     reference's own voxel-lookup count per invocation.
+The HOST side of the path is pinned the same way: generate_samples and RVPT::generate_probe_rays
+(src/rvpt/rvpt.cpp:1145-1224) and struct ProbeRay (src/rvpt/probe.h, included where it lies) are
+compiled verbatim against a small glm stand-in (glm_shim/glm/glm.hpp; glm itself is fetched from
+the network by the reference's CMake) -> ref_generate_probe_rays.
+
 Further builds restore lines the reference itself has commented out — comment markers removed,
 nothing else (RESTORE below):
   ref_probe_pass_hysteresis   the hysteresis blend, probe_pass.comp:298-299;
@@ -263,6 +268,79 @@ def build_unit(shader: str, ns: str, shader_dir: str, harness: str, entry: str =
     return body, seen
 
 
+HOST_HARNESS = r'''
+// GENERATED by oracle/ref_glsl/build_ref.py — do not commit.
+// The reference's HOST ray generator compiled from its own text: src/rvpt/probe.h is included where
+// it lies, generate_samples / RVPT::generate_probe_rays are lines %(first)d-%(last)d of src/rvpt/rvpt.cpp and
+// struct IrradianceField lines %(f0)d-%(f1)d of src/rvpt/rvpt.h, verbatim, against oracle/ref_glsl/glm_shim.
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <glm/glm.hpp>
+#include "%(probe_h)s"
+
+class RVPT
+{
+public:
+    void generate_probe_rays();
+%(field_struct)s
+    IrradianceField ir;
+    std::vector<ProbeRay> probe_rays;
+    bool need_generate_probe_rays = true;
+};
+
+%(text)s
+
+extern "C" __attribute__((visibility("default")))
+uint32_t ref_generate_probe_rays(const int* probe_count, int side_length, int sqrt_rays_per_probe, const float* field_origin,
+                                 int reseed, float* out12, uint32_t capacity)
+{
+    static_assert(sizeof(ProbeRay) == 48, "ProbeRay is 48 bytes");
+    if (reseed) srand(1);   // the state of a process that never called srand
+    RVPT r;
+    r.ir.probe_count = glm::ivec3(probe_count[0], probe_count[1], probe_count[2]);
+    r.ir.side_length = side_length;
+    r.ir.sqrt_rays_per_probe = sqrt_rays_per_probe;
+    r.ir.field_origin = glm::vec3(field_origin[0], field_origin[1], field_origin[2]);
+    r.generate_probe_rays();
+    uint32_t n = (uint32_t)r.probe_rays.size();
+    if (out12 && n <= capacity) {
+        memset(out12, 0, (size_t)n * 48);
+        for (uint32_t k = 0; k < n; k++) {
+            const ProbeRay& p = r.probe_rays[k];
+            float* o = out12 + 12 * (size_t)k;
+            o[0] = p.origin.x; o[1] = p.origin.y; o[2] = p.origin.z;
+            o[4] = p.direction.x; o[5] = p.direction.y; o[6] = p.direction.z;
+            o[8] = p.probe_info.x; o[9] = p.probe_info.y; o[10] = p.probe_info.z;
+        }
+    }
+    return n;
+}
+'''
+
+
+def build_host_unit(reference: str) -> str:
+    """The reference's host ray generator (rvpt.cpp: #define PI ... end of RVPT::generate_probe_rays)."""
+    cpp = open(os.path.join(reference, "src", "rvpt", "rvpt.cpp"), encoding="utf-8", errors="replace").read().split("\n")
+    first = next(i for i, l in enumerate(cpp) if l.startswith("#define PI"))
+    start_fn = next(i for i, l in enumerate(cpp) if l.startswith("void RVPT::generate_probe_rays()"))
+    depth, last = 0, None
+    for i in range(start_fn, len(cpp)):
+        depth += cpp[i].count("{") - cpp[i].count("}")
+        if depth == 0 and "}" in cpp[i] and i > start_fn:
+            last = i
+            break
+    if last is None:
+        raise SystemExit("rvpt.cpp: end of RVPT::generate_probe_rays not found")
+    hdr = open(os.path.join(reference, "src", "rvpt", "rvpt.h"), encoding="utf-8", errors="replace").read().split("\n")
+    f0 = next(i for i, l in enumerate(hdr) if l.strip() == "struct IrradianceField")
+    f1 = next(i for i in range(f0, len(hdr)) if hdr[i].strip() == "};")
+    return HOST_HARNESS % {"first": first + 1, "last": last + 1, "f0": f0 + 1, "f1": f1 + 1,
+                           "probe_h": os.path.join(reference, "src", "rvpt", "probe.h"),
+                           "field_struct": "\n".join(hdr[f0:f1 + 1]), "text": "\n".join(cpp[first:last + 1])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -287,11 +365,20 @@ def main():
             f.write(f"// GENERATED by oracle/ref_glsl/build_ref.py from {shader} + {', '.join(seen)} — do not commit\n")
             f.write(head + body)
         units.append(path)
+    with open(os.path.join(OUT, "host_rays_ref.cpp"), "w") as f:
+        f.write(build_host_unit(args.reference))
     with open(os.path.join(OUT, "globals_ref.cpp"), "w") as f:
         f.write('#include "../ref_glsl/glsl_shim.h"\nuvec3 gl_GlobalInvocationID;\nuint32_t glsl_lookup_counter = 0;\n')
     units.append(os.path.join(OUT, "globals_ref.cpp"))
     subprocess.check_call(["make", "-s", "-C", ORACLE])
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    # the host ray generator is its own object: it must see the glm stand-in, not the GLSL shim
+    host_obj = os.path.join(OUT, "host_rays_ref.o")
+    host_cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-c", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden", "-w",
+                "-I" + os.path.join(HERE, "glm_shim"), "-o", host_obj, os.path.join(OUT, "host_rays_ref.cpp")]
+    print(" ".join(host_cmd))
+    subprocess.check_call(host_cmd)
+    units.append(host_obj)
     cmd = [cxx, "-O2", "-std=c++20", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden",
            "-fpermissive", "-w", "-o", os.path.join(OUT, "libddgi_ref.so"), *units,
            "-L" + ORACLE, "-lddgi_oracle", "-Wl,-rpath,$ORIGIN/..", "-lm"]

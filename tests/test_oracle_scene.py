@@ -5,7 +5,9 @@ import ctypes as C
 import numpy as np
 
 import util
-from oracle import oracle
+import pytest
+
+from oracle import oracle, ref
 
 CFG = util.configs.CONFIGS
 
@@ -121,3 +123,22 @@ def test_probe_texture_invariants():
     # rectangular tile reduces to the square case
     sq = util.oracle_scene(util.small(cfg, tile=(8, 8)))
     assert sq.tex_size == (72, 24)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("pc,side,s,org", [((3, 3, 3), 11, 8, (0.0, 0.0, 15.0)), ((2, 2, 2), 15, 8, (0.0, 0.0, 15.0)),
+                                           ((9, 7, 9), 11, 20, (1.4, 0.0, 1.0)), ((2, 3, 4), 7, 5, (0.5, -2.0, 3.25))])
+def test_host_ray_generator_against_the_reference_text_compiled_here(pc, side, s, org):
+    """generate_samples + RVPT::generate_probe_rays (rvpt.cpp:1145-1224) and struct ProbeRay (probe.h) compiled
+    verbatim against a glm stand-in (oracle/ref_glsl/build_ref.py).  The two rand() calls of rvpt.cpp:1161-1162
+    are constructor arguments — their order is unspecified in C++; g++ runs the second first.  With that
+    order the oracle's restatement is bit-identical to the compiled text; with PIN 5's order (x jitter
+    first: what the fixtures and the engine use) only the jitter pairing, hence the directions, differ."""
+    want = ref.generate_probe_rays(probe_count=pc, side_length=side, field_origin=org, s=s, reseed=True)
+    sc = oracle.Scene(probe_count=pc, side_length=side, field_origin=org, rx=s, lights=[], scene=1, procedural=True)
+    as_compiled = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True, y_first=True))
+    assert np.array_equal(as_compiled.view(np.uint32), want.view(np.uint32))
+    pinned = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True))
+    assert np.array_equal(pinned[:, [0, 1, 2, 8, 9, 10]].view(np.uint32), want[:, [0, 1, 2, 8, 9, 10]].view(np.uint32))   # origins, probe / tile indices
+    assert not np.array_equal(pinned[:, 4:7], want[:, 4:7])
+    assert np.allclose(np.linalg.norm(pinned[:, 4:7], axis=1), 1.0, atol=1e-6)
