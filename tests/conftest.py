@@ -24,6 +24,10 @@ def _has_gpu():
 
 def pytest_collection_modifyitems(config, items):
     if _has_gpu():
+        # a persistent kernel that lost a ray would never end: no GPU test may hang the run
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(300))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
