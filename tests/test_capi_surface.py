@@ -72,3 +72,40 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert not bad.search(text), f"{fn} reaches into oracle/"
+
+
+def test_header_is_plain_c_and_the_cpp_mirror_compiles(tmp_path):
+    """include/ddgi.h must be usable from C (C99, -pedantic) — it is the FFI boundary — and
+    include/rvpt_ddgi.hpp from C++17 without warnings; both link against the in-tree library."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    pkg = os.path.dirname(capi.LIB_PATH)
+    c_src = tmp_path / "use_ddgi.c"
+    c_src.write_text(
+        '#include "ddgi.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "    ddgi_light l[DDGI_MAX_LIGHTS], moved[DDGI_MAX_LIGHTS];\n"
+        "    int32_t n = 0;\n"
+        "    ddgi_ctx* ctx = 0;\n"
+        "    if (sizeof(ddgi_render_settings) != 32 || sizeof(ddgi_irradiance_field) != 48 || sizeof(ddgi_probe_ray) != 48) return 2;\n"
+        "    if (ddgi_default_lights(0, l, &n) != DDGI_OK || n != 1) return 3;\n"
+        "    if (ddgi_update_lights(0, 74.0f, l, n, moved) != DDGI_OK) return 4;\n"
+        '    printf("%s %d %.6f\\n", ddgi_version(), ddgi_create(&ctx, 0), (double)moved[0].pos[2]);\n'
+        "    if (ctx) ddgi_destroy(ctx);\n"
+        "    return 0;\n"
+        "}\n")
+    exe = tmp_path / "use_ddgi"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + inc, str(c_src), "-o", str(exe),
+                           "-L" + pkg, "-lddgi_b200", "-Wl,-rpath," + pkg])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert out[1] == "sm_100a" and float(out[3]) != 8.5          # the cave light moved with time
+    import torch
+
+    assert int(out[2]) == (capi.OK if torch.cuda.is_available() else capi.E_CUDA)
+    cpp_src = tmp_path / "use_mirror.cpp"
+    cpp_src.write_text('#include "rvpt_ddgi.hpp"\nint main() { ddgi::RVPT r(64, 64); return r.render_settings.max_bounces == 8 ? 0 : 1; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + inc, str(cpp_src), "-o", str(tmp_path / "use_mirror"),
+                           "-L" + pkg, "-lddgi_b200", "-Wl,-rpath," + pkg])
+    assert subprocess.call([str(tmp_path / "use_mirror")]) == 0
