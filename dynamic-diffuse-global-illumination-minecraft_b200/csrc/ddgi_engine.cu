@@ -20,7 +20,7 @@ struct ddgi_ctx {
     char err[512] = {0};
     uint64_t launches = 0;
     int debug = 0;
-    int variant = 1;
+    int variant = 2;
     int color_mode = 0;  // 0 flat palette, 1 the reference's procedural colours
     int blend_mode = 0;  // 1: hysteresis blend into the previous texel (field.hysteresis)
     int layout = 0, oct = 8;  // probe-texture layout: 0 the reference's ray tile, 1 octahedral oct x oct tiles
@@ -297,6 +297,7 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
         P->scene.vdim[a] = c->vdim[a];
         P->scene.nb[a] = c->nb[a];
         P->scene.borg[a] = c->borg[a];
+        P->scene.kneg[a] = -(kCellBias + c->borg[a]);
         P->scene.lo[a] = (float)c->vorg[a];
         P->scene.hi[a] = (float)(c->vorg[a] + c->vdim[a] - 1);
         P->probe_count[a] = c->field.probe_count[a];
@@ -322,6 +323,7 @@ static void fill_params(const ddgi_ctx* c, FrameParams* P)
     P->oct = c->oct;
     P->tile_w = tile_w(c);
     P->tile_h = tile_h(c);
+    P->early_out = c->variant == 2;
 }
 
 // The flat-colour table of the reference's block types: 2-5 are getColorAt's own flat
@@ -1036,7 +1038,7 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         J.ray_out = ctx->d_ray_out;
     }
     ctx->warp_times_n = 0;
-    if (ctx->debug >= 2 && ctx->variant == 1 && P.max_bounces > 0) {
+    if (ctx->debug >= 2 && ctx->variant != 0 && P.max_bounces > 0) {
         size_t warps = wavefront_warps(J.n_owned * J.slot_rays, ctx->grid_limit);
         if (warps > ctx->warp_times_cap) {
             dfree(ctx->d_warp_times);

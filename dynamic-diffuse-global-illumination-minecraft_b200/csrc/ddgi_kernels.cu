@@ -12,7 +12,6 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (see csrc/Makefile).
 #include "ddgi_internal.h"
-#include "ddgi_pooled.cuh"
 #include "ddgi_shade.cuh"
 #include "ddgi_wavefront.cuh"
 
@@ -119,7 +118,9 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // march_min/32 of its rays are marching; below that it counts its lanes per remaining
 // state (ballots), picks the fullest one and runs that state's code for exactly those
 // lanes.  The other lanes wait and accumulate, so each code block executes with many
-// lanes active instead of once per divergent lane group.
+// lanes active instead of once per divergent lane group.  Every ended march - a bounce ray's
+// or a shadow feeler's - waits in the same state (WF_HIT), so what the two have in common
+// is issued once for both.
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
 constexpr int kWfThreads = 128;
@@ -129,9 +130,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#ifndef DDGI_WF_UNROLL
-#define DDGI_WF_UNROLL 1  // march steps per lane-count check
-#endif
 #ifndef DDGI_WF_MIN_BLOCKS
 #define DDGI_WF_MIN_BLOCKS 7  // 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
@@ -169,33 +167,40 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         // ---- march while at least march_min/32 of the lanes holding a ray are marching ----
         const int n_live = __popc(__ballot_sync(full, R.mode != WF_IDLE));
         if (n_live == 0) break;
-        const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // in 1/32 lanes, >= 1 lane
-        while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) * 32 >= enough) {
-#pragma unroll
-            for (int u = 0; u < DDGI_WF_UNROLL; u++)
-                if (R.mode == WF_MARCH) wf_step(P, R);
+        const int enough = (n_live * march_min + 31) >> 5 > 1 ? (n_live * march_min + 31) >> 5 : 1;  // lanes
+        while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) >= enough) {
+            if (R.mode == WF_MARCH) wf_step(P, R);
         }
-        // ---- otherwise run the fullest of the other states (ties: the later stage):
-        //      one MATCH gives every lane the size of its own group, one REDUX the winner ----
-        const unsigned peers = __match_any_sync(full, R.mode);
-        const unsigned key = (R.mode != WF_MARCH && R.mode != WF_IDLE) ? ((unsigned)__popc(peers) << 3) | (unsigned)R.mode : 0u;
-        const int best = (int)(__reduce_max_sync(full, key) & 7u);
-        if (best == WF_MARCH) continue;  // only marching lanes are left: lower the bar next pass
+        wf_end_march(R);
+        // ---- otherwise run the fullest of the other states (ties: the later stage).  Ended marches
+        //      of bounce rays and of shadow feelers run the same code (wf_resolve_hit) but are
+        //      scheduled as two states: the kind that waits keeps accumulating lanes, which the
+        //      model (profiles/policy_sim.py) and round 1's measurements favour over one merged pass ----
+        const bool hit_feeler = R.mode == WF_HIT && R.phase != 0, hit_bounce = R.mode == WF_HIT && R.phase == 0;
+        const int n_hit_f = __popc(__ballot_sync(full, hit_feeler));
+        const int n_hit_b = __popc(__ballot_sync(full, hit_bounce));
+        const unsigned fetching = __ballot_sync(full, R.mode == WF_FETCH);
+        const int n_fetch = __popc(fetching);
+        const int n_slow = __popc(__ballot_sync(full, R.mode == WF_MARCH_SLOW));
+        const int n_hit = n_hit_f > n_hit_b ? n_hit_f : n_hit_b;
+        if (n_hit + n_fetch + n_slow == 0) continue;  // (only marching lanes: cannot be fewer than `enough`)
 
-        if (best == WF_BOUNCE_HIT) {
-            if (R.mode == WF_BOUNCE_HIT) {
-                float* first_t = (want_first_t && R.bounce == 0) ? &s_first_t[threadIdx.x] : nullptr;
-                wf_resolve_bounce<kLiteral>(P, R, stash, kWfThreads, first_t);
+        if (n_slow > n_hit && n_slow > n_fetch) {
+            if (R.mode == WF_MARCH_SLOW) {
+                wf_step_literal(P, R);
+                wf_end_march(R);
             }
-        } else if (best == WF_FEELER_HIT) {
-            if (R.mode == WF_FEELER_HIT) wf_resolve_feeler<kLiteral>(P, R, stash, kWfThreads);
-        } else if (best == WF_MARCH_SLOW) {
-            if (R.mode == WF_MARCH_SLOW) wf_step_literal(P, R);
+        } else if (n_hit > n_fetch) {
+            if (n_hit_f >= n_hit_b ? hit_feeler : hit_bounce) {
+                float* first_t = (want_first_t && R.bounce == 0 && R.phase == 0) ? &s_first_t[threadIdx.x] : nullptr;
+                wf_resolve_hit<kLiteral>(P, R, stash, kWfThreads, first_t);
+            }
         } else {
             // WF_FETCH: store the finished ray, take the next one
-            bool need = R.mode == WF_FETCH;
-            if (need && k != 0xffffffffu) store_texel(J, tx, ty, R.color, k, R.lookups, want_first_t ? s_first_t[threadIdx.x] : 0.0f);
-            unsigned want = __ballot_sync(full, need);
+            const bool need = R.mode == WF_FETCH;
+            if (need && k != 0xffffffffu)
+                store_texel(J, tx, ty, wf_final_color(P, R), k, R.lookups, want_first_t ? s_first_t[threadIdx.x] : 0.0f);
+            const unsigned want = fetching;
             uint32_t cnt = (uint32_t)__popc(want);
             uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
             uint32_t avail = chunk_end - chunk_next;
@@ -238,233 +243,14 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                 }
             }
         }
-        // a resolved bounce scatters at once, and every state above hands over to WF_QUERY or
+        // a finished bounce scatters at once, and every state above hands over to WF_QUERY or
         // ends the ray: arm the new queries right away.  Neither is scheduled as a state of
-        // its own (one MATCH/REDUX round less per bounce and per query).
+        // its own (one scheduling round less per bounce and per query).
         if (R.mode == WF_SCATTER) wf_scatter(P, R);
         if (R.mode == WF_QUERY) wf_begin_query(P, R);
     }
     if (lane == 0) DDGI_WARP_TIME(2);
 #undef DDGI_WARP_TIME
-}
-
-// ------------------------------------------------------------------ variant 2 (experimental)
-// The wavefront state machine with a block's rays in a shared-memory pool (ddgi_pooled.cuh):
-// kPoolSlots ray records, one queue of slot indices per state.  Each warp repeatedly takes the
-// queue with the most rays waiting (up to 32, MARCH first on ties), claims that many entries with
-// one CAS on the queue head, loads the records into registers, runs the state's code — for a march:
-// DDA steps while at least march_keep/32 of the claimed rays are still marching — stores the
-// records and appends each ray to the queue of its new state.  Queues are rings of kPoolSlots
-// entries (a slot waits in at most one queue); appends reserve positions with one atomic per warp
-// and state and are committed in reservation order, so `tail` only ever covers written entries.
-constexpr int kPoolThreads = 128;
-constexpr int kPoolSlots = 128;
-#ifndef DDGI_POOL_MIN_BLOCKS
-#define DDGI_POOL_MIN_BLOCKS 7
-#endif
-struct PoolShared {
-    float4 ray[kPoolSlots][kPoolVecs];
-    int queue[PQ_COUNT][kPoolSlots];
-    unsigned head[PQ_COUNT], tail[PQ_COUNT], reserve[PQ_COUNT];
-    int live;  // slots that hold a ray or may still take one
-};
-__device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
-__device__ __forceinline__ void pool_load(const float4* rec, PoolVec* r, int first, int count)
-{
-#pragma unroll
-    for (int i = 0; i < count; i++) {
-        float4 v = rec[first + i];
-        r[first + i].x = v.x;
-        r[first + i].y = v.y;
-        r[first + i].z = v.z;
-        r[first + i].w = v.w;
-    }
-}
-__device__ __forceinline__ void pool_store(float4* rec, const PoolVec* r, int i) { rec[i] = make_float4(r[i].x, r[i].y, r[i].z, r[i].w); }
-
-// Appends `slot` of every active lane to queue q (lanes may name different queues).
-__device__ __forceinline__ void pool_push(PoolShared& S, bool active, int q, int slot, int lane)
-{
-    const unsigned m = __match_any_sync(0xffffffffu, active ? q : 31);
-    if (active) {
-        const int leader = __ffs(m) - 1;
-        const unsigned cnt = (unsigned)__popc(m), rank = (unsigned)__popc(m & ((1u << lane) - 1u));
-        unsigned pos = 0;
-        if (lane == leader) pos = atomicAdd(&S.reserve[q], cnt);
-        pos = __shfl_sync(m, pos, leader);
-        *reinterpret_cast<volatile int*>(&S.queue[q][(pos + rank) % kPoolSlots]) = slot;
-        __threadfence_block();  // the record and the entry before the commit below
-        __syncwarp(m);
-        if (lane == leader) {
-            while (ld_vol(&S.tail[q]) != pos) {
-            }  // commit in reservation order
-            *reinterpret_cast<volatile unsigned*>(&S.tail[q]) = pos + cnt;
-        }
-    }
-}
-
-// Destination texel of ray k (what fetch_ray computes besides the ray itself).
-__device__ __forceinline__ void ray_texel(const FrameParams& P, const ProbeJob& J, uint32_t k, int* tx, int* ty)
-{
-    int tiles_x = P.probe_count[0] * P.probe_count[2];
-    int p, ix, iy;
-    if (J.rays) {
-        float4 c = __ldg(J.rays + 3 * (size_t)k + 2);
-        p = f2i(c.x);
-        ix = f2i(c.y);
-        iy = f2i(c.z);
-    } else {
-        int n = P.rx * P.ry;
-        p = (int)(k / (uint32_t)n);
-        int i = (int)(k - (uint32_t)p * (uint32_t)n);
-        iy = i / P.rx;
-        ix = i - iy * P.rx;
-    }
-    int yp = p / tiles_x;
-    int xp = p - yp * tiles_x;
-    *tx = xp * P.rx + ix;
-    *ty = yp * P.ry + iy;
-}
-
-__global__ void __launch_bounds__(kPoolThreads, DDGI_POOL_MIN_BLOCKS) probe_update_pooled(const __grid_constant__ FrameParams P,
-                                                                                        const __grid_constant__ ProbeJob J,
-                                                                                        uint32_t* __restrict__ next_ray, int march_keep)
-{
-    __shared__ PoolShared S;
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const uint32_t n_rays = J.n_owned * J.slot_rays;
-    const uint32_t no_ray = 0xffffffffu;
-    for (int i = threadIdx.x; i < kPoolSlots; i += kPoolThreads) {
-        S.queue[PQ_FETCH][i] = i;
-        S.ray[i][6].w = __uint_as_float(no_ray);  // the slot holds no ray yet
-        S.ray[i][2].w = 0.0f;
-        S.ray[i][7].w = 0.0f;
-        S.ray[i][8] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (threadIdx.x < PQ_COUNT) {
-        S.head[threadIdx.x] = 0u;
-        S.tail[threadIdx.x] = S.reserve[threadIdx.x] = threadIdx.x == PQ_FETCH ? (unsigned)kPoolSlots : 0u;
-    }
-    if (threadIdx.x == 0) S.live = kPoolSlots;
-    __syncthreads();
-    float dummy_stash = 0.0f;
-
-    for (;;) {
-        // ---- the fullest queue (at most a warp's worth counts), MARCH first on ties
-        unsigned key = 0u;
-        if (lane < PQ_COUNT) {
-            unsigned c = ld_vol(&S.tail[lane]) - ld_vol(&S.head[lane]);
-            const unsigned pref = lane == PQ_MARCH ? 7u : lane == PQ_FETCH ? 6u : lane == PQ_FEELER ? 5u : lane == PQ_BOUNCE ? 4u : 3u;
-            if (c) key = ((c < 32u ? c : 32u) << 3) | pref;
-        }
-        const unsigned best = __reduce_max_sync(full, key);
-        if (best == 0u) {
-            if (*reinterpret_cast<volatile int*>(&S.live) <= 0) break;
-            __nanosleep(100);
-            continue;
-        }
-        const unsigned pref = best & 7u;
-        const int q = pref == 7u ? PQ_MARCH : pref == 6u ? PQ_FETCH : pref == 5u ? PQ_FEELER : pref == 4u ? PQ_BOUNCE : PQ_SLOW;
-        // ---- claim up to 32 entries
-        unsigned old = 0u, n = 0u;
-        if (lane == 0) {
-            old = ld_vol(&S.head[q]);
-            unsigned avail = ld_vol(&S.tail[q]) - old;
-            n = avail < 32u ? avail : 32u;
-            if (n && atomicCAS(&S.head[q], old, old + n) != old) n = 0u;
-        }
-        n = __shfl_sync(full, n, 0);
-        old = __shfl_sync(full, old, 0);
-        if (n == 0u) continue;
-        __threadfence_block();
-        const bool mine = (unsigned)lane < n;
-        const int slot = mine ? *reinterpret_cast<volatile int*>(&S.queue[q][(old + (unsigned)lane) % kPoolSlots]) : 0;
-        float4* rec = S.ray[slot];
-        PoolVec r[kPoolVecs];
-        WfRay R;
-        R.mode = WF_IDLE;
-
-        if (q == PQ_MARCH || q == PQ_SLOW) {
-            const int run_mode = q == PQ_MARCH ? WF_MARCH : WF_MARCH_SLOW;
-            if (mine) {
-                pool_load(rec, r, 0, 4);
-                pool_unpack_march(r, R);
-                R.mode = run_mode;
-            }
-            unsigned active;
-            do {
-                if (R.mode == run_mode) {
-                    if (q == PQ_MARCH) wf_step(P, R);
-                    else wf_step_literal(P, R);
-                }
-                active = (unsigned)__popc(__ballot_sync(full, R.mode == run_mode));
-            } while (active && active * 32u >= n * (unsigned)march_keep);
-            if (mine) {
-                pool_pack_march(R, r);
-                pool_store(rec, r, 0);
-                pool_store(rec, r, 1);
-                pool_store(rec, r, 3);
-            }
-            pool_push(S, mine, pool_queue_of(R.mode), slot, lane);
-            continue;
-        }
-
-        if (q == PQ_FETCH) {
-            uint32_t k = no_ray;
-            if (mine) {
-                pool_load(rec, r, 2, 1);
-                pool_load(rec, r, 6, 3);
-                k = __float_as_uint(r[6].w);
-                if (k != no_ray) {
-                    int tx, ty;
-                    ray_texel(P, J, k, &tx, &ty);
-                    store_texel(J, tx, ty, V3(r[8].x, r[8].y, r[8].z), k, __float_as_uint(r[2].w), r[7].w);
-                }
-            }
-            uint32_t base = 0u;
-            if (lane == 0) base = atomicAdd(next_ray, n);
-            base = __shfl_sync(full, base, 0);
-            const uint32_t idx = base + (uint32_t)lane;
-            const bool got = mine && idx < n_rays && base < n_rays;
-            if (got) {
-                k = shard_ray(J, idx);
-                RayIn in = fetch_ray(P, J, k);
-                wf_init(R, in.origin, in.direction, k);
-                wf_begin_query(P, R);
-                pool_pack(R, k, 0.0f, r);
-#pragma unroll
-                for (int i = 0; i < kPoolVecs; i++) pool_store(rec, r, i);
-            }
-            const unsigned retired = (unsigned)__popc(__ballot_sync(full, mine && !got));
-            if (lane == 0 && retired) atomicSub(&S.live, (int)retired);
-            pool_push(S, got, pool_queue_of(R.mode), slot, lane);
-            continue;
-        }
-
-        // ---- PQ_BOUNCE / PQ_FEELER: resolve, then scatter and arm the next query in the same pass
-        uint32_t k = no_ray;
-        float first_t = 0.0f;
-        if (mine) {
-            pool_load(rec, r, 0, kPoolVecs);
-            pool_unpack(r, R, k, first_t);
-            R.mode = q == PQ_BOUNCE ? WF_BOUNCE_HIT : WF_FEELER_HIT;
-            if (q == PQ_BOUNCE) {
-                const bool first = R.bounce == 0;
-                float nearest;
-                wf_resolve_bounce<false>(P, R, &dummy_stash, 0, &nearest);
-                if (first) first_t = nearest;
-            } else {
-                wf_resolve_feeler<false>(P, R, &dummy_stash, 0);
-            }
-            if (R.mode == WF_SCATTER) wf_scatter(P, R);
-            if (R.mode == WF_QUERY) wf_begin_query(P, R);
-            pool_pack(R, k, first_t, r);
-#pragma unroll
-            for (int i = 0; i < kPoolVecs; i++) pool_store(rec, r, i);
-        }
-        pool_push(S, mine, pool_queue_of(R.mode), slot, lane);
-    }
 }
 
 // ------------------------------------------------------------------ octahedral blend
@@ -663,7 +449,7 @@ __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, i
                     int gx = bx * 4 + x - sx, gy = by * 4 + y - sy, gz = bz * 2 + z - sz;
                     if (gx >= 0 && gy >= 0 && gz >= 0 && gx < dx && gy < dy && gz < dz &&
                         types[((size_t)gz * dy + gy) * dx + gx] != 0)
-                        w |= 1u << (x | (y << 2) | (z << 4));
+                        w |= 1u << (occ_shift(bx * 4 + x, by * 4 + y, bz * 2 + z) & 31);
                 }
         occ[((size_t)bz * nby + by) * nbx + bx] = w;
     }
@@ -714,24 +500,6 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    if (variant == 2 && P.scene.color_mode == 0 && !J.warp_times) {
-        // experimental pooled kernel (palette colours only; everything else runs variant 1)
-        static int pool_blocks = 0, pool_sms = 0;
-        if (!pool_blocks) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&pool_sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pool_blocks, probe_update_pooled, kPoolThreads, 0);
-            if (pool_blocks < 1) pool_blocks = 1;
-        }
-        int per_sm = grid_limit > 0 && grid_limit < pool_blocks ? grid_limit : pool_blocks;
-        uint32_t pgrid = (uint32_t)(pool_sms * per_sm);
-        uint32_t needed = (n + kPoolSlots - 1) / kPoolSlots;
-        if (pgrid > needed) pgrid = needed;
-        probe_update_pooled<<<pgrid, kPoolThreads, 0, s>>>(P, J, counter, march_min);
-        (*launches)++;
-        return cudaGetLastError();
-    }
     uint32_t grid = wavefront_warps(n, grid_limit) / (kWfThreads / 32);
     const bool literal = P.scene.color_mode != 0, timed = J.warp_times != nullptr;
     if (literal && timed) probe_update_wavefront<true, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);

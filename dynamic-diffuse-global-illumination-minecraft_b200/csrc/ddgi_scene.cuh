@@ -3,7 +3,7 @@
 // scene bakers that evaluate that procedural function once per voxel.
 //
 // HBM layout (DESIGN.md "Data layout"):
-//   occ   : one uint32 per 4x4x2 voxel brick, bit (x&3)|(y&3)<<2|(z&1)<<4 set = solid,
+//   occ   : one uint32 per 4x4x2 voxel brick, bit occ_shift(x, y, z) & 31 set = solid,
 //           x/y/z = voxel id relative to `borg` (a multiple of 4 per axis).  Brick index
 //           ((bz*nby)+by)*nbx+bx, x fastest: a 32-byte sector holds 32x4x2 voxels.
 //           512^3 voxels -> 16 MiB, L1/L2 resident.
@@ -23,6 +23,7 @@ struct SceneView {
     int vorg[3];
     int vdim[3];
     int borg[3];  // voxel id of brick (0,0,0)'s first cell: vorg rounded down to a multiple of 4
+    int kneg[3];  // -(kCellBias + borg): biased cell coordinate -> borg-relative cell coordinate in one add
     int nb[3];    // bricks per axis (4 cells in x and y, 2 in z)
     float lo[3];  // (float)vorg
     float hi[3];  // (float)(vorg + vdim - 1)
@@ -59,20 +60,37 @@ DDGI_HD uint32_t shr_wrap(uint32_t w, int s)
 #endif
 }
 
+// Bit of the cell with borg-relative coordinates (gx, gy, gz) inside its brick word, as a shift
+// count that is taken modulo 32: bits 0-1 = gx & 3, bits 2-3 = gy & 3, bit 4 = (gz ^ (gy >> 2)) & 1.
+// The z layer of a brick is skewed by the brick row's parity so that the count is three
+// shift-adds with no masking of gy and gz; writers (build_occupancy_kernel, tests/hostsim) and
+// readers (cell_solid) share this one definition.
+DDGI_HD int occ_shift(int gx, int gy, int gz) { return (gx & 3) + (gy << 2) + (gz << 4); }
+
+// The occupancy word `idx` when `inside`, else 0 (bricks outside the grid are empty): one
+// predicated load, no branch, no divergence.
+DDGI_HD uint32_t occ_word(const uint32_t* occ, unsigned idx, bool inside)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t w = 0u;
+    if (inside) w = __ldg(occ + idx);
+    return w;
+#else
+    return inside ? occ[idx] : 0u;
+#endif
+}
+
 // Occupancy test of the cell with biased integer coordinates (kx,ky,kz) = cell_bits(c)
 // per axis; bricks outside the grid read as empty.
 DDGI_HD bool cell_solid(const SceneView& S, int kx, int ky, int kz)
 {
-    int gx = kx - (kCellBias + S.borg[0]);
-    int gy = ky - (kCellBias + S.borg[1]);
-    int gz = kz - (kCellBias + S.borg[2]);
-    unsigned bx = (unsigned)(gx >> 2), by = (unsigned)(gy >> 2), bz = (unsigned)(gz >> 1);
-    // out-of-grid bricks read word 0 and are masked off: no branch, no divergence
+    int gx = kx + S.kneg[0];
+    int gy = ky + S.kneg[1];
+    int gz = kz + S.kneg[2];
+    unsigned bx = (unsigned)gx >> 2, by = (unsigned)gy >> 2, bz = (unsigned)gz >> 1;  // (negative: huge)
     bool inside = (bx < (unsigned)S.nb[0]) & (by < (unsigned)S.nb[1]) & (bz < (unsigned)S.nb[2]);
-    unsigned idx = inside ? (bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx : 0u;
-    uint32_t word = S.occ[idx];
-    // bit (gx&3) | (gy&3)<<2 | (gz&1)<<4; the higher bits of gz fall off the 5-bit shift count
-    return inside & (bool)(shr_wrap(word, (gx & 3) + ((gy & 3) << 2) + (gz << 4)) & 1u);
+    uint32_t word = occ_word(S.occ, (bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx, inside);
+    return (bool)(shr_wrap(word, occ_shift(gx, gy, gz)) & 1u);
 }
 
 // Block type of an occupied cell (only called after its occupancy bit tested set).

@@ -52,6 +52,10 @@ struct FrameParams {
     // tile of oct x oct texels (ddgi_octahedral.cuh); tile_w x tile_h is the tile either way
     int layout, oct;
     int tile_w, tile_h;
+    // 1: result-preserving early-outs of the wavefront kernel (ddgi_wavefront.cuh: a shadow feeler's
+    // march ends once it has left its light behind); texels are unchanged, the voxel-lookup counts
+    // are no longer those of the reference algorithm (kernel variant 2, the default)
+    int early_out;
 };
 
 struct Hit {
@@ -204,6 +208,24 @@ DDGI_HD v3 face_normal_unit(v3 p, v3 cell)
     return n;
 }
 
+// face_normal_unit for the common case, without the normalize(): when one component of
+// p - cell_centre is the clear winner - in [2^-20, 4] and more than 2^-20 (relative) above the
+// other two - scaling all three by the same finite positive factor 1/|diff| and rounding cannot
+// change which one is largest (rounding is monotone and moves a value by at most 2^-24 relative)
+// nor its sign, so face_normal's comparisons on the normalised vector pick that axis.  Anything
+// else (near ties at cell edges, zero / NaN / huge positions) takes the literal path.
+DDGI_HD v3 face_normal_axis(v3 p, v3 cell)
+{
+    v3 centre = V3(cell.x - 0.5f, cell.y - 0.5f, cell.z - 0.5f);
+    v3 d = p - centre;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const float margin = 1.00000095367431640625f;  // 1 + 2^-20
+    if (ax >= 9.5367431640625e-07f && ax <= 4.0f && ax > ay * margin && ax > az * margin) return V3(d.x > 0.0f ? 1.0f : -1.0f, 0, 0);
+    if (ay >= 9.5367431640625e-07f && ay <= 4.0f && ay > ax * margin && ay > az * margin) return V3(0, d.y > 0.0f ? 1.0f : -1.0f, 0);
+    if (az >= 9.5367431640625e-07f && az <= 4.0f && az > ax * margin && az > ay * margin) return V3(0, 0, d.z > 0.0f ? 1.0f : -1.0f);
+    return face_normal_unit(p, cell);
+}
+
 // One DDA advance: distance to the next lattice plane along each axis, the
 // smallest plus the 1e-4 nudge, accumulate, re-evaluate the position.
 DDGI_HD void march_advance(v3 origin, v3 dir, float& t, v3& p)
@@ -229,8 +251,7 @@ DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32
     v3 dir = normalize(direction);
     v3 p = origin;
     float t = 0.0f;
-    const bool fast = regular_component(dir.x) && regular_component(dir.y) && regular_component(dir.z) &&
-                      regular_origin(origin.x) && regular_origin(origin.y) && regular_origin(origin.z);
+    const bool fast = regular_direction(dir.x, dir.y, dir.z) && regular_origin3(origin.x, origin.y, origin.z);
     bool hit = false;
     if (fast) {
         const v3 inv = V3(rcp_regular(dir.x), rcp_regular(dir.y), rcp_regular(dir.z));

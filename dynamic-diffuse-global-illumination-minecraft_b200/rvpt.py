@@ -88,6 +88,7 @@ class RVPT:
         self.lights = None    # None = the reference's table for render_settings.scene
         self.animate_lights = False  # True = update_lights() restored: lights move with render_settings.time
         self._applied_field = None
+        self.kernel_variant = 2  # the engine's default (ddgi_set_kernel_variant)
 
     # -- plumbing -------------------------------------------------------------------
     def _check(self, rc: int):
@@ -379,6 +380,7 @@ class RVPT:
 
     def set_kernel_variant(self, v: int):
         self._check(self._lib.ddgi_set_kernel_variant(self._ctx, v))
+        self.kernel_variant = v
 
     def set_tuning(self, march_min: int):
         self._check(self._lib.ddgi_set_tuning(self._ctx, march_min))

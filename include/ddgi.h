@@ -279,7 +279,7 @@ DDGI_API int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes
 
 /* ---- instrumentation ---- */
 /* debug >= 1: keep fp32 copies of the outputs and per-invocation voxel-lookup counts.
-   debug == 2: kernel variant 1 also records, per warp, the %globaltimer (ns) at which it started,
+   debug == 2: kernel variants 1 and 2 also record, per warp, the %globaltimer (ns) at which it started,
    took its last ray and exited (ddgi_read_warp_times) — how long the persistent kernel's tail is. */
 DDGI_API int ddgi_set_debug(ddgi_ctx* ctx, int32_t debug);
 /* *n_warps = warps of the last probe update that recorded times; dst (may be NULL to query the
@@ -287,10 +287,13 @@ DDGI_API int ddgi_set_debug(ddgi_ctx* ctx, int32_t debug);
 DDGI_API int ddgi_read_warp_times(ddgi_ctx* ctx, uint64_t* dst, size_t count, size_t* n_warps);
 /* Per-ray (which = 0) or per-pixel (which = 1) voxel lookups of the last dispatch. */
 DDGI_API int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t count);
-/* Kernel variant: 0 = one thread per ray, reference loop order; 1 = regrouped
-   state-machine kernel (default); 2 = EXPERIMENTAL: the same state machine with a block's rays
-   pooled in shared memory so that a warp gathers any 32 rays in the same state (palette colour
-   mode only, otherwise variant 1 runs).  Results are identical. */
+/* Kernel variant: 0 = one thread per ray, reference loop order; 1 = regrouped state-machine
+   kernel performing exactly the voxel lookups of the reference algorithm; 2 (default) = the same
+   kernel with its result-preserving early-outs: the march of a shadow feeler ends once the feeler
+   has left its light behind (the reference marches on to the next block or 125 cells and then
+   discards that hit, probe_pass.comp:186-207 with intersection.glsl:1262-1295).  Texels are
+   identical bit for bit in all three; the per-ray lookup counts of ddgi_read_lookup_counts are the
+   reference algorithm's in variants 0 and 1 and at most those in variant 2. */
 DDGI_API int ddgi_set_kernel_variant(ddgi_ctx* ctx, int32_t variant);
 /* Scheduling knob of variant 1: a warp keeps stepping its marches while at least
    march_min/32 of the lanes that hold a ray are marching (1..32, default 16).  Results do

@@ -10,7 +10,6 @@
 #include <vector>
 
 #include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_shade.cuh"
-#include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_pooled.cuh"
 #include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_wavefront.cuh"
 
 using namespace ddgi;
@@ -55,6 +54,7 @@ static void build(const SimParams* S, const float* cam, Built* B)
         P.scene.vorg[a] = S->vorg[a];
         P.scene.vdim[a] = S->vdim[a];
         P.scene.borg[a] = borg;
+        P.scene.kneg[a] = -(kCellBias + borg);
         P.scene.nb[a] = nb[a];
         P.scene.lo[a] = (float)S->vorg[a];
         P.scene.hi[a] = (float)(S->vorg[a] + S->vdim[a] - 1);
@@ -67,8 +67,7 @@ static void build(const SimParams* S, const float* cam, Built* B)
             for (int x = 0; x < S->vdim[0]; x++)
                 if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x]) {
                     int bx = x + sh[0], by = y + sh[1], bz = z + sh[2];
-                    B->occ[((size_t)(bz >> 1) * nb[1] + (by >> 2)) * nb[0] + (bx >> 2)] |=
-                        1u << ((bx & 3) | ((by & 3) << 2) | ((bz & 1) << 4));
+                    B->occ[((size_t)(bz >> 1) * nb[1] + (by >> 2)) * nb[0] + (bx >> 2)] |= 1u << (occ_shift(bx, by, bz) & 31);
                 }
     P.scene.occ = B->occ.data();
     P.scene.types = S->vox;
@@ -103,72 +102,17 @@ static void build(const SimParams* S, const float* cam, Built* B)
     }
 }
 
-// Variant 2 (ddgi_pooled.cuh) for one ray: the state machine with the ray living in its packed
-// pool record — after every state execution it is packed, and the next execution unpacks it into
-// a WfRay whose every byte was poisoned first, the march through its own smaller record and in
-// sessions of at most 3 steps.  A field missing from a record cannot go unnoticed.
-static v3 pooled_trace_scalar(const FrameParams& P, v3 origin, v3 direction, uint32_t ray_index, uint32_t& lookups, float* first_t_out)
-{
-    if (P.max_bounces <= 0) return wavefront_trace_scalar(P, origin, direction, ray_index, lookups, first_t_out);  // the engine runs variant 0 then
-    PoolVec rec[kPoolVecs];
-    memset(rec, 0xFF, sizeof(rec));
-    int mode;
-    {
-        WfRay R;
-        memset(&R, 0xFF, sizeof(R));
-        wf_init(R, origin, direction, ray_index);
-        wf_begin_query(P, R);
-        pool_pack(R, ray_index, 0.0f, rec);
-        mode = R.mode;
-    }
-    float stash[3] = {0, 0, 0};
-    for (;;) {
-        WfRay R;
-        memset(&R, 0xFF, sizeof(R));
-        if (mode == WF_MARCH || mode == WF_MARCH_SLOW) {
-            pool_unpack_march(rec, R);
-            R.mode = mode;
-            for (int i = 0; i < 3 && R.mode == mode; i++) {
-                if (mode == WF_MARCH) wf_step(P, R);
-                else wf_step_literal(P, R);
-            }
-            pool_pack_march(R, rec);
-            mode = R.mode;
-            continue;
-        }
-        uint32_t k;
-        float first_t;
-        pool_unpack(rec, R, k, first_t);
-        R.mode = mode;
-        if (mode == WF_FETCH) {
-            lookups += R.lookups;
-            if (first_t_out) *first_t_out = first_t;
-            return R.color;
-        }
-        if (mode == WF_BOUNCE_HIT) {
-            float nearest = 0.0f;
-            bool first = R.bounce == 0;
-            wf_resolve_bounce<false>(P, R, stash, 1, &nearest);
-            if (first) first_t = nearest;
-        } else {
-            wf_resolve_feeler<false>(P, R, stash, 1);
-        }
-        if (R.mode == WF_SCATTER) wf_scatter(P, R);
-        if (R.mode == WF_QUERY) wf_begin_query(P, R);
-        pool_pack(R, k, first_t, rec);
-        mode = R.mode;
-    }
-}
-
 extern "C" {
 
 // variant 0: trace_probe_ray (reference loop order); variant 1: the wavefront
-// state machine stepped one lane at a time.
+// state machine stepped one lane at a time; variant 2: the same with its result-preserving
+// early-outs (FrameParams::early_out: same texels, fewer voxel lookups).
 void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32_t k0, uint32_t k1,
                       int variant, uint32_t* albedo, float* f32, uint32_t* lookups, uint32_t* distance)
 {
     Built B;
     build(S, nullptr, &B);
+    B.P.early_out = variant == 2;
     const FrameParams& P = B.P;
     int W = P.probe_count[0] * P.probe_count[2] * P.rx;
     int tiles_x = P.probe_count[0] * P.probe_count[2];
@@ -181,9 +125,8 @@ void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32
         int tx = xp * P.rx + f2i(r[9]), ty = yp * P.ry + f2i(r[10]);
         uint32_t n = 0;
         float first_t = 0.0f;
-        v3 c = variant == 0   ? trace_probe_ray(P, o, d, (uint32_t)k, n, &first_t)
-               : variant == 1 ? wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t)
-                              : pooled_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
+        v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n, &first_t)
+                            : wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
         size_t t = (size_t)ty * W + tx;
         if (S->blend_mode) c = blend_hysteresis(albedo[t], c, S->hysteresis);
         albedo[t] = pack_rgba8(c.x, c.y, c.z, 1.0f);
@@ -279,6 +222,29 @@ void sim_bake_scene(int scene, const int32_t* org, const int32_t* dim, uint8_t* 
                     (uint8_t)block_procedural(V3((float)(x + org[0]), (float)(y + org[1]), (float)(z + org[2])), scene);
 }
 
+// Range checks of the fast march step and the face-normal shortcut, for brute-force comparison with
+// their float / literal definitions (tests/test_oracle_math.py).
+void sim_regular_checks(const float* x, int n, uint8_t* component, uint8_t* origin, uint8_t* dir3, uint8_t* org3)
+{
+    for (int i = 0; i < n; i++) {
+        component[i] = regular_component(x[i]);
+        origin[i] = regular_origin(x[i]);
+    }
+    for (int i = 0; i + 2 < n; i += 3) {
+        dir3[i / 3] = regular_direction(x[i], x[i + 1], x[i + 2]);
+        org3[i / 3] = regular_origin3(x[i], x[i + 1], x[i + 2]);
+    }
+}
+void sim_face_normals(const float* p, const float* cell, int n, float* fast, float* literal)
+{
+    for (int i = 0; i < n; i++) {
+        v3 a = face_normal_axis(V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(cell[3 * i], cell[3 * i + 1], cell[3 * i + 2]));
+        v3 b = face_normal_unit(V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V3(cell[3 * i], cell[3 * i + 1], cell[3 * i + 2]));
+        fast[3 * i] = a.x; fast[3 * i + 1] = a.y; fast[3 * i + 2] = a.z;
+        literal[3 * i] = b.x; literal[3 * i + 1] = b.y; literal[3 * i + 2] = b.z;
+    }
+}
+
 void sim_pin_sincos(const float* x, int n, float* s, float* c)
 {
     for (int i = 0; i < n; i++) pin_sincos(x[i], &s[i], &c[i]);
@@ -291,181 +257,171 @@ void sim_pin_acos(const float* x, int n, float* out)
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------
-// Scheduling-policy model of probe_update_wavefront (profiles/policy_sim.py): the kernel's
-// warp loop re-enacted on the host with the same per-lane state functions, `n_warps` warps
-// advanced in order of their accumulated cost (so the dynamic ray fetch behaves as on the
-// device), counting how often each state's code runs and with how many lanes.  Not a test:
-// a tool for comparing scheduling rules without a GPU.
-//   policy 0: the kernel's rule (march while >= march_min/32 of the live lanes march, else the
-//             fullest other state, ties to the later stage)
-//   policy 1: always the fullest state, MARCH counted like any other (ties: march)
-//   policy 2: as 0, but a non-march state runs only with >= min_other lanes unless no lane marches
-//   policy 3: hysteresis: start marching at >= min_other/32 of the live lanes, keep marching down to march_min/32
-//   policy 4: drain: below the march threshold run the other states until none of them holds
-//             min_other or more lanes (re-ranked after each), only then look at the march count again
+// Scheduling model of probe_update_wavefront (profiles/policy_sim.py): the kernel's warp loop
+// re-enacted on the host with the same per-lane state functions, `n_warps` warps advanced in
+// order of their accumulated cost (so the dynamic ray fetch behaves as on the device), counting
+// how often each piece of code is issued and with how many lanes.  Not a test: a tool for
+// comparing scheduling rules without a GPU.
+//   split_hits = 0: the kernel's rule — march while >= march_min/32 of the live lanes can march,
+//                   else the fullest of {HIT, FETCH, MARCH_SLOW}; bounce hits and feeler hits are
+//                   one state whose common code (light test, aim, query) is issued once
+//   split_hits = 1: round 1's rule — bounce hits and feeler hits are separate states, the fullest runs
+//   rays_per_lane K > 1: every lane owns K rays and marches / resolves one of them per issue
+//                   (static multiplexing; `cost[C_SWAP]` is charged when a lane changes the ray it marches)
+// cost[]: warp instructions per issue of each code piece.
+enum { C_MARCH, C_SLOW, C_LIGHT, C_BOUNCE, C_FEELER, C_AIM, C_SCATTER, C_QUERY, C_FETCH, C_ROUND, C_SWAP, C_COUNT };
 struct PolicyOut {
-    uint64_t exec[8];    // executions of each state's code (warp passes)
-    uint64_t lanes[8];   // lanes active over those executions
-    uint64_t passes;     // outer-loop passes (scheduler rounds)
-    double makespan;     // largest accumulated warp cost
-    double busy;         // sum of warp costs
+    uint64_t issues[C_COUNT];  // issues of each code piece
+    uint64_t lanes[C_COUNT];   // lanes active over those issues
+    double makespan;           // largest accumulated warp cost
+    double busy;               // sum of warp costs
 };
-// `group` > 1 models ideal regrouping inside a block of `group` warps: the scheduling unit holds
-// 32 * group rays and a state's code is issued ceil(count / 32) times (moving ray state between
-// lanes is taken as free: an upper bound on what block-level compaction could give).
-template <int kGroup>
-static void wavefront_policy(const SimParams* S, const float* rays, const uint32_t* order, uint32_t n_rays, int n_warps, int policy,
-                             int march_min, int min_other, const double* cost, PolicyOut* out);
 
 extern "C" void sim_wavefront_policy(const SimParams* S, const float* rays, const uint32_t* order, uint32_t n_rays, int n_warps,
-                                     int policy, int march_min, int min_other, const double* cost /* [8] + scheduler */,
-                                     PolicyOut* out, int group)
+                                     int split_hits, int march_min, int rays_per_lane, const double* cost, PolicyOut* out)
 {
-    if (group == 2) wavefront_policy<2>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
-    else if (group == 4) wavefront_policy<4>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
-    else if (group == 8) wavefront_policy<8>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
-    else wavefront_policy<1>(S, rays, order, n_rays, n_warps, policy, march_min, min_other, cost, out);
-}
-
-template <int kGroup>
-static void wavefront_policy(const SimParams* S, const float* rays, const uint32_t* order, uint32_t n_rays, int n_warps, int policy,
-                             int march_min, int min_other, const double* cost, PolicyOut* out)
-{
-    constexpr int kLanes = 32 * kGroup;
+    const int K = rays_per_lane < 1 ? 1 : (rays_per_lane > 4 ? 4 : rays_per_lane);
     Built B;
     build(S, nullptr, &B);
     const FrameParams& P = B.P;
+    struct Lane {
+        WfRay R[4];
+        int cur = 0;  // the ray whose march state the lane holds in registers
+    };
     struct Warp {
-        WfRay R[kLanes];
+        Lane L[32];
         double t = 0;
         bool done = false;
-        bool marching = false;  // policy 3
-        bool draining = false;  // policy 4
     };
     std::vector<Warp> warps((size_t)n_warps);
     for (auto& w : warps)
-        for (int l = 0; l < kLanes; l++) w.R[l].mode = WF_FETCH;
+        for (int l = 0; l < 32; l++)
+            for (int k = 0; k < 4; k++) w.L[l].R[k].mode = k < K ? WF_FETCH : WF_IDLE;
     memset(out, 0, sizeof(*out));
     uint32_t next = 0;
     float stash[3];
     size_t live = (size_t)n_warps;
+    auto issue = [&](Warp* w, int piece, int lanes) {
+        if (lanes <= 0) return;
+        out->issues[piece]++;
+        out->lanes[piece] += (uint64_t)lanes;
+        w->t += cost[piece];
+    };
+    // the ray of lane L in `state` (the current one first), or -1
+    auto pick = [&](Lane& L, int state, bool feeler_only, bool bounce_only) {
+        for (int j = 0; j < K; j++) {
+            int k = (L.cur + j) % K;
+            const WfRay& R = L.R[k];
+            if (R.mode != state) continue;
+            if (state == WF_HIT && feeler_only && R.phase == 0) continue;
+            if (state == WF_HIT && bounce_only && R.phase != 0) continue;
+            return k;
+        }
+        return -1;
+    };
     while (live) {
-        // the warp that is furthest behind runs its next pass
         Warp* w = nullptr;
         for (auto& c : warps)
             if (!c.done && (!w || c.t < w->t)) w = &c;
-        int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int l = 0; l < kLanes; l++) count[w->R[l].mode]++;
-        int n_live = kLanes - count[WF_IDLE];
+        int n_live = 0, n_march = 0, n_hit = 0, n_hit_b = 0, n_hit_f = 0, n_fetch = 0, n_slow = 0;
+        for (int l = 0; l < 32; l++) {
+            Lane& L = w->L[l];
+            bool any = false;
+            for (int k = 0; k < K; k++) any = any || L.R[k].mode != WF_IDLE;
+            n_live += any;
+            n_march += pick(L, WF_MARCH, false, false) >= 0;
+            n_hit += pick(L, WF_HIT, false, false) >= 0;
+            n_hit_b += pick(L, WF_HIT, false, true) >= 0;
+            n_hit_f += pick(L, WF_HIT, true, false) >= 0;
+            n_fetch += pick(L, WF_FETCH, false, false) >= 0;
+            n_slow += pick(L, WF_MARCH_SLOW, false, false) >= 0;
+        }
         if (n_live == 0) {
             w->done = true;
             live--;
             continue;
         }
-        out->passes++;
-        w->t += cost[8];
-        auto run = [&](int state) {
-            const int issues = (count[state] + 31) / 32;
-            out->exec[state] += (uint64_t)issues;
-            out->lanes[state] += (uint64_t)count[state];
-            w->t += cost[state] * issues;
-            // regrouping is not free: moving a ray's state between the pool and a lane's registers
-            // costs `cost[7]` instructions per issue (a quarter of it per march step: a warp keeps
-            // its rays in registers over a run of steps)
-            if (kGroup > 1) w->t += (state == WF_MARCH ? 0.25 : 1.0) * cost[7] * issues;
-            int n_scatter = 0, n_query = 0;
-            for (int l = 0; l < kLanes; l++) {
-                WfRay& R = w->R[l];
-                if (R.mode != state) continue;
-                switch (state) {
-                    case WF_MARCH: wf_step(P, R); break;
-                    case WF_MARCH_SLOW: wf_step_literal(P, R); break;
-                    case WF_BOUNCE_HIT: wf_resolve_bounce<false>(P, R, stash, 1); break;
-                    case WF_FEELER_HIT: wf_resolve_feeler<false>(P, R, stash, 1); break;
-                    case WF_FETCH:
-                        if (next < n_rays) {
-                            uint32_t k = order[next++];
-                            const float* r = rays + 12 * (size_t)k;
-                            wf_init(R, V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), k);
-                        } else {
-                            R.mode = WF_IDLE;
-                        }
-                        break;
+        int enough = (n_live * march_min + 31) >> 5;
+        if (enough < 1) enough = 1;
+        if (n_march >= enough || n_hit + n_fetch + n_slow == 0) {
+            int swaps = 0;
+            for (int l = 0; l < 32; l++) {
+                Lane& L = w->L[l];
+                int k = pick(L, WF_MARCH, false, false);
+                if (k < 0) continue;
+                if (k != L.cur) {
+                    swaps++;
+                    L.cur = k;
                 }
-                // scatter and query are armed in the same pass, as in the kernel
-                if (R.mode == WF_SCATTER) {
-                    wf_scatter(P, R);
-                    n_scatter++;
-                }
-                if (R.mode == WF_QUERY) {
-                    wf_begin_query(P, R);
-                    n_query++;
-                }
+                wf_step(P, L.R[k]);
+                wf_end_march(L.R[k]);
             }
-            if (n_scatter) {
-                out->exec[WF_SCATTER] += (uint64_t)((n_scatter + 31) / 32);
-                out->lanes[WF_SCATTER] += (uint64_t)n_scatter;
-                w->t += cost[WF_SCATTER] * ((n_scatter + 31) / 32);
+            issue(w, C_SWAP, swaps);
+            issue(w, C_MARCH, n_march);
+            continue;
+        }
+        issue(w, C_ROUND, 32);
+        int n_scatter = 0, n_query = 0, n_aim = 0;
+        auto after = [&](WfRay& R) {
+            if (R.mode == WF_SCATTER) {
+                wf_scatter(P, R);
+                n_scatter++;
             }
-            if (n_query) {
-                out->exec[WF_QUERY] += (uint64_t)((n_query + 31) / 32);
-                out->lanes[WF_QUERY] += (uint64_t)n_query;
-                w->t += cost[WF_QUERY] * ((n_query + 31) / 32);
+            if (R.mode == WF_QUERY) {
+                wf_begin_query(P, R);
+                n_query++;
             }
         };
-        auto fullest_other = [&]() {
-            int best = -1, bc = 0;
-            for (int s : {WF_BOUNCE_HIT, WF_FEELER_HIT, WF_FETCH, WF_MARCH_SLOW})
-                if (count[s] > bc || (count[s] == bc && bc > 0 && s > best)) {
-                    best = s;
-                    bc = count[s];
-                }
-            return best;
+        auto run_hits = [&](bool feeler_only, bool bounce_only) {
+            int nl = 0, nb = 0, nf = 0;
+            for (int l = 0; l < 32; l++) {
+                Lane& L = w->L[l];
+                int k = pick(L, WF_HIT, feeler_only, bounce_only);
+                if (k < 0) continue;
+                WfRay& R = L.R[k];
+                nl++;
+                (R.phase == 0 ? nb : nf)++;
+                wf_resolve_hit<false>(P, R, stash, 1);
+                if (R.mode == WF_QUERY) n_aim++;
+                after(R);
+            }
+            issue(w, C_LIGHT, nl);
+            issue(w, C_BOUNCE, nb);
+            issue(w, C_FEELER, nf);
         };
-        if (policy == 1) {
-            int o = fullest_other();
-            if (count[WF_MARCH] > 0 && (o < 0 || count[WF_MARCH] >= count[o])) run(WF_MARCH);
-            else if (o >= 0) run(o);
-            continue;
-        }
-        if (policy == 3) {
-            int lo = n_live * march_min > 32 ? n_live * march_min : 32, hi = n_live * min_other > 32 ? n_live * min_other : 32;
-            int m32 = count[WF_MARCH] * 32;
-            if (w->marching ? m32 >= lo : m32 >= hi) {
-                w->marching = true;
-                run(WF_MARCH);
-                w->t -= cost[8];
-                out->passes--;
-                continue;
+        if (n_slow > n_hit && n_slow > n_fetch) {
+            for (int l = 0; l < 32; l++) {
+                int k = pick(w->L[l], WF_MARCH_SLOW, false, false);
+                if (k >= 0) {
+                    wf_step_literal(P, w->L[l].R[k]);
+                    wf_end_march(w->L[l].R[k]);
+                }
             }
-            w->marching = false;
-            int o = fullest_other();
-            if (o >= 0) run(o);
-            else if (count[WF_MARCH] > 0) run(WF_MARCH);
-            continue;
-        }
-        if (policy == 4 && w->draining) {
-            int o = fullest_other();
-            if (o >= 0 && count[o] >= min_other) {
-                run(o);
-                continue;
+            issue(w, C_SLOW, n_slow);
+        } else if (!split_hits ? n_hit > n_fetch : (n_hit_b > n_fetch || n_hit_f > n_fetch)) {
+            if (!split_hits) run_hits(false, false);
+            else if (n_hit_f >= n_hit_b) run_hits(true, false);
+            else run_hits(false, true);
+        } else {
+            for (int l = 0; l < 32; l++) {
+                Lane& L = w->L[l];
+                int k = pick(L, WF_FETCH, false, false);
+                if (k < 0) continue;
+                WfRay& R = L.R[k];
+                if (next < n_rays) {
+                    uint32_t kk = order[next++];
+                    const float* r = rays + 12 * (size_t)kk;
+                    wf_init(R, V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), kk);
+                    after(R);
+                } else {
+                    R.mode = WF_IDLE;
+                }
             }
-            w->draining = false;
+            issue(w, C_FETCH, n_fetch);
         }
-        const int enough = n_live * march_min > 32 ? n_live * march_min : 32;  // march_min/32 of the live lanes
-        if (count[WF_MARCH] * 32 >= enough) {
-            run(WF_MARCH);  // (one step per pass here; the kernel's inner loop re-checks the same condition)
-            w->t -= cost[8];  // the inner march loop does not pay a scheduler round
-            out->passes--;
-            continue;
-        }
-        int o = fullest_other();
-        if (o < 0 || (policy == 2 && count[o] < min_other && count[WF_MARCH] > 0)) {
-            if (count[WF_MARCH] > 0) run(WF_MARCH);
-            continue;
-        }
-        if (policy == 4) w->draining = true;
-        run(o);
+        issue(w, C_AIM, n_aim);
+        issue(w, C_SCATTER, n_scatter);
+        issue(w, C_QUERY, n_query);
     }
     for (auto& c : warps) {
         out->busy += c.t;
@@ -491,9 +447,9 @@ extern "C" void sim_ray_profile(const SimParams* S, const float* rays, uint32_t 
             switch (R.mode) {
                 case WF_MARCH: wf_step(P, R); break;
                 case WF_MARCH_SLOW: wf_step_literal(P, R); break;
+                case WF_LIMIT: wf_end_march(R); break;
                 case WF_QUERY: wf_begin_query(P, R); q++; break;
-                case WF_BOUNCE_HIT: wf_resolve_bounce<false>(P, R, stash, 1); b++; break;
-                case WF_FEELER_HIT: wf_resolve_feeler<false>(P, R, stash, 1); f++; break;
+                case WF_HIT: (R.phase == 0 ? b : f)++; wf_resolve_hit<false>(P, R, stash, 1); break;
                 default: wf_scatter(P, R); break;
             }
         }
@@ -502,213 +458,4 @@ extern "C" void sim_ray_profile(const SimParams* S, const float* rays, uint32_t 
         counts[4 * k + 2] = b;
         counts[4 * k + 3] = f;
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// Host re-enactment of probe_update_pooled's BLOCK logic (ddgi_kernels.cu) — queues, claims,
-// march sessions, fetch / retire accounting — with the block's warps taking turns.  It cannot show
-// races, but a slot that is lost or a pool that never drains shows up here, not as a hung GPU.
-// Writes the same texels as sim_probe_update; returns the number of loop passes (0 = did not end).
-// stats (optional, 16 values): [q] issues per queue, [5 + q] lanes over those issues, [10] march iterations,
-// [11] lanes over march iterations, [12] passes that found no work.
-// pool_slots: ray slots per block (the kernel has 128 = one per thread); lockstep != 0: the block's
-// warps all claim before any of them appends (every warp is always holding the rays it works on, as
-// on the device) instead of taking turns.
-extern "C" uint64_t sim_probe_update_pooled_stats(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
-                                                  uint32_t* albedo, uint32_t* lookups_out, uint64_t* stats, int pool_slots, int lockstep);
-extern "C" uint64_t sim_probe_update_pooled(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
-                                            uint32_t* albedo, uint32_t* lookups_out)
-{
-    return sim_probe_update_pooled_stats(S, rays, n_rays, n_blocks, march_keep, albedo, lookups_out, nullptr, 128, 0);
-}
-extern "C" uint64_t sim_probe_update_pooled_stats(const SimParams* S, const float* rays, uint32_t n_rays, int n_blocks, int march_keep,
-                                                  uint32_t* albedo, uint32_t* lookups_out, uint64_t* stats, int pool_slots, int lockstep)
-{
-    uint64_t local_stats[16] = {0};
-    if (!stats) stats = local_stats;
-    Built B;
-    build(S, nullptr, &B);
-    const FrameParams& P = B.P;
-    const int W = P.probe_count[0] * P.probe_count[2] * P.rx;
-    const int tiles_x = P.probe_count[0] * P.probe_count[2];
-    constexpr int WARPS = 4;
-    const int N = pool_slots;
-    struct Block {
-        std::vector<PoolVec> ray;        // N x kPoolVecs
-        std::vector<int> queue[PQ_COUNT];  // rings of N
-        unsigned head[PQ_COUNT] = {0, 0, 0, 0, 0}, tail[PQ_COUNT] = {0, 0, 0, 0, 0};
-        int live = 0;
-        bool warp_done[WARPS] = {false, false, false, false};
-    };
-    std::vector<Block> blocks((size_t)n_blocks);
-    for (auto& b : blocks) {
-        b.ray.assign((size_t)N * kPoolVecs, PoolVec{0, 0, 0, 0});
-        for (int qi = 0; qi < PQ_COUNT; qi++) b.queue[qi].assign((size_t)N, 0);
-        for (int i = 0; i < N; i++) {
-            b.queue[PQ_FETCH][i] = i;
-            b.ray[(size_t)i * kPoolVecs + 6].w = pool_bits_f(0xffffffffu);
-        }
-        b.tail[PQ_FETCH] = (unsigned)N;
-        b.live = N;
-    }
-    uint32_t next = 0;
-    uint64_t passes = 0;
-    float stash[3] = {0, 0, 0};
-    size_t running = (size_t)n_blocks * WARPS;
-    const uint64_t limit = 64ull * (uint64_t)n_rays * 400ull / 32ull + 100000ull;
-    struct Claim {
-        int q = -1;
-        unsigned n = 0;
-        int slots[32];
-    };
-    auto claim = [&](Block& b, Claim& c) {
-        unsigned bestc = 0;
-        c.q = -1;
-        const int order[PQ_COUNT] = {PQ_MARCH, PQ_FETCH, PQ_FEELER, PQ_BOUNCE, PQ_SLOW};
-        for (int qi : order) {
-            unsigned cnt = b.tail[qi] - b.head[qi];
-            unsigned cc = cnt < 32u ? cnt : 32u;
-            if (cc > bestc) {
-                bestc = cc;
-                c.q = qi;
-            }
-        }
-        if (c.q < 0) return;
-        unsigned old = b.head[c.q];
-        c.n = bestc;
-        b.head[c.q] += c.n;
-        for (unsigned l = 0; l < c.n; l++) c.slots[l] = b.queue[c.q][(old + l) % (unsigned)N];
-        stats[c.q]++;
-        stats[5 + c.q] += c.n;
-    };
-    auto work = [&](Block& b, const Claim& c) {
-        const int q = c.q;
-        const unsigned n = c.n;
-        int newq[32];
-        bool push[32];
-        auto rec = [&](unsigned l) { return &b.ray[(size_t)c.slots[l] * kPoolVecs]; };
-        if (q == PQ_MARCH || q == PQ_SLOW) {
-            const int run_mode = q == PQ_MARCH ? WF_MARCH : WF_MARCH_SLOW;
-            WfRay R[32];
-            for (unsigned l = 0; l < n; l++) {
-                memset(&R[l], 0xFF, sizeof(WfRay));
-                pool_unpack_march(rec(l), R[l]);
-                R[l].mode = run_mode;
-            }
-            unsigned active;
-            do {
-                active = 0;
-                stats[10]++;
-                for (unsigned l = 0; l < n; l++) {
-                    if (R[l].mode == run_mode) {
-                        stats[11]++;
-                        if (q == PQ_MARCH) wf_step(P, R[l]);
-                        else wf_step_literal(P, R[l]);
-                    }
-                    active += R[l].mode == run_mode;
-                }
-            } while (active && active * 32u >= n * (unsigned)march_keep);
-            for (unsigned l = 0; l < n; l++) {
-                pool_pack_march(R[l], rec(l));
-                newq[l] = pool_queue_of(R[l].mode);
-                push[l] = true;
-            }
-        } else if (q == PQ_FETCH) {
-            uint32_t base = next;
-            next += n;
-            for (unsigned l = 0; l < n; l++) {
-                PoolVec* r = rec(l);
-                uint32_t k = pool_f_bits(r[6].w);
-                if (k != 0xffffffffu) {
-                    const float* ry = rays + 12 * (size_t)k;
-                    int p = f2i(ry[8]);
-                    int yp = p / tiles_x, xp = p - yp * tiles_x;
-                    size_t t = (size_t)(yp * P.ry + f2i(ry[10])) * W + (xp * P.rx + f2i(ry[9]));
-                    albedo[t] = pack_rgba8(r[8].x, r[8].y, r[8].z, 1.0f);
-                    if (lookups_out) lookups_out[k] = pool_f_bits(r[2].w);
-                }
-                uint32_t idx = base + l;
-                push[l] = idx < n_rays;
-                newq[l] = PQ_FETCH;
-                if (push[l]) {
-                    const float* ry = rays + 12 * (size_t)idx;
-                    WfRay R;
-                    memset(&R, 0xFF, sizeof(R));
-                    wf_init(R, V3(ry[0], ry[1], ry[2]), V3(ry[4], ry[5], ry[6]), idx);
-                    wf_begin_query(P, R);
-                    pool_pack(R, idx, 0.0f, r);
-                    newq[l] = pool_queue_of(R.mode);
-                } else {
-                    r[6].w = pool_bits_f(0xffffffffu);
-                    b.live--;
-                }
-            }
-        } else {
-            for (unsigned l = 0; l < n; l++) {
-                PoolVec* r = rec(l);
-                WfRay R;
-                memset(&R, 0xFF, sizeof(R));
-                uint32_t k;
-                float first_t;
-                pool_unpack(r, R, k, first_t);
-                R.mode = q == PQ_BOUNCE ? WF_BOUNCE_HIT : WF_FEELER_HIT;
-                if (q == PQ_BOUNCE) {
-                    bool first = R.bounce == 0;
-                    float nearest = 0.0f;
-                    wf_resolve_bounce<false>(P, R, stash, 1, &nearest);
-                    if (first) first_t = nearest;
-                } else {
-                    wf_resolve_feeler<false>(P, R, stash, 1);
-                }
-                if (R.mode == WF_SCATTER) wf_scatter(P, R);
-                if (R.mode == WF_QUERY) wf_begin_query(P, R);
-                pool_pack(R, k, first_t, r);
-                newq[l] = pool_queue_of(R.mode);
-                push[l] = true;
-            }
-        }
-        for (unsigned l = 0; l < n; l++)
-            if (push[l]) {
-                int qi = newq[l];
-                b.queue[qi][b.tail[qi] % (unsigned)N] = c.slots[l];
-                b.tail[qi]++;
-            }
-    };
-    size_t turn = 0;
-    while (running) {
-        if (++passes > limit) return 0;
-        Block& b = blocks[turn++ % blocks.size()];
-        Claim claims[WARPS];
-        if (lockstep) {
-            for (int w = 0; w < WARPS; w++)
-                if (!b.warp_done[w]) claim(b, claims[w]);
-            for (int w = 0; w < WARPS; w++) {
-                if (b.warp_done[w]) continue;
-                if (claims[w].q >= 0) work(b, claims[w]);
-            }
-            for (int w = 0; w < WARPS; w++) {
-                if (b.warp_done[w] || claims[w].q >= 0) continue;
-                if (b.live <= 0) {
-                    b.warp_done[w] = true;
-                    running--;
-                } else {
-                    stats[12]++;
-                }
-            }
-        } else {
-            for (int w = 0; w < WARPS; w++) {
-                if (b.warp_done[w]) continue;
-                claim(b, claims[w]);
-                if (claims[w].q >= 0) {
-                    work(b, claims[w]);
-                } else if (b.live <= 0) {
-                    b.warp_done[w] = true;
-                    running--;
-                } else {
-                    stats[12]++;
-                }
-            }
-        }
-    }
-    return passes;
 }

@@ -115,7 +115,7 @@ def test_engine_headers_edge_cases(case):
         f32 = np.zeros_like(want[2])
         lk = np.zeros_like(want[3])
         hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data, None)
-        assert np.array_equal(lk, want[3]), f"{case}: lookup counts, variant {variant}"
+        util.assert_lookups(lk, want[3], variant, case)
         assert np.array_equal(f32.view(np.uint32), want[2].view(np.uint32)), f"{case}: fp32 texels, variant {variant}"
         assert np.array_equal(alb, want[0])
     # pixel pass: looking at the lights (emissive pixels) through the same scene
@@ -142,12 +142,12 @@ def test_cuda_edge_cases(case):
         r.render_settings.max_bounces = bounces
         r.lights = [capi.Light(l.intensity, tuple(l.col), tuple(l.pos)) for l in lights]
         r.generate_probe_rays(reseed=True)
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             r.set_kernel_variant(variant)
             r.update(advance_time=False)
             r.draw()
             r.sync()
-            assert np.array_equal(r.read_lookup_counts(0), want[3]), f"{case}: lookup counts, variant {variant}"
+            util.assert_lookups(r.read_lookup_counts(0), want[3], variant, case)
             assert np.array_equal(r.read_probe_texture(0, capi.FMT_F32).view(np.uint32), want[2].view(np.uint32))
             assert np.array_equal(r.read_probe_texture(0), want[0])
             assert np.array_equal(r.read_frame(capi.FMT_F32).view(np.uint32), f[1].view(np.uint32))

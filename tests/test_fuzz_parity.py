@@ -76,7 +76,7 @@ def test_engine_headers_on_random_scenes(seed):
         for _ in range(2):
             hs.sim_probe_update(C.byref(sc.p), rays.ctypes.data, 0, sc.num_rays, variant, alb.ctypes.data, f32.ctypes.data, lk.ctypes.data,
                                 dist.ctypes.data)
-        assert np.array_equal(lk, want[3]), f"seed {seed} variant {variant}: lookup counts"
+        util.assert_lookups(lk, want[3], variant, f"seed {seed}")
         assert np.array_equal(f32.view(np.uint32), want[2].view(np.uint32)), f"seed {seed} variant {variant}: fp32 texels"
         assert np.array_equal(alb, want[0]) and np.array_equal(dist, want[1])
     w, h = c["screen"]
@@ -128,14 +128,14 @@ def test_cuda_engine_on_random_scenes(seed):
                 return c["cam"]
 
         r.scene_camera = FixedCamera()
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             r.set_kernel_variant(variant)
             r.update(advance_time=False)
             r.write_probe_texture(np.zeros((H, W), dtype=np.uint32), 0)
             r.probe_update()
             r.draw()
             r.sync()
-            assert np.array_equal(r.read_lookup_counts(0), want[3]), f"seed {seed} variant {variant}: lookup counts"
+            util.assert_lookups(r.read_lookup_counts(0), want[3], variant, f"seed {seed}")
             assert np.array_equal(r.read_probe_texture(0, capi.FMT_F32).view(np.uint32), want[2].view(np.uint32))
             assert np.array_equal(r.read_probe_texture(0), want[0]) and np.array_equal(r.read_probe_texture(1), want[1])
             assert np.array_equal(r.read_lookup_counts(1).reshape(h, w), frame[2])

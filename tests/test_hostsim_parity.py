@@ -35,7 +35,7 @@ def test_probe_update_headers_match_oracle(name, variant):
     k0, k1 = (0, sc.num_rays) if sc.num_rays <= 4096 else (sc.num_rays // 2 - 16384, sc.num_rays // 2 + 16384)
     want = oracle.probe_update(sc, rays, k0, k1)
     alb, f32, lk = _sim_probe_update(sc, rays, variant, k0, k1)
-    assert np.array_equal(lk[k0:k1], want[3][k0:k1]), "voxel lookup counts differ"
+    util.assert_lookups(lk[k0:k1], want[3][k0:k1], variant, name)
     assert np.array_equal(f32.view(np.uint32), want[2].view(np.uint32))
     assert np.array_equal(alb, want[0])
 
@@ -61,7 +61,7 @@ def test_wavefront_on_axis_parallel_and_degenerate_rays():
         want = oracle.probe_update(sc, rays, 0, n)
         for variant in (0, 1, 2):
             alb, f32, lk = _sim_probe_update(sc, rays, variant, 0, n)
-            assert np.array_equal(lk[:n], want[3][:n])
+            util.assert_lookups(lk[:n], want[3][:n], variant)
             assert np.array_equal(f32.view(np.uint32), want[2].view(np.uint32))
             assert np.array_equal(alb, want[0])
 
@@ -92,9 +92,9 @@ def test_literal_colour_mode_matches_oracle_on_the_textured_cave():
     sc = oracle.Scene(probe_count=(3, 3, 3), side_length=7, field_origin=(0.0, 0.0, 0.0), rx=8, lights=oracle.default_lights(0),
                       scene=0, voxels=vox, vorg=(-64, -64, -64), literal_colors=True, screen=tuple(int(v) for v in g["screen"]))
     rays = g["rays"]
-    for variant in (0, 1):   # (variant 2 carries no procedural-colour stash: the engine runs variant 1 for it)
+    for variant in (0, 1, 2):
         alb, f32, lk = _sim_probe_update(sc, rays, variant)
-        assert np.array_equal(lk, g["lookups"])
+        util.assert_lookups(lk, g["lookups"], variant)
         assert np.array_equal(f32.view(np.uint32), g["albedo_f32"].view(np.uint32))
         assert np.array_equal(alb, g["albedo"])
     hs = util.hostsim()

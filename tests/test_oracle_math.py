@@ -106,3 +106,65 @@ def test_hemisphere_direction_is_unit_and_above_the_surface():
             lib.orc_hemisphere(nn.ctypes.data, seed, d.ctypes.data)
             assert abs(np.linalg.norm(d) - 1) < 1e-5
             assert np.dot(d, nn) >= -1e-6
+
+
+def test_integer_range_checks_equal_their_float_definitions():
+    """ddgi_fastmath.cuh: regular_component / regular_origin as unsigned compares of the bit patterns, and
+    their three-component forms, against the float comparisons they replace - on every exponent boundary,
+    zeros, denormals, Inf, NaN and 2^22 random bit patterns."""
+    import ctypes as C
+    import util
+    rng = np.random.default_rng(7)
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, 2.0 ** -70, np.nextafter(np.float32(2.0 ** -70), np.float32(0)), 2.0 ** -60,
+                        np.nextafter(np.float32(2.0 ** -60), np.float32(0)), 2.0, np.nextafter(np.float32(2.0), np.float32(3)), 2.0 ** 20,
+                        np.nextafter(np.float32(2.0 ** 20), np.float32(0)), np.inf, -np.inf, np.nan, 1.0, -1.0, 0.5, 3e38, -3e38], dtype=np.float32)
+    bits = rng.integers(0, 2 ** 32, size=3 * (1 << 21), dtype=np.uint64).astype(np.uint32)
+    x = np.concatenate([special, -special, bits.view(np.float32)])
+    x = np.ascontiguousarray(x[: (x.size // 3) * 3])
+    n = x.size
+    comp, org = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+    dir3, org3 = np.zeros(n // 3, dtype=np.uint8), np.zeros(n // 3, dtype=np.uint8)
+    hs = util.hostsim()
+    hs.sim_regular_checks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    hs.sim_regular_checks(x.ctypes.data, n, comp.ctypes.data, org.ctypes.data, dir3.ctypes.data, org3.ctypes.data)
+    with np.errstate(invalid="ignore"):
+        ax = np.abs(x)
+        want_comp = (ax >= np.float32(8.6736174e-19)) & (ax <= np.float32(2.0))
+        want_org = (ax == 0) | ((ax >= np.float32(8.4703295e-22)) & (ax < np.float32(1048576.0)))
+    assert np.array_equal(comp.astype(bool), want_comp)
+    assert np.array_equal(org.astype(bool), want_org)
+    assert np.array_equal(dir3.astype(bool), want_comp.reshape(-1, 3).all(axis=1))
+    assert np.array_equal(org3.astype(bool), want_org.reshape(-1, 3).all(axis=1))
+
+
+def test_face_normal_shortcut_equals_the_literal_normal():
+    """ddgi_trace.cuh: face_normal_axis (no normalize() when one component of p - cell centre is the clear
+    winner) against face_normal_unit on hit-like points (on a face, 1e-4 inside), exact edges and corners
+    (ties), near ties a few ulp apart, and degenerate inputs."""
+    import ctypes as C
+    import util
+    rng = np.random.default_rng(11)
+    n = 400000
+    cell = rng.integers(-200, 200, size=(n, 3)).astype(np.float32)
+    p = cell - rng.random((n, 3)).astype(np.float32)
+    axis = rng.integers(0, 3, size=n)
+    side = rng.integers(0, 2, size=n)
+    idx = np.arange(n)
+    p[idx, axis] = cell[idx, axis] - side.astype(np.float32) - np.where(side == 1, np.float32(-1e-4), np.float32(1e-4))   # just inside a face
+    # ties and near ties: copy one coordinate's offset onto another, then nudge by 0..3 ulp
+    t = slice(0, n // 4)
+    off = p[t, 0] - (cell[t, 0] - np.float32(0.5))
+    sign = np.where(rng.integers(0, 2, size=off.size) == 1, np.float32(1), np.float32(-1))
+    p[t, 1] = (cell[t, 1] - np.float32(0.5)) + sign * off
+    for k in range(3):
+        sel = slice(k * (n // 16), (k + 1) * (n // 16))
+        for _ in range(k + 1):
+            p[sel, 1] = np.nextafter(p[sel, 1], np.float32(1e9))
+    p[-6:] = [[np.nan, 0, 0], [np.inf, 1, 1], [0, 0, 0], [1e30, 1e30, 1e30], [0.5, 0.5, 0.5], [-0.5, -0.5, -0.5]]
+    cell[-2:] = [[1, 1, 1], [0, 0, 0]]   # p exactly the cell centre: the zero vector
+    p, cell = np.ascontiguousarray(p), np.ascontiguousarray(cell)
+    fast, lit = np.zeros((n, 3), dtype=np.float32), np.zeros((n, 3), dtype=np.float32)
+    hs = util.hostsim()
+    hs.sim_face_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    hs.sim_face_normals(p.ctypes.data, cell.ctypes.data, n, fast.ctypes.data, lit.ctypes.data)
+    assert np.array_equal(fast.view(np.uint32), lit.view(np.uint32))

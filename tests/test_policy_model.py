@@ -1,7 +1,6 @@
-"""The scheduling-policy model behind profiles/r1_policy_model.md (tests/hostsim: sim_wavefront_policy,
-sim_probe_update_pooled_stats) — a design tool, kept honest by two cheap checks: every rule processes every
-ray exactly once (executions and lanes add up), and the pooled block logic ends with the right texture for
-pool sizes other than the kernel's."""
+"""The scheduling model behind profiles/policy_sim.py (tests/hostsim: sim_wavefront_policy) — a design
+tool, kept honest by one cheap check: every rule traces every ray to the end exactly once (march steps =
+voxel lookups, one resolve per query), whatever the rule, the threshold or the number of rays per lane."""
 import ctypes as C
 
 import numpy as np
@@ -9,52 +8,34 @@ import numpy as np
 import util
 from oracle import oracle
 
+PIECES = ["MARCH", "SLOW", "LIGHT", "BOUNCE", "FEELER", "AIM", "SCATTER", "QUERY", "FETCH", "ROUND", "SWAP"]
+
 
 class PolicyOut(C.Structure):
-    _fields_ = [("exec", C.c_uint64 * 8), ("lanes", C.c_uint64 * 8), ("passes", C.c_uint64), ("makespan", C.c_double), ("busy", C.c_double)]
-
-
-def _scene():
-    cfg = util.configs.CONFIGS["cornell_3x3x3"]
-    sc = util.oracle_scene(cfg)
-    rays = np.ascontiguousarray(oracle.generate_probe_rays(sc, oracle.generate_samples(8, 8, reseed=True)))
-    return sc, rays
+    _fields_ = [("issues", C.c_uint64 * 11), ("lanes", C.c_uint64 * 11), ("makespan", C.c_double), ("busy", C.c_double)]
 
 
 def test_every_rule_resolves_every_query_once():
-    sc, rays = _scene()
+    cfg = util.configs.CONFIGS["cornell_3x3x3"]
+    sc = util.oracle_scene(cfg)
+    rays = np.ascontiguousarray(oracle.generate_probe_rays(sc, oracle.generate_samples(8, 8, reseed=True)))
     n = rays.shape[0]
     want = oracle.probe_update(sc, rays)
     hs = util.hostsim()
     hs.sim_wavefront_policy.argtypes = [C.POINTER(oracle.OrcParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.c_void_p, C.POINTER(PolicyOut), C.c_int]
+                                        C.c_void_p, C.POINTER(PolicyOut)]
     order = np.arange(n, dtype=np.uint32)
-    cost = np.ones(9, dtype=np.float64)
-    lanes_ref = None
-    for policy, mm, mo, group in ((0, 16, 0, 1), (0, 8, 0, 1), (1, 16, 0, 1), (2, 16, 8, 1), (3, 12, 20, 1), (4, 16, 4, 1), (0, 12, 0, 4)):
+    cost = np.ones(11, dtype=np.float64)
+    ref = None
+    for split, mm, k in ((1, 16, 1), (0, 16, 1), (0, 8, 1), (1, 24, 1), (0, 16, 2), (1, 28, 3)):
         out = PolicyOut()
-        hs.sim_wavefront_policy(C.byref(sc.p), rays.ctypes.data, order.ctypes.data, n, 4, policy, mm, mo, cost.ctypes.data, C.byref(out), group)
-        lanes = list(out.lanes)
-        # lane-executions are a property of the rays, not of the rule: steps = lookups, one fetch per ray (+ the final empty ones)
-        assert lanes[0] + lanes[6] == int(want[3].sum()), (policy, lanes)
-        if lanes_ref is None:
-            lanes_ref = lanes
-        assert lanes[1:5] == lanes_ref[1:5], "queries / resolves / scatters per ray do not depend on the rule"
+        hs.sim_wavefront_policy(C.byref(sc.p), rays.ctypes.data, order.ctypes.data, n, 4, split, mm, k, cost.ctypes.data, C.byref(out))
+        lanes = dict(zip(PIECES, out.lanes))
+        # lane-executions are a property of the rays, not of the rule
+        assert lanes["MARCH"] + lanes["SLOW"] == int(want[3].sum()), (split, mm, k, lanes)
+        assert lanes["LIGHT"] == lanes["BOUNCE"] + lanes["FEELER"]
+        assert lanes["QUERY"] == lanes["LIGHT"], "one resolve per query"
+        per_ray = (lanes["BOUNCE"], lanes["FEELER"], lanes["AIM"], lanes["SCATTER"], lanes["QUERY"])
+        ref = ref or per_ray
+        assert per_ray == ref, "queries / resolves / scatters per ray do not depend on the rule"
         assert out.busy > 0 and out.makespan * 4 >= out.busy
-
-
-def test_pooled_block_logic_for_other_pool_sizes():
-    sc, rays = _scene()
-    want = oracle.probe_update(sc, rays)
-    hs = util.hostsim()
-    hs.sim_probe_update_pooled_stats.restype = C.c_uint64
-    hs.sim_probe_update_pooled_stats.argtypes = [C.POINTER(oracle.OrcParams), C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                                 C.c_void_p, C.c_int, C.c_int]
-    for slots, lockstep, keep in ((128, 0, 16), (128, 1, 24), (256, 1, 16), (64, 1, 8), (33, 1, 16)):
-        alb, lk = np.zeros_like(want[0]), np.zeros_like(want[3])
-        st = np.zeros(16, dtype=np.uint64)
-        passes = hs.sim_probe_update_pooled_stats(C.byref(sc.p), rays.ctypes.data, rays.shape[0], 3, keep, alb.ctypes.data, lk.ctypes.data,
-                                                  st.ctypes.data, slots, lockstep)
-        assert passes > 0, "the pool did not drain"
-        assert np.array_equal(alb, want[0]) and np.array_equal(lk, want[3]), (slots, lockstep, keep)
-        assert int(st[11]) == int(want[3].sum())   # march lane-steps = voxel lookups

@@ -110,3 +110,15 @@ def small(cfg, **over):
     c = dict(cfg)
     c.update(over)
     return c
+
+
+def assert_lookups(got, want, variant, what=""):
+    """Per-ray voxel-lookup counts against the reference algorithm's (oracle / reference shaders).
+    Variants 0 and 1 perform exactly the reference's lookups (a different count = a different discrete
+    path); variant 2 ends shadow-feeler marches behind their light (result-preserving early-out,
+    csrc/ddgi_wavefront.cuh), so it may only ever perform fewer."""
+    got, want = np.asarray(got), np.asarray(want)
+    if variant == 2:
+        assert (got <= want).all(), f"{what}: the early-out variant performed MORE lookups than the reference algorithm"
+    else:
+        assert np.array_equal(got, want), f"{what}: voxel lookup counts differ: a ray took another discrete path"
