@@ -29,12 +29,14 @@ def workload_config(name: str) -> dict:
     return configs.CONFIGS[name]
 
 
-def _sample_rows(cfg):
-    """Middle probe rows (the representative part of the field): Y/8 rows, at least 1."""
+def _sample_rows(cfg, n_rows=None):
+    """Probe rows the CPU legs trace: every (Y/4)-th row starting at 3/8 of that stride, i.e. spread over
+    the whole field so that the sample's voxel lookups per ray are close to the field's mean (field_32:
+    rows 3, 11, 19, 27 -> 104.9 lookups/ray against 106.4 for all 32 rows; the middle rows alone have 170)."""
     Y = cfg["probe_count"][1]
-    n = max(1, Y // 8)
-    y0 = Y // 2 - n // 2
-    return y0, y0 + n
+    n = max(1, min(Y, n_rows if n_rows else 4))
+    stride = Y / float(n)
+    return sorted({min(Y - 1, int(stride * i + 0.375 * stride)) for i in range(n)})
 
 
 def _oracle_scene(cfg, voxels, time_value):
@@ -44,32 +46,51 @@ def _oracle_scene(cfg, voxels, time_value):
     return util.oracle_scene(cfg, time=time_value, voxels=voxels)
 
 
-def _time_oracle(cfg, voxels, steps, warmup, time0=0.0):
+def host_threads():
+    """All host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _time_oracle(cfg, voxels, steps, warmup, time0=0.0, budget_s=200.0):
+    """The oracle (OpenMP, `host_threads()` threads set explicitly) over the sample rows, `warmup` untimed +
+    `steps` timed passes with the lights moving as in the GPU arm.  If the first pass says the whole run would
+    exceed `budget_s`, the sample shrinks to 2 rows, then 1 (the steps stay the GPU arm's)."""
     from oracle import oracle
 
     rx, ry = cfg["tile"]
     X, Y, Z = cfg["probe_count"]
     sc = _oracle_scene(cfg, voxels, time0)
     rays = oracle.generate_probe_rays(sc, oracle.generate_samples(rx, ry, reseed=True))
-    y0, y1 = _sample_rows(cfg)
     per_row = X * Z * rx * ry
-    k0, k1 = y0 * per_row, y1 * per_row
-    threads = oracle.load().orc_num_threads()
+    threads = host_threads()
     W, H = sc.tex_size
     tex = np.zeros((H, W), dtype=np.uint32)
-    times = []
-    lookups = None
+    rows = _sample_rows(cfg)
+
+    def one_pass(sc, rows):
+        t0 = time.perf_counter()
+        total, n = 0.0, 0
+        for y in rows:
+            _, _, _, st, _ = oracle.probe_update(sc, rays, y * per_row, (y + 1) * per_row, threads=threads, tex=tex)
+            total += float(st[y * per_row:(y + 1) * per_row].sum(dtype=np.float64))
+            n += per_row
+        return time.perf_counter() - t0, total / n
+
+    times, traced, lookups = [], [], None
     for i in range(warmup + steps):
         sc = _oracle_scene(cfg, sc.vox, time0 + 2.0 * (i + 1))
-        t0 = time.perf_counter()
-        _, _, _, st, _ = oracle.probe_update(sc, rays, k0, k1, threads=0, tex=tex)
-        dt = time.perf_counter() - t0
+        dt, lookups = one_pass(sc, rows)
         if i >= warmup:
             times.append(dt)
-        lookups = st[k0:k1]
-    n = k1 - k0
-    return {"rays": n, "seconds": float(np.mean(times)), "threads": threads, "rows": (y0, y1),
-            "mean_lookups": float(lookups.mean()), "tex": tex, "k": (k0, k1)}
+            traced.append(len(rows) * per_row)
+        if i == 0 and dt * (warmup + steps) > budget_s and len(rows) > 1:
+            rows = _sample_rows(cfg, 2 if dt * (warmup + steps) / 2 <= budget_s else 1)
+    # (rays and seconds per step, averaged over the timed steps)
+    return {"rays": float(np.mean(traced)), "seconds": float(np.mean(times)), "threads": threads, "rows": rows,
+            "mean_lookups": lookups, "tex": tex}
 
 
 def _reference_shaders_available(cfg):
@@ -113,11 +134,11 @@ def cpu_baseline(rvpt, cfg, name):
                 "mean_lookups_per_ray_in_sample": res["mean_lookups"]}
     X, Y, Z = cfg["probe_count"]
     vox = rvpt.read_voxels(cfg["voxels"][1])
-    res = _time_oracle(cfg, vox, steps=2, warmup=1)
-    y0, y1 = res["rows"]
+    res = _time_oracle(cfg, vox, steps=3, warmup=1, budget_s=30.0)
     return {"value": res["rays"] / res["seconds"], "unit": "probe-rays/s", "cores": res["threads"], "kind": "port",
-            "sample": f"probe rows [{y0},{y1}) of {Y} = {res['rays']} of {X*Y*Z*cfg['tile'][0]*cfg['tile'][1]} rays "
-                      f"per step, mean of 2 steps, oracle/ddgi_oracle.c with OpenMP",
+            "sample": f"probe rows {res['rows']} of {Y} (spread over the field) = {res['rays']} of "
+                      f"{X*Y*Z*cfg['tile'][0]*cfg['tile'][1]} rays per step, mean of 3 steps, oracle/ddgi_oracle.c with OpenMP "
+                      f"on {res['threads']} threads",
             "mean_lookups_per_ray_in_sample": res["mean_lookups"]}
 
 
@@ -130,23 +151,24 @@ def reference_arm(args, name):
     X, Y, Z = cfg["probe_count"]
     rx, ry = cfg["tile"]
     kind, cores = "port", None
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     if _reference_shaders_available(cfg):
-        res = _time_reference_shaders(cfg, steps=max(1, min(args.steps, 5)), warmup=1)
+        res = _time_reference_shaders(cfg, steps=steps, warmup=warmup)
         kind, cores = "reference", 1
         sample = (f"all {res['rays']} probe rays per step: the reference's own probe_pass.comp transpiled to C++ "
                   f"(oracle/_ref), single thread (its globals are process-wide)")
     else:
         vox, _ = util.oracle_voxels(cfg)
-        res = _time_oracle(cfg, vox, steps=max(1, min(args.steps, 5)), warmup=1)
-        y0, y1 = res["rows"]
+        res = _time_oracle(cfg, vox, steps=steps, warmup=warmup)
         cores = res["threads"]
-        sample = (f"probe rows [{y0},{y1}) of {Y} = {res['rays']} rays per step (the GLSL reference cannot be built: "
+        sample = (f"probe rows {res['rows']} of {Y} (spread over the field: {res['mean_lookups']:.1f} voxel lookups per ray in the "
+                  f"sample) = {res['rays']} rays per step (the GLSL reference cannot be built: "
                   f"no glslang/Vulkan/lavapipe, and its transpiled shaders (oracle/_ref) have the reference's own scenes "
                   f"compiled in, not this workload's voxel field; this is the CPU oracle port, OpenMP, all host threads)")
     value = res["rays"] / res["seconds"]
     return {
         "impl": "reference", "metric": "probe_rays_per_s", "value": value, "unit": "probe-rays/s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": max(1, min(args.steps, 5)), "warmup": 1,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup,
         "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "probes": [X, Y, Z], "rays_per_probe": rx * ry, "probe_rays": X * Y * Z * rx * ry,

@@ -22,7 +22,7 @@ STALLS = ["stall_long_sb", "stall_short_sb", "stall_wait", "stall_math", "stall_
 def label_of(kernel_src, line):
     """Label of a kernel source line: the nearest preceding `// ----` comment or state call."""
     text = kernel_src[line - 1] if 0 < line <= len(kernel_src) else ""
-    for pat, name in (("wf_step(", "MARCH"), ("wf_begin_query", "QUERY"), ("wf_resolve_bounce", "BOUNCE_HIT"),
+    for pat, name in (("wf_step(", "MARCH"), ("wf_begin_query", "QUERY"), ("wf_resolve_hit", "HIT"), ("wf_end_march", "MARCH"), ("wf_resolve_bounce", "BOUNCE_HIT"),
                       ("wf_resolve_feeler", "FEELER_HIT"), ("wf_scatter", "SCATTER"), ("wf_step_literal", "MARCH_SLOW"),
                       ("store_texel", "FETCH"), ("fetch_ray", "FETCH"), ("wf_init", "FETCH"),
                       ("wf_query_block", "QUERY")):
