@@ -51,7 +51,7 @@ struct ddgi_ctx {
     // voxel field
     int vdim[3] = {0, 0, 0}, vorg[3] = {0, 0, 0}, borg[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
     uint8_t* d_types = nullptr;
-    uint32_t* d_occ = nullptr;  // one word per 4x4x2 brick
+    uint32_t* d_occ = nullptr;  // one word per brick of 32 cells (ddgi_scene.cuh: kBrickL*)
     uint8_t* d_edit = nullptr;  // staging buffer of ddgi_edit_voxels
     size_t edit_cap = 0;
     float* d_palette = nullptr;
@@ -352,8 +352,8 @@ static int alloc_voxels(ddgi_ctx* ctx, const int32_t dims[3], const int32_t orig
     for (int a = 0; a < 3; a++) {
         ctx->vdim[a] = dims[a];
         ctx->vorg[a] = origin[a];
-        ctx->borg[a] = origin[a] & ~3;  // two's complement: rounds toward -inf to a multiple of 4
-        int cells = a == 2 ? 2 : 4;  // bricks are 4x4x2 cells
+        ctx->borg[a] = origin[a] & ~(kBrickAlign - 1);  // two's complement: rounds toward -inf to a multiple of 8
+        int cells = 1 << (a == 0 ? kBrickLx : a == 1 ? kBrickLy : kBrickLz);
         ctx->nb[a] = (origin[a] + dims[a] - ctx->borg[a] + cells - 1) / cells;
     }
     size_t n = (size_t)dims[0] * dims[1] * dims[2];
@@ -701,10 +701,10 @@ int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[
     CU(cudaMemcpyAsync(ctx->d_edit, types, n, cudaMemcpyHostToDevice, s));
     int l = 0;
     CU(launch_edit_voxels(ctx->vdim, at, ext, ctx->d_edit, ctx->d_types, s, &l));
-    // the bricks the box touches (bricks are 4x4x2 cells, aligned to borg)
+    // the bricks the box touches (aligned to borg)
     int shift[3], b0[3], bn[3];
     for (int a = 0; a < 3; a++) {
-        int cells = a == 2 ? 2 : 4;
+        int cells = 1 << (a == 0 ? kBrickLx : a == 1 ? kBrickLy : kBrickLz);
         shift[a] = ctx->vorg[a] - ctx->borg[a];
         b0[a] = (at[a] + shift[a]) / cells;
         bn[a] = (at[a] + ext[a] - 1 + shift[a]) / cells - b0[a] + 1;

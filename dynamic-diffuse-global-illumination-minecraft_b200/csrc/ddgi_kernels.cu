@@ -431,7 +431,7 @@ __global__ void bake_synthetic_kernel(int dx, int dy, int dz, int permille, uint
     }
 }
 
-// One thread per 4x4x2 brick of the brick box [b0, b0 + bn): gathers 32 type bytes into the
+// One thread per brick of the brick box [b0, b0 + bn): gathers 32 type bytes into the
 // occupancy word.  The whole grid after an upload / bake, the touched bricks after an edit.
 __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, int sz, int nbx, int nby, int b0x, int b0y,
                                        int b0z, int bnx, int bny, int bnz, const uint8_t* types, uint32_t* occ)
@@ -442,14 +442,15 @@ __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, i
         int by = b0y + (int)((b / bnx) % bny);
         int bz = b0z + (int)(b / ((size_t)bnx * bny));
         uint32_t w = 0u;
-        for (int z = 0; z < 2; z++)
-            for (int y = 0; y < 4; y++)
-                for (int x = 0; x < 4; x++) {
+        for (int z = 0; z < (1 << kBrickLz); z++)
+            for (int y = 0; y < (1 << kBrickLy); y++)
+                for (int x = 0; x < (1 << kBrickLx); x++) {
                     // grid cell of this brick cell: bricks start (sx,sy,sz) cells before the grid
-                    int gx = bx * 4 + x - sx, gy = by * 4 + y - sy, gz = bz * 2 + z - sz;
+                    const int cx = (bx << kBrickLx) + x, cy = (by << kBrickLy) + y, cz = (bz << kBrickLz) + z;
+                    int gx = cx - sx, gy = cy - sy, gz = cz - sz;
                     if (gx >= 0 && gy >= 0 && gz >= 0 && gx < dx && gy < dy && gz < dz &&
                         types[((size_t)gz * dy + gy) * dx + gx] != 0)
-                        w |= 1u << (occ_shift(bx * 4 + x, by * 4 + y, bz * 2 + z) & 31);
+                        w |= 1u << (occ_shift(cx, cy, cz) & 31);
                 }
         occ[((size_t)bz * nby + by) * nbx + bx] = w;
     }

@@ -3,9 +3,9 @@
 // scene bakers that evaluate that procedural function once per voxel.
 //
 // HBM layout (DESIGN.md "Data layout"):
-//   occ   : one uint32 per 4x4x2 voxel brick, bit occ_shift(x, y, z) & 31 set = solid,
-//           x/y/z = voxel id relative to `borg` (a multiple of 4 per axis).  Brick index
-//           ((bz*nby)+by)*nbx+bx, x fastest: a 32-byte sector holds 32x4x2 voxels.
+//   occ   : one uint32 per brick of 1x4x8 voxels (kBrickL*), bit occ_shift(x, y, z) & 31 set = solid,
+//           x/y/z = voxel id relative to `borg` (a multiple of 8 per axis).  Brick index
+//           ((bz*nby)+by)*nbx+bx, x fastest: a 32-byte sector holds 8x4x8 voxels.
 //           512^3 voxels -> 16 MiB, L1/L2 resident.
 //   types : one uint8 block type per voxel, linear x-fastest; read only on a hit.
 //   palette: 256 x rgb fp32 albedo by block type (flat-colour variant, README.md:266).
@@ -22,9 +22,9 @@ struct SceneView {
     const float* palette;
     int vorg[3];
     int vdim[3];
-    int borg[3];  // voxel id of brick (0,0,0)'s first cell: vorg rounded down to a multiple of 4
+    int borg[3];  // voxel id of brick (0,0,0)'s first cell: vorg rounded down to a multiple of kBrickAlign
     int kneg[3];  // -(kCellBias + borg): biased cell coordinate -> borg-relative cell coordinate in one add
-    int nb[3];    // bricks per axis (4 cells in x and y, 2 in z)
+    int nb[3];    // bricks per axis
     float lo[3];  // (float)vorg
     float hi[3];  // (float)(vorg + vdim - 1)
     int color_mode;  // 0: flat palette by block type, 1: the reference's procedural colours (ddgi_texture.cuh)
@@ -60,12 +60,36 @@ DDGI_HD uint32_t shr_wrap(uint32_t w, int s)
 #endif
 }
 
+// Brick shape: a brick is 2^kBrickLx x 2^kBrickLy x 2^kBrickLz cells = 32 cells = one uint32.  The
+// words are stored x fastest, so a 32-byte sector holds 8 bricks along x.  DDGI_BRICK 148 (default):
+// bricks of 1 x 4 x 8 cells, a sector covers 8 x 4 x 8 cells - close to a cube, so a march crosses
+// into a new sector about equally rarely along every axis (round 1's 4 x 4 x 2 bricks made a sector
+// 32 x 4 x 2 cells: every second step along z left it).  Measured in profiles/r2_ab.md.
+#ifndef DDGI_BRICK
+#define DDGI_BRICK 148
+#endif
+#if DDGI_BRICK == 442
+constexpr int kBrickLx = 2, kBrickLy = 2, kBrickLz = 1;
+#else
+constexpr int kBrickLx = 0, kBrickLy = 2, kBrickLz = 3;
+#endif
+constexpr int kBrickAlign = 8;  // borg is a multiple of this on every axis (>= the largest brick side)
+
 // Bit of the cell with borg-relative coordinates (gx, gy, gz) inside its brick word, as a shift
-// count that is taken modulo 32: bits 0-1 = gx & 3, bits 2-3 = gy & 3, bit 4 = (gz ^ (gy >> 2)) & 1.
-// The z layer of a brick is skewed by the brick row's parity so that the count is three
-// shift-adds with no masking of gy and gz; writers (build_occupancy_kernel, tests/hostsim) and
-// readers (cell_solid) share this one definition.
-DDGI_HD int occ_shift(int gx, int gy, int gz) { return (gx & 3) + (gy << 2) + (gz << 4); }
+// count that is taken modulo 32.  1x4x8 bricks: bits 0-1 = gy & 3, bits 2-4 = gz & 7.  4x4x2 bricks:
+// bits 0-1 = gx & 3, bits 2-3 = gy & 3, bit 4 = (gz ^ (gy >> 2)) & 1 - the z layer of a brick is
+// skewed by the brick row's parity so that the count is three shift-adds with no masking of gy, gz.
+// Writers (build_occupancy_kernel, tests/hostsim) and readers (cell_solid / cell_fetch) share this
+// one definition.
+DDGI_HD int occ_shift(int gx, int gy, int gz)
+{
+#if DDGI_BRICK == 442
+    return (gx & 3) + (gy << 2) + (gz << 4);
+#else
+    (void)gx;
+    return (gy & 3) + (gz << 2);
+#endif
+}
 
 // The occupancy word `idx` when `inside`, else 0 (bricks outside the grid are empty): one
 // predicated load, no branch, no divergence.
@@ -87,7 +111,7 @@ DDGI_HD bool cell_solid(const SceneView& S, int kx, int ky, int kz)
     int gx = kx + S.kneg[0];
     int gy = ky + S.kneg[1];
     int gz = kz + S.kneg[2];
-    unsigned bx = (unsigned)gx >> 2, by = (unsigned)gy >> 2, bz = (unsigned)gz >> 1;  // (negative: huge)
+    unsigned bx = (unsigned)gx >> kBrickLx, by = (unsigned)gy >> kBrickLy, bz = (unsigned)gz >> kBrickLz;  // (negative: huge)
     bool inside = (bx < (unsigned)S.nb[0]) & (by < (unsigned)S.nb[1]) & (bz < (unsigned)S.nb[2]);
     uint32_t word = occ_word(S.occ, (bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx, inside);
     return (bool)(shr_wrap(word, occ_shift(gx, gy, gz)) & 1u);

@@ -30,7 +30,7 @@
 //     the second, for d < 0 the other way round (f in [0,1]); zero / NaN / tiny
 //     components take the literal two-division form (WF_MARCH_SLOW).
 //   * that division and x/0.1f use the FMA-corrected reciprocal of ddgi_fastmath.cuh.
-//   * the voxel test reads one bit of the 4x4x2-brick occupancy word (16 MiB for 512^3
+//   * the voxel test reads one bit of the cell's 32-cell brick word (16 MiB for 512^3
 //     voxels, L1/L2 resident); the block type is fetched only on a hit.
 //   * a light sphere whose discriminant is not positive yields t = INF in the reference
 //     (intersection.glsl:100-113), so the two root divisions are skipped for it; and the
@@ -104,6 +104,7 @@ DDGI_HD float light_test(const FrameParams& P, v3 origin, v3 direction, float di
     float closest = inf_f();
     *which = -1;
     float reach2 = inf_f();
+    unsigned near = 0xffu;  // bit i: light i may beat the block hit
     if (t_block < inf_f()) {
         float reach = (t_block * dir_len) * 1.01f + 0.101f;
         reach2 = reach * reach;
@@ -112,19 +113,19 @@ DDGI_HD float light_test(const FrameParams& P, v3 origin, v3 direction, float di
         v3 wc = origin - V3(P.lights_centre[0], P.lights_centre[1], P.lights_centre[2]);
         float far = reach + P.lights_radius;
         if (dot(wc, wc) > (far * far) * 1.0001f) return closest;
-    }
-    bool scaled = false;
-    v3 d = V3(0, 0, 0);
-    float A = 0.0f;
-    for (int i = 0; i < P.n_lights; i++) {
-        v3 w = origin - lpos(P.lights[i]);
-        if (dot(w, w) > reach2) continue;
-        if (!scaled) {
-            d = div_tenth(direction);
-            A = dot(d, d);
-            scaled = true;
+        // light by light, without a branch per light (the loop count is the same for every lane)
+        near = 0u;
+        for (int i = 0; i < P.n_lights; i++) {
+            v3 w = origin - lpos(P.lights[i]);
+            near |= (dot(w, w) > reach2 ? 0u : 1u) << i;
         }
-        v3 o = div_tenth(w);
+        if (near == 0u) return closest;
+    }
+    v3 d = div_tenth(direction);
+    float A = dot(d, d);
+    for (int i = 0; i < P.n_lights; i++) {
+        if (!((near >> i) & 1u)) continue;
+        v3 o = div_tenth(origin - lpos(P.lights[i]));
         float B = -dot(d, o);
         float C = dot(o, o) - 1.0f;
         float D = B * B - A * C;
@@ -193,23 +194,12 @@ DDGI_HD void wf_init(WfRay& R, v3 origin, v3 direction, uint32_t ray_index)
     R.mode = WF_QUERY;
 }
 
-// Voxel test at the new position, shared by both march flavours.  Returns true while the march
+// Voxel test at the new position of the literal march.  Returns true while the march
 // goes on; when it ends the lane is in WF_HIT (a solid cell: R.t is the hit) or WF_LIMIT.
-DDGI_HD bool wf_test_cell(const FrameParams& P, WfRay& R, bool small_coords)
+DDGI_HD bool wf_test_cell(const FrameParams& P, WfRay& R)
 {
     R.steps++;
-    int kx, ky, kz;
-    if (small_coords) {
-        // |p| < 2^22: p + 1.5*2^23 rounded up IS ceil(p) + 1.5*2^23 (one directed-rounding add)
-        kx = float_bits(add_round_up(R.p.x, kCellMagic));
-        ky = float_bits(add_round_up(R.p.y, kCellMagic));
-        kz = float_bits(add_round_up(R.p.z, kCellMagic));
-    } else {
-        kx = cell_bits(ceilf(R.p.x));
-        ky = cell_bits(ceilf(R.p.y));
-        kz = cell_bits(ceilf(R.p.z));
-    }
-    const bool solid = cell_solid(P.scene, kx, ky, kz);
+    const bool solid = cell_solid(P.scene, cell_bits(ceilf(R.p.x)), cell_bits(ceilf(R.p.y)), cell_bits(ceilf(R.p.z)));
     const bool limit = R.steps >= kMarchSteps || R.t > R.t_stop;
     if (solid) R.mode = WF_HIT;
     else if (limit) R.mode = WF_LIMIT;
@@ -228,9 +218,12 @@ DDGI_HD void wf_end_march(WfRay& R)
 }
 
 // WF_MARCH: one DDA advance and voxel test (the body of the reference's 125-iteration
-// loop): t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 with f = fract(p).  The larger
-// quotient has numerator 1-f for d > 0 and -f for d < 0 (a zero numerator may come out as
-// +0 where the reference has -0: min(..)+1e-4 is the same).
+// loop, intersection.glsl:1059-1097): t += min_a(max((-f_a)/d_a, (1-f_a)/d_a)) + 1e-4 with f = fract(p).
+// The larger quotient has numerator 1-f for d > 0 and -f for d < 0 (a zero numerator may come out as
+// +0 where the reference has -0: min(..)+1e-4 is the same).  floor: see floor_small.
+// (A software-pipelined form - fetch the brick word of the new cell, test it one call later behind the
+// next advance's quotients - hid the load but cost one set of quotients per march: slower on three of
+// four workloads once the brick layout had raised the L1 hit rate, profiles/r2_ab.md c.)
 DDGI_HD bool wf_step(const FrameParams& P, WfRay& R)
 {
     float tx = div_markstein(R.sel.x - (R.p.x - floor_small(R.p.x)), R.md.x, R.inv.x);
@@ -238,14 +231,21 @@ DDGI_HD bool wf_step(const FrameParams& P, WfRay& R)
     float tz = div_markstein(R.sel.z - (R.p.z - floor_small(R.p.z)), R.md.z, R.inv.z);
     R.t += gmin(gmin(tx, ty), tz) + 0.0001f;
     R.p = R.mo + R.md * R.t;
-    return wf_test_cell(P, R, true);
+    R.steps++;
+    // |p| < 2^22: p + 1.5*2^23 rounded up IS ceil(p) + 1.5*2^23 (one directed-rounding add)
+    const bool solid = cell_solid(P.scene, float_bits(add_round_up(R.p.x, kCellMagic)), float_bits(add_round_up(R.p.y, kCellMagic)),
+                                  float_bits(add_round_up(R.p.z, kCellMagic)));
+    const bool limit = R.steps >= kMarchSteps || R.t > R.t_stop;
+    if (solid) R.mode = WF_HIT;
+    else if (limit) R.mode = WF_LIMIT;
+    return !(solid || limit);
 }
 
 // WF_MARCH_SLOW: the literal two-division form.
 DDGI_HD bool wf_step_literal(const FrameParams& P, WfRay& R)
 {
     march_advance(R.mo, R.md, R.t, R.p);
-    return wf_test_cell(P, R, false);
+    return wf_test_cell(P, R);
 }
 
 // Arms the shadow feeler to light R.phase-1 from the current bounce hit.

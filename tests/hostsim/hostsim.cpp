@@ -38,7 +38,7 @@ struct SimParams {
 
 struct Built {
     FrameParams P;
-    std::vector<uint32_t> occ;  // one word per 4x4x2 brick
+    std::vector<uint32_t> occ;  // one word per brick
 };
 
 static void build(const SimParams* S, const float* cam, Built* B)
@@ -47,9 +47,9 @@ static void build(const SimParams* S, const float* cam, Built* B)
     memset(&P, 0, sizeof(P));
     int nb[3], sh[3];
     for (int a = 0; a < 3; a++) {
-        int borg = S->vorg[a] & ~3;
+        int borg = S->vorg[a] & ~(kBrickAlign - 1);
         sh[a] = S->vorg[a] - borg;
-        int cells = a == 2 ? 2 : 4;
+        int cells = 1 << (a == 0 ? kBrickLx : a == 1 ? kBrickLy : kBrickLz);
         nb[a] = (S->vorg[a] + S->vdim[a] - borg + cells - 1) / cells;
         P.scene.vorg[a] = S->vorg[a];
         P.scene.vdim[a] = S->vdim[a];
@@ -67,7 +67,7 @@ static void build(const SimParams* S, const float* cam, Built* B)
             for (int x = 0; x < S->vdim[0]; x++)
                 if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x]) {
                     int bx = x + sh[0], by = y + sh[1], bz = z + sh[2];
-                    B->occ[((size_t)(bz >> 1) * nb[1] + (by >> 2)) * nb[0] + (bx >> 2)] |= 1u << (occ_shift(bx, by, bz) & 31);
+                    B->occ[((size_t)(bz >> kBrickLz) * nb[1] + (by >> kBrickLy)) * nb[0] + (bx >> kBrickLx)] |= 1u << (occ_shift(bx, by, bz) & 31);
                 }
     P.scene.occ = B->occ.data();
     P.scene.types = S->vox;
