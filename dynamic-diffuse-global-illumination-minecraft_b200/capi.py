@@ -118,6 +118,16 @@ PROTOTYPES = {
     "ddgi_set_probes_cyclic": (C.c_int, [_P, _I32, _I32, _I32]),
     "ddgi_probe_texture_device_ptr": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_SZ)]),
     "ddgi_export_texture_handle": (C.c_int, [_P, _P]),
+    "ddgi_export_texture_handles": (C.c_int, [_P, _P, C.POINTER(_I32)]),
+    "ddgi_comm_unique_id": (C.c_int, [_P]),
+    "ddgi_comm_init": (C.c_int, [_P, _P, _I32, _I32]),
+    "ddgi_comm_destroy": (C.c_int, [_P]),
+    "ddgi_exchange_allgather": (C.c_int, [_P, _P]),
+    "ddgi_save_voxels": (C.c_int, [_P, C.c_char_p]),
+    "ddgi_load_voxels": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(_I32), C.POINTER(_I32)]),
+    "ddgi_save_checkpoint": (C.c_int, [_P, C.c_char_p, C.c_float]),
+    "ddgi_load_checkpoint": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_float)]),
+    "ddgi_set_sample_order": (C.c_int, [_P, _I32]),
     "ddgi_open_peers": (C.c_int, [_P, _I32, _P, _I32]),
     "ddgi_close_peers": (C.c_int, [_P]),
     "ddgi_exchange_barrier": (C.c_int, [_P, _P]),

@@ -2,6 +2,7 @@
 // buffers (what class RVPT's per-frame UBOs / SSBO / storage images were,
 // src/rvpt/rvpt.h:150-201) and the C-ABI of include/ddgi.h.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -64,6 +65,8 @@ struct ddgi_ctx {
     float4* d_rays = nullptr;    // literal storage-buffer mode
     size_t n_rays_ssbo = 0;
     int ray_mode = 0;  // 0 none, 1 generated, 2 storage buffer
+    bool sample_y_first = false;  // order of the two rand() draws of a sample (ddgi_set_sample_order)
+    cudaStream_t last_stream = nullptr;  // stream of the last dispatch: what ddgi_sync waits for
 
     // probe textures: one allocation, albedo then distance
     int tex_w = 0, tex_h = 0;
@@ -82,6 +85,7 @@ struct ddgi_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // last asynchronous read of each buffer
     float4* d_tex_f32 = nullptr;
     uint32_t* d_ray_lookups = nullptr;
+    size_t ray_lookups_cap = 0;  // rays d_ray_lookups was allocated for
     int row0 = 0, row1 = 0;  // probe rows owned by this context (contiguous ownership)
     int cyc_world = 0, cyc_rank = 0, cyc_block = 1;  // block-cyclic ownership when cyc_world > 0
     int cyc_unit = 0;                                // 0: blocks of probe rows, 1: blocks of probes
@@ -106,11 +110,19 @@ struct ddgi_ctx {
     int band_rank = 0, band_world = 1;  // pixel pass: this context renders band `rank` of `world` row bands
 
     // fused exchange
-    uint32_t epoch = 0;              // barriers issued since the textures were created
+    uint32_t epoch = 0;              // completion barriers issued since the textures were created
+    uint32_t epoch_pre = 0;          // pre-update barriers (single-buffered fused exchange)
     uint32_t* d_barrier_error = nullptr;
     int n_peers = 0, self_index = 0;
-    void* peer_base[kMaxPeers] = {nullptr};
-    bool peer_opened[kMaxPeers] = {false};
+    // the peers' texture allocations: [0] the only one, or [0] / [1] the two of a double-buffered
+    // context (what ddgi_export_texture_handles listed, in that order); [b][self] is the local one
+    void* peer_base[2][kMaxPeers] = {{nullptr}};
+    bool peer_opened[2][kMaxPeers] = {{false}};
+    int peer_buffers = 0;  // allocations mapped per rank: 1 or 2
+
+    // NCCL exchange (ddgi_comm_init / ddgi_exchange_allgather)
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 0;
 };
 
 // ------------------------------------------------------------------ helpers
@@ -217,8 +229,17 @@ static int schedule(ddgi_ctx* ctx)
     return DDGI_OK;
 }
 
+// Per-ray debug buffers are sized by the ray count, which changes with the ray tile even when the
+// texture size does not (octahedral layout): they are re-created on demand.
+static void free_ray_buffers(ddgi_ctx* ctx)
+{
+    dfree(ctx->d_ray_lookups);
+    ctx->ray_lookups_cap = 0;
+}
+
 // (Re)creates the probe textures for the current field, as recreate_probe_textures
-// does when probe counts or rays/probe change (src/rvpt/rvpt.cpp:661-755).
+// does when probe counts or rays/probe change (src/rvpt/rvpt.cpp:661-755).  The new allocations are
+// made before the old ones are released: a failure leaves the context as it was.
 static int resize_textures(ddgi_ctx* ctx)
 {
     int w = ctx->field.probe_count[0] * ctx->field.probe_count[2] * tile_w(ctx);
@@ -226,22 +247,29 @@ static int resize_textures(ddgi_ctx* ctx)
     if (w == ctx->tex_w && h == ctx->tex_h && ctx->d_tex) return DDGI_OK;
     if (ctx->n_peers) return fail(ctx, DDGI_E_STATE, "close peers before resizing the probe textures");
     if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+    size_t n = (size_t)w * h;
+    // both planes, then the epoch flags of the fused exchange (ddgi_exchange_barrier)
+    uint32_t* fresh[2] = {nullptr, nullptr};
+    for (int b = 0; b < (ctx->double_buffer ? 2 : 1); b++) {
+        cudaError_t e = cudaMalloc(&fresh[b], (2 * n + kFlagWords) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(fresh[b], 0, (2 * n + kFlagWords) * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            dfree(fresh[0]);
+            dfree(fresh[1]);
+            return fail(ctx, DDGI_E_CUDA, "probe textures %d x %d: %s", w, h, cudaGetErrorString(e));
+        }
+    }
     dfree(ctx->d_tex_pair[0]);
     dfree(ctx->d_tex_pair[1]);
-    ctx->d_tex = nullptr;
     dfree(ctx->d_tex_f32);
-    dfree(ctx->d_ray_lookups);
+    free_ray_buffers(ctx);
+    ctx->d_tex_pair[0] = fresh[0];
+    ctx->d_tex_pair[1] = fresh[1];
     ctx->tex_w = w;
     ctx->tex_h = h;
-    size_t n = tex_texels(ctx);
-    // both planes, then the epoch flags of the fused exchange (ddgi_exchange_barrier)
-    for (int b = 0; b < (ctx->double_buffer ? 2 : 1); b++) {
-        CU(cudaMalloc(&ctx->d_tex_pair[b], (2 * n + kFlagWords) * sizeof(uint32_t)));
-        CU(cudaMemset(ctx->d_tex_pair[b], 0, (2 * n + kFlagWords) * sizeof(uint32_t)));
-    }
     ctx->cur_tex = 0;
     ctx->d_tex = ctx->d_tex_pair[0];
-    ctx->epoch = 0;
+    ctx->epoch = ctx->epoch_pre = 0;
     ctx->distance_dirty[0] = ctx->distance_dirty[1] = false;
     return DDGI_OK;
 }
@@ -254,9 +282,11 @@ static int ensure_debug_buffers(ddgi_ctx* ctx)
         CU(cudaMalloc(&ctx->d_tex_f32, n * sizeof(float4)));
         CU(cudaMemset(ctx->d_tex_f32, 0, n * sizeof(float4)));
     }
-    if (n && !ctx->d_ray_lookups) {
+    if (n && (!ctx->d_ray_lookups || ctx->ray_lookups_cap != num_rays(ctx))) {
+        free_ray_buffers(ctx);
         CU(cudaMalloc(&ctx->d_ray_lookups, num_rays(ctx) * sizeof(uint32_t)));
         CU(cudaMemset(ctx->d_ray_lookups, 0, num_rays(ctx) * sizeof(uint32_t)));
+        ctx->ray_lookups_cap = num_rays(ctx);
     }
     size_t px = (size_t)ctx->frame_w * ctx->frame_h;
     if (px && !ctx->d_frame_f32) {
@@ -381,8 +411,8 @@ static int finish_voxels(ddgi_ctx* ctx)
 }
 
 // generate_samples, src/rvpt/rvpt.cpp:1147-1173, generalised to an rx x ry tile: libc
-// rand() jitter (x first), PI = 3.1415926 as a double, libm cosf/sinf/sqrtf.
-static void host_generate_samples(int rx, int ry, std::vector<float>& out)
+// rand() jitter, PI = 3.1415926 as a double, libm cosf/sinf/sqrtf.
+static void host_generate_samples(int rx, int ry, bool y_first, std::vector<float>& out)
 {
     const double host_pi = 3.1415926;
     float inv_x = 1.f / float(rx), inv_y = 1.f / float(ry);
@@ -390,8 +420,17 @@ static void host_generate_samples(int rx, int ry, std::vector<float>& out)
     size_t i = 0;
     for (int y = 0; y < ry; y++)
         for (int x = 0; x < rx; x++) {
-            float jx = float(rand()) / float(RAND_MAX);
-            float jy = float(rand()) / float(RAND_MAX);
+            // the two rand() calls are constructor arguments in the reference (rvpt.cpp:1161-1162): C++
+            // leaves their order open.  x first is SURVEY.md 8c-5's pin (default); g++, the reference's
+            // Linux toolchain, evaluates them right to left: y first (ddgi_set_sample_order)
+            float jx, jy;
+            if (y_first) {
+                jy = float(rand()) / float(RAND_MAX);
+                jx = float(rand()) / float(RAND_MAX);
+            } else {
+                jx = float(rand()) / float(RAND_MAX);
+                jy = float(rand()) / float(RAND_MAX);
+            }
             float su = (x + jx) * inv_x;
             float sv = (y + jy) * inv_y;
             float z = 1 - (2 * su);
@@ -457,6 +496,7 @@ void ddgi_destroy(ddgi_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ddgi_close_peers(ctx);
+    ddgi_comm_destroy(ctx);
     dfree(ctx->d_counter);
     dfree(ctx->d_types);
     dfree(ctx->d_occ);
@@ -515,17 +555,31 @@ int ddgi_set_irradiance_field(ddgi_ctx* ctx, const ddgi_irradiance_field* f)
     CU(cudaSetDevice(ctx->device));
     bool shape_changed = !ctx->have_field || memcmp(ctx->field.probe_count, f->probe_count, sizeof(f->probe_count)) ||
                          ctx->field.sqrt_rays_per_probe != f->sqrt_rays_per_probe;
+    if (!shape_changed) {
+        ctx->field = *f;
+        return DDGI_OK;
+    }
+    // a new shape re-creates the textures, which can fail (peers open, out of memory): commit the
+    // new field only when it has not, so that the context never holds a shape its textures do not have
+    const ddgi_irradiance_field old_field = ctx->field;
+    const bool old_have = ctx->have_field;
+    const int old_rx = ctx->rx, old_ry = ctx->ry;
     ctx->field = *f;
     ctx->have_field = true;
-    if (shape_changed) {
-        ctx->rx = ctx->ry = f->sqrt_rays_per_probe;
-        ctx->ray_mode = 0;
-        ctx->row0 = 0;
-        ctx->row1 = f->probe_count[1];
-        ctx->order_dirty = true;
-        ctx->calibrated = false;
-        return resize_textures(ctx);
+    ctx->rx = ctx->ry = f->sqrt_rays_per_probe;
+    int rc = resize_textures(ctx);
+    if (rc != DDGI_OK) {
+        ctx->field = old_field;
+        ctx->have_field = old_have;
+        ctx->rx = old_rx;
+        ctx->ry = old_ry;
+        return rc;
     }
+    ctx->ray_mode = 0;
+    ctx->row0 = 0;
+    ctx->row1 = f->probe_count[1];
+    ctx->order_dirty = true;
+    ctx->calibrated = false;
     return DDGI_OK;
 }
 
@@ -536,12 +590,19 @@ int ddgi_set_ray_tile(ddgi_ctx* ctx, int32_t rx, int32_t ry)
     NEED(rx >= 1 && ry >= 1 && rx <= 64 && ry <= 64, "tile out of range");
     CU(cudaSetDevice(ctx->device));
     if (rx != ctx->rx || ry != ctx->ry) {
+        const int old_rx = ctx->rx, old_ry = ctx->ry;
         ctx->rx = rx;
         ctx->ry = ry;
+        int rc = resize_textures(ctx);
+        if (rc != DDGI_OK) {  // (see ddgi_set_irradiance_field)
+            ctx->rx = old_rx;
+            ctx->ry = old_ry;
+            return rc;
+        }
         ctx->ray_mode = 0;
         ctx->calibrated = false;
         ctx->order_dirty = true;  // the slot count changed
-        return resize_textures(ctx);
+        free_ray_buffers(ctx);    // sized by rays per probe
     }
     return DDGI_OK;
 }
@@ -711,9 +772,10 @@ int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[
     }
     CU(launch_build_occupancy(ctx->vdim, shift, ctx->nb, b0, bn, ctx->d_types, ctx->d_occ, s, &l));
     ctx->launches += l;
-    // host memory is pageable in general: the copy above has completed or been staged by the
-    // runtime when cudaMemcpyAsync returns only for pinned memory, so wait for it here
-    CU(cudaStreamSynchronize(s));
+    ctx->last_stream = s;
+    // `types` may be reused on return: a copy from pageable memory is staged by the runtime before
+    // cudaMemcpyAsync returns; a PINNED source must stay untouched until the stream has passed the
+    // copy (ddgi_sync, or any later synchronisation of `stream`) - documented in ddgi.h
     return DDGI_OK;
 }
 
@@ -723,6 +785,7 @@ int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes)
     NEED(ctx->d_types, "no voxel field");
     NEED(dst && bytes == (size_t)ctx->vdim[0] * ctx->vdim[1] * ctx->vdim[2], "size mismatch");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));  // the dispatches may run on a non-blocking stream
     CU(cudaMemcpy(dst, ctx->d_types, bytes, cudaMemcpyDeviceToHost));
     return DDGI_OK;
 }
@@ -733,7 +796,7 @@ int ddgi_generate_probe_rays(ddgi_ctx* ctx, int32_t reseed)
     NEED(ctx->have_field, "set the irradiance field first");
     CU(cudaSetDevice(ctx->device));
     if (reseed) srand(1);
-    host_generate_samples(ctx->rx, ctx->ry, ctx->samples);
+    host_generate_samples(ctx->rx, ctx->ry, ctx->sample_y_first, ctx->samples);
     return upload_dirs(ctx);
 }
 
@@ -893,6 +956,7 @@ int ddgi_export_texture_handle(ddgi_ctx* ctx, void* handle64)
 {
     if (!ctx) return DDGI_E_INVALID;
     NEED(ctx->d_tex && handle64, "no probe texture");
+    NEED(!ctx->double_buffer, "a double-buffered context has two allocations: use ddgi_export_texture_handles");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CU(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
@@ -901,46 +965,70 @@ int ddgi_export_texture_handle(ddgi_ctx* ctx, void* handle64)
     return DDGI_OK;
 }
 
+int ddgi_export_texture_handles(ddgi_ctx* ctx, void* handles, int32_t* count)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ctx->d_tex && handles && count, "no probe texture");
+    CU(cudaSetDevice(ctx->device));
+    *count = ctx->double_buffer ? 2 : 1;
+    for (int b = 0; b < *count; b++) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ctx->double_buffer ? ctx->d_tex_pair[b] : ctx->d_tex));
+        memcpy((char*)handles + 64 * b, &h, 64);
+    }
+    return DDGI_OK;
+}
+
 int ddgi_open_peers(ddgi_ctx* ctx, int32_t n_peers, const void* handles64, int32_t self_index)
 {
     if (!ctx) return DDGI_E_INVALID;
     NEED(ctx->d_tex, "no probe texture");
     NEED(n_peers >= 1 && n_peers <= kMaxPeers && handles64 && self_index >= 0 && self_index < n_peers, "bad peers");
-    NEED(!ctx->double_buffer, "the fused exchange maps one allocation per rank: turn double buffering off");
     CU(cudaSetDevice(ctx->device));
     ddgi_close_peers(ctx);
-    for (int g = 0; g < n_peers; g++) {
-        if (g == self_index) {
-            ctx->peer_base[g] = ctx->d_tex;
-            continue;
+    // per rank as many handles as this context has allocations (every rank must be configured alike)
+    const int nb = ctx->double_buffer ? 2 : 1;
+    for (int g = 0; g < n_peers; g++)
+        for (int b = 0; b < nb; b++) {
+            if (g == self_index) {
+                ctx->peer_base[b][g] = ctx->double_buffer ? ctx->d_tex_pair[b] : ctx->d_tex;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles64 + 64 * ((size_t)g * nb + b), 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_base[b][g], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                ctx->peer_base[b][g] = nullptr;
+                ddgi_close_peers(ctx);
+                return fail(ctx, DDGI_E_CUDA, "cudaIpcOpenMemHandle (rank %d, buffer %d): %s", g, b, cudaGetErrorString(e));
+            }
+            ctx->peer_opened[b][g] = true;
         }
-        cudaIpcMemHandle_t h;
-        memcpy(&h, (const char*)handles64 + 64 * g, 64);
-        CU(cudaIpcOpenMemHandle(&ctx->peer_base[g], h, cudaIpcMemLazyEnablePeerAccess));
-        ctx->peer_opened[g] = true;
-    }
     ctx->n_peers = n_peers;
     ctx->self_index = self_index;
+    ctx->peer_buffers = nb;
     return DDGI_OK;
 }
 
 int ddgi_close_peers(ddgi_ctx* ctx)
 {
     if (!ctx) return DDGI_E_INVALID;
-    for (int g = 0; g < kMaxPeers; g++) {
-        if (ctx->peer_opened[g]) cudaIpcCloseMemHandle(ctx->peer_base[g]);
-        ctx->peer_opened[g] = false;
-        ctx->peer_base[g] = nullptr;
-    }
+    for (int b = 0; b < 2; b++)
+        for (int g = 0; g < kMaxPeers; g++) {
+            if (ctx->peer_opened[b][g]) cudaIpcCloseMemHandle(ctx->peer_base[b][g]);
+            ctx->peer_opened[b][g] = false;
+            ctx->peer_base[b][g] = nullptr;
+        }
     ctx->n_peers = 0;
+    ctx->peer_buffers = 0;
     return DDGI_OK;
 }
 
-int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream)
+// One epoch barrier over the peers' flag words (which live behind the planes of allocation [0] of
+// every rank): `phase` 0 = completion barrier after an update (flag slots 0..7), 1 = the barrier in
+// front of an update of a single-buffered context (slots 32..39).
+static int issue_barrier(ddgi_ctx* ctx, int phase, cudaStream_t stream)
 {
-    if (!ctx) return DDGI_E_INVALID;
-    if (ctx->n_peers < 1 || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no peers: call ddgi_open_peers first");
-    CU(cudaSetDevice(ctx->device));
     if (!ctx->d_barrier_error) {
         CU(cudaMalloc(&ctx->d_barrier_error, sizeof(uint32_t)));
         CU(cudaMemset(ctx->d_barrier_error, 0, sizeof(uint32_t)));
@@ -949,16 +1037,30 @@ int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream)
     memset(&B, 0, sizeof(B));
     B.n_ranks = ctx->n_peers;
     B.self = ctx->self_index;
-    B.epoch = ++ctx->epoch;
+    B.epoch = phase == 0 ? ++ctx->epoch : ++ctx->epoch_pre;
     B.timeout_ns = 5000000000ull;
-    size_t flags_at = 2 * tex_texels(ctx);
-    B.local_flags = ctx->d_tex + flags_at;
-    for (int g = 0; g < ctx->n_peers; g++) B.peer_flags[g] = (uint32_t*)ctx->peer_base[g] + flags_at;
+    size_t flags_at = 2 * tex_texels(ctx) + (phase ? kFlagWords / 2 : 0);
+    B.local_flags = (uint32_t*)ctx->peer_base[0][ctx->self_index] + flags_at;
+    for (int g = 0; g < ctx->n_peers; g++) B.peer_flags[g] = (uint32_t*)ctx->peer_base[0][g] + flags_at;
     B.error = ctx->d_barrier_error;
     int l = 0;
-    CU(launch_peer_barrier(B, (cudaStream_t)stream, &l));
+    CU(launch_peer_barrier(B, stream, &l));
     ctx->launches += l;
     return DDGI_OK;
+}
+
+int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (ctx->n_peers < 1 || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no peers: call ddgi_open_peers first");
+    CU(cudaSetDevice(ctx->device));
+    // The peers' NEXT update stores into the allocation this context's next update writes too.  An
+    // asynchronous read of that allocation (ddgi_read_probe_texture_async, on the copy stream) must
+    // be over before any peer may start: this rank only arrives at the barrier once it is.
+    int next = ctx->double_buffer ? ctx->cur_tex ^ 1 : ctx->cur_tex;
+    if (ctx->ev_copied[next]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_copied[next], 0));
+    ctx->last_stream = (cudaStream_t)stream;
+    return issue_barrier(ctx, 0, (cudaStream_t)stream);
 }
 
 int ddgi_exchange_status(ddgi_ctx* ctx)
@@ -972,6 +1074,265 @@ int ddgi_exchange_status(ddgi_ctx* ctx)
     return DDGI_OK;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------ NCCL exchange
+// The collective library is bound at run time (dlopen of libnccl.so.2: the copy the process
+// already holds, e.g. torch's, or the system's), so libddgi_b200.so has no link-time dependency
+// on it and a single-GPU host needs no NCCL at all.
+namespace {
+struct NcclId {
+    char internal[128];  // ncclUniqueId
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    const char* why = nullptr;
+};
+constexpr int kNcclUint8 = 1;  // ncclUint8
+
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) {
+        api.why = "libnccl.so.2 not found";
+        return api;
+    }
+    bool ok = true;
+    auto sym = [&](const char* n) {
+        void* p = dlsym(api.lib, n);
+        ok = ok && p != nullptr;
+        return p;
+    };
+    api.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclBroadcast");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!ok) {
+        api.why = "libnccl.so.2 lacks an expected symbol";
+        api.lib = nullptr;
+    }
+    return api;
+}
+}  // namespace
+#define NCCLCHK(call)                                                                                     \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0) return fail(ctx, DDGI_E_CUDA, "%s: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(r_) : "nccl error"); \
+    } while (0)
+
+extern "C" {
+
+int ddgi_comm_unique_id(void* id128)
+{
+    if (!id128) return DDGI_E_INVALID;
+    NcclApi& N = nccl();
+    if (!N.lib) return DDGI_E_STATE;
+    NcclId id;
+    if (N.GetUniqueId(&id) != 0) return DDGI_E_CUDA;
+    memcpy(id128, &id, sizeof(id));
+    return DDGI_OK;
+}
+
+int ddgi_comm_init(ddgi_ctx* ctx, const void* id128, int32_t rank, int32_t world)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(id128 && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+    NcclApi& N = nccl();
+    if (!N.lib) return fail(ctx, DDGI_E_STATE, "NCCL is not available: %s", N.why ? N.why : "?");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) {
+        N.CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    NCCLCHK(N.CommInitRank(&ctx->nccl_comm, world, id, rank));
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    return DDGI_OK;
+}
+
+int ddgi_comm_destroy(ddgi_ctx* ctx)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (ctx->nccl_comm) {
+        cudaSetDevice(ctx->device);
+        nccl().CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->comm_world = 0;
+    return DDGI_OK;
+}
+
+// In-place exchange of the texture planes over NCCL after ddgi_probe_update: probe row
+// y is texture rows [y*th, (y+1)*th), a contiguous byte range of each plane.
+//  * contiguous slabs of Y/world probe rows (ddgi_set_probe_rows(rank*Y/world, (rank+1)*Y/world)):
+//    ONE ncclAllGather per plane whose send buffer is the rank's own slab inside the receive buffer;
+//  * block-cyclic rows (ddgi_set_probe_rows_cyclic(rank, world, block)): every block is broadcast in
+//    place from its owner, all of them inside one ncclGroupStart / ncclGroupEnd.
+// The distance plane is skipped while it only holds the reference's zeros (every replica has them).
+int ddgi_exchange_allgather(ddgi_ctx* ctx, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    if (!ctx->nccl_comm) return fail(ctx, DDGI_E_STATE, "no communicator: call ddgi_comm_init first");
+    if (!ctx->have_field || !ctx->d_tex) return fail(ctx, DDGI_E_STATE, "no irradiance field");
+    NcclApi& N = nccl();
+    CU(cudaSetDevice(ctx->device));
+    const int Y = ctx->field.probe_count[1], G = ctx->comm_world, r = ctx->comm_rank;
+    const size_t row_bytes = (size_t)ctx->tex_w * 4 * tile_h(ctx);  // one probe row of one plane
+    const size_t plane = tex_texels(ctx) * 4;
+    const int planes = ctx->distance_dirty[ctx->cur_tex] ? 2 : 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    ctx->last_stream = s;
+    if (ctx->cyc_world == 0) {
+        if (Y % G != 0 || ctx->row0 != r * (Y / G) || ctx->row1 != (r + 1) * (Y / G))
+            return fail(ctx, DDGI_E_STATE, "ddgi_exchange_allgather needs equal slabs: ddgi_set_probe_rows(rank*Y/world, (rank+1)*Y/world) "
+                                          "with Y %% world == 0, or block-cyclic rows (ddgi_set_probe_rows_cyclic)");
+        const size_t chunk = (size_t)(Y / G) * row_bytes;
+        for (int p = 0; p < planes; p++) {
+            char* base = (char*)ctx->d_tex + p * plane;
+            NCCLCHK(N.AllGather(base + r * chunk, base, chunk, kNcclUint8, ctx->nccl_comm, s));
+        }
+        return DDGI_OK;
+    }
+    if (ctx->cyc_unit != 0 || ctx->cyc_world != G || ctx->cyc_rank != r)
+        return fail(ctx, DDGI_E_STATE, "ddgi_exchange_allgather moves probe rows: probe-cyclic ownership scatters tiles, use the fused exchange");
+    NCCLCHK(N.GroupStart());
+    for (int p = 0; p < planes; p++) {
+        char* base = (char*)ctx->d_tex + p * plane;
+        for (int y = 0, b = 0; y < Y; y += ctx->cyc_block, b++) {
+            int y1 = y + ctx->cyc_block < Y ? y + ctx->cyc_block : Y;
+            char* at = base + (size_t)y * row_bytes;
+            int rc = N.Broadcast(at, at, (size_t)(y1 - y) * row_bytes, kNcclUint8, b % G, ctx->nccl_comm, s);
+            if (rc != 0) {
+                N.GroupEnd();
+                return fail(ctx, DDGI_E_CUDA, "ncclBroadcast: %s", N.GetErrorString(rc));
+            }
+        }
+    }
+    NCCLCHK(N.GroupEnd());
+    return DDGI_OK;
+}
+
+// ------------------------------------------------------------------ on-disk formats
+// Voxel file: "DDGIVOX1", int32 dims[3] (x, y, z), int32 origin[3], then dims product block types, x fastest.
+// Checkpoint: "DDGIPTX1", int32 W, int32 H, float time, albedo plane, distance plane (RGBA8 rows).
+// All little-endian (the only byte order the engine runs on).
+int ddgi_save_voxels(ddgi_ctx* ctx, const char* path)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(path, "null path");
+    NEED(ctx->d_types, "no voxel field");
+    size_t n = (size_t)ctx->vdim[0] * ctx->vdim[1] * ctx->vdim[2];
+    std::vector<uint8_t> vox(n);
+    int rc = ddgi_read_voxels(ctx, vox.data(), n);
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ctx, DDGI_E_INVALID, "%s: cannot open for writing", path);
+    int32_t hdr[6] = {ctx->vdim[0], ctx->vdim[1], ctx->vdim[2], ctx->vorg[0], ctx->vorg[1], ctx->vorg[2]};
+    bool ok = fwrite("DDGIVOX1", 1, 8, f) == 8 && fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(vox.data(), 1, n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(ctx, DDGI_E_INVALID, "%s: write failed", path);
+    return DDGI_OK;
+}
+
+int ddgi_load_voxels(ddgi_ctx* ctx, const char* path, const float* palette, int32_t dims_out[3], int32_t origin_out[3])
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(path, "null path");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ctx, DDGI_E_INVALID, "%s: cannot open", path);
+    char magic[8];
+    int32_t hdr[6];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "DDGIVOX1", 8) != 0 || fread(hdr, sizeof(hdr), 1, f) != 1) {
+        fclose(f);
+        return fail(ctx, DDGI_E_INVALID, "%s: not a voxel file", path);
+    }
+    if (hdr[0] <= 0 || hdr[1] <= 0 || hdr[2] <= 0 || (size_t)hdr[0] * hdr[1] * hdr[2] > ((size_t)1 << 34)) {
+        fclose(f);
+        return fail(ctx, DDGI_E_INVALID, "%s: bad voxel dimensions", path);
+    }
+    size_t n = (size_t)hdr[0] * hdr[1] * hdr[2];
+    std::vector<uint8_t> vox(n);
+    size_t got = fread(vox.data(), 1, n, f);
+    fclose(f);
+    if (got != n) return fail(ctx, DDGI_E_INVALID, "%s: truncated voxel file", path);
+    if (dims_out) memcpy(dims_out, hdr, 3 * sizeof(int32_t));
+    if (origin_out) memcpy(origin_out, hdr + 3, 3 * sizeof(int32_t));
+    return ddgi_upload_voxels(ctx, hdr, hdr + 3, vox.data(), palette);
+}
+
+int ddgi_save_checkpoint(ddgi_ctx* ctx, const char* path, float time)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(path, "null path");
+    NEED(ctx->d_tex, "no probe texture");
+    size_t n = tex_texels(ctx);
+    std::vector<uint32_t> planes(2 * n);
+    for (int which = 0; which < 2; which++) {
+        int rc = ddgi_read_probe_texture(ctx, which, DDGI_FMT_RGBA8, planes.data() + which * n, n * 4);
+        if (rc) return rc;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ctx, DDGI_E_INVALID, "%s: cannot open for writing", path);
+    int32_t wh[2] = {ctx->tex_w, ctx->tex_h};
+    bool ok = fwrite("DDGIPTX1", 1, 8, f) == 8 && fwrite(wh, sizeof(wh), 1, f) == 1 && fwrite(&time, 4, 1, f) == 1 &&
+              fwrite(planes.data(), 4, 2 * n, f) == 2 * n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(ctx, DDGI_E_INVALID, "%s: write failed", path);
+    return DDGI_OK;
+}
+
+int ddgi_load_checkpoint(ddgi_ctx* ctx, const char* path, float* time_out)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(path, "null path");
+    NEED(ctx->d_tex, "no probe texture: set the irradiance field of the dumped shape first");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ctx, DDGI_E_INVALID, "%s: cannot open", path);
+    char magic[8];
+    int32_t wh[2];
+    float time = 0.0f;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "DDGIPTX1", 8) != 0 || fread(wh, sizeof(wh), 1, f) != 1 || fread(&time, 4, 1, f) != 1) {
+        fclose(f);
+        return fail(ctx, DDGI_E_INVALID, "%s: not a probe-texture checkpoint", path);
+    }
+    if (wh[0] != ctx->tex_w || wh[1] != ctx->tex_h) {
+        fclose(f);
+        return fail(ctx, DDGI_E_INVALID, "%s: checkpoint is %dx%d, the field's texture is %dx%d", path, wh[0], wh[1], ctx->tex_w, ctx->tex_h);
+    }
+    size_t n = tex_texels(ctx);
+    std::vector<uint32_t> planes(2 * n);
+    size_t got = fread(planes.data(), 4, 2 * n, f);
+    fclose(f);
+    if (got != 2 * n) return fail(ctx, DDGI_E_INVALID, "%s: truncated checkpoint", path);
+    for (int which = 0; which < 2; which++) {
+        int rc = ddgi_write_probe_texture(ctx, which, planes.data() + which * n, n * 4);
+        if (rc) return rc;
+    }
+    if (time_out) *time_out = time;
+    return DDGI_OK;
+}
+
 int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
 {
     if (!ctx) return DDGI_E_INVALID;
@@ -980,6 +1341,9 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     if (ctx->ray_mode == 0) return fail(ctx, DDGI_E_STATE, "no probe rays: call ddgi_generate_probe_rays or ddgi_set_probe_rays");
     if (ctx->layout == DDGI_LAYOUT_OCTAHEDRAL && ctx->ray_mode != 1)
         return fail(ctx, DDGI_E_STATE, "the octahedral layout needs a generated ray set (ddgi_generate_probe_rays / _fibonacci_rays / ddgi_set_ray_samples)");
+    if (ctx->tex_w != ctx->field.probe_count[0] * ctx->field.probe_count[2] * tile_w(ctx) ||
+        ctx->tex_h != ctx->field.probe_count[1] * tile_h(ctx))
+        return fail(ctx, DDGI_E_STATE, "the probe textures do not have the field's shape");
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_debug_buffers(ctx);
     if (rc) return rc;
@@ -1023,11 +1387,25 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     J.albedo_old = old_tex;
     J.albedo_f32 = ctx->debug ? ctx->d_tex_f32 : nullptr;
     J.lookups = ctx->debug ? ctx->d_ray_lookups : nullptr;
+    // fused exchange: every texel also goes into the peers' replicas - of the same allocation this
+    // update writes locally (the other one of a double-buffered context holds the frame the peers
+    // may still be rendering or reading)
+    const int peer_buf = ctx->peer_buffers == 2 ? ctx->cur_tex : 0;
     for (int g = 0; g < ctx->n_peers; g++) {
         if (g == ctx->self_index) continue;
-        J.peer_albedo[J.n_peers] = (uint32_t*)ctx->peer_base[g];
-        J.peer_distance[J.n_peers] = (uint32_t*)ctx->peer_base[g] + tex_texels(ctx);
+        J.peer_albedo[J.n_peers] = (uint32_t*)ctx->peer_base[peer_buf][g];
+        J.peer_distance[J.n_peers] = (uint32_t*)ctx->peer_base[peer_buf][g] + tex_texels(ctx);
         J.n_peers++;
+    }
+    if (ctx->n_peers > 1 && ctx->peer_buffers == 1) {
+        // Single-buffered replicas: a faster rank's update i+1 would store into this rank's texture
+        // while it still renders or reads frame i.  A second epoch barrier in front of every update
+        // closes that window: nobody starts update i+1 before everybody has issued - in stream order,
+        // behind its readers of frame i - its own.  (A double-buffered context does not need it: update
+        // i+1 writes the other allocation, and update i+2 cannot start before this rank has passed
+        // the completion barrier of i+1, which its readers of frame i precede in stream order.)
+        rc = issue_barrier(ctx, 1, (cudaStream_t)stream);
+        if (rc) return rc;
     }
     if (ctx->layout == 1) {
         if (num_rays(ctx) > ctx->ray_out_cap) {
@@ -1076,6 +1454,7 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         CU(launch_probe_blend_octahedral(P, O, (cudaStream_t)stream, &l));
     }
     ctx->launches += l;
+    ctx->last_stream = (cudaStream_t)stream;
     if (!ctx->ev_update) CU(cudaEventCreateWithFlags(&ctx->ev_update, cudaEventDisableTiming));
     CU(cudaEventRecord(ctx->ev_update, (cudaStream_t)stream));
     if (calibrate) {
@@ -1121,6 +1500,7 @@ int ddgi_render_frame(ddgi_ctx* ctx, void* stream)
     int l = 0;
     CU(launch_render_frame(P, J, (cudaStream_t)stream, &l));
     ctx->launches += l;
+    ctx->last_stream = (cudaStream_t)stream;
     return DDGI_OK;
 }
 
@@ -1146,7 +1526,10 @@ int ddgi_sync(ddgi_ctx* ctx)
 {
     if (!ctx) return DDGI_E_INVALID;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaDeviceSynchronize());
+    // the stream of the last dispatch and the engine's own copy stream - not the device: the caller's
+    // other streams keep running (raytrace_work_fence.wait, rvpt.cpp:277, waits for one submission too)
+    CU(cudaStreamSynchronize(ctx->last_stream));
+    if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
     return DDGI_OK;
 }
 
@@ -1164,6 +1547,7 @@ int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, void* dst
     NEED(ctx->d_tex, "no probe texture");
     NEED(dst && (which == 0 || which == 1), "bad arguments");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));  // the dispatches may run on a non-blocking stream
     size_t n = tex_texels(ctx);
     if (fmt == DDGI_FMT_RGBA8) {
         NEED(bytes == n * 4, "expected width*height*4 bytes");
@@ -1182,7 +1566,7 @@ int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, void* dst
 int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on)
 {
     if (!ctx) return DDGI_E_INVALID;
-    NEED(ctx->n_peers == 0, "close peers first: the fused exchange maps one allocation per rank");
+    NEED(ctx->n_peers == 0, "close peers first: the peers have mapped this context's allocations");
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
     bool want = on != 0;
@@ -1241,6 +1625,7 @@ int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes)
     if (!ctx) return DDGI_E_INVALID;
     NEED(ctx->d_frame && dst, "no frame");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));  // the dispatches may run on a non-blocking stream
     size_t n = (size_t)ctx->frame_w * ctx->frame_h;
     if (fmt == DDGI_FMT_RGBA8) {
         NEED(bytes == n * 4, "expected w*h*4 bytes");
@@ -1298,8 +1683,9 @@ int ddgi_read_lookup_counts(ddgi_ctx* ctx, int32_t which, uint32_t* dst, size_t 
     if (!ctx) return DDGI_E_INVALID;
     NEED(dst, "null dst");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));  // the dispatches may run on a non-blocking stream
     if (which == 0) {
-        NEED(ctx->d_ray_lookups && count == num_rays(ctx), "no per-ray counts (debug mode off?)");
+        NEED(ctx->d_ray_lookups && count == num_rays(ctx) && ctx->ray_lookups_cap == count, "no per-ray counts (debug mode off, or no update since the ray set changed)");
         CU(cudaMemcpy(dst, ctx->d_ray_lookups, count * 4, cudaMemcpyDeviceToHost));
         return DDGI_OK;
     }
@@ -1355,6 +1741,13 @@ int ddgi_set_distance_mode(ddgi_ctx* ctx, int32_t mode, float scale)
     NEED(scale > 0.0f && scale < 1e30f, "distance scale must be positive and finite");
     ctx->distance_mode = mode;
     ctx->distance_scale = scale;
+    return DDGI_OK;
+}
+
+int ddgi_set_sample_order(ddgi_ctx* ctx, int32_t y_first)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    ctx->sample_y_first = y_first != 0;
     return DDGI_OK;
 }
 

@@ -75,6 +75,9 @@ __device__ __forceinline__ void store_texel(const ProbeJob& J, int tx, int ty, v
         if (J.slot_cost) atomicMax(J.slot_cost + k / J.slot_rays, lookups);
         return;
     }
+    // literal storage-buffer mode: the texel comes from the caller's probe_info floats; an
+    // out-of-range imageStore is discarded, as Vulkan does for the reference (probe_pass.comp:301-302)
+    if (J.rays && ((unsigned)tx >= (unsigned)J.tex_w || (unsigned)ty >= (unsigned)J.tex_h)) return;
     size_t t = (size_t)ty * J.tex_w + tx;
     if (J.blend) color = blend_hysteresis(J.albedo_old[t], color, J.hysteresis);
     uint32_t rgba = pack_rgba8(color.x, color.y, color.z, 1.0f);

@@ -171,28 +171,16 @@ class RVPT:
         o = (C.c_int32 * 3)(*origin)
         self._check(self._lib.ddgi_edit_voxels(self._ctx, o, d, types.ctypes.data, self.stream))
 
-    VOXEL_MAGIC = b"DDGIVOX1"
-
-    def save_voxels(self, path: str, dims, origin):
-        """Raw voxel file: magic, dims (x, y, z), origin, then dims product block types, x fastest."""
-        vox = self.read_voxels(dims)
-        with open(path, "wb") as f:
-            f.write(self.VOXEL_MAGIC)
-            f.write(np.array(list(dims) + list(origin), dtype="<i4").tobytes())
-            f.write(vox.tobytes())
+    def save_voxels(self, path: str, dims=None, origin=None):
+        """Raw voxel file (ddgi_save_voxels): magic, dims (x, y, z), origin, then dims product block types, x fastest."""
+        self._check(self._lib.ddgi_save_voxels(self._ctx, str(path).encode()))
 
     def load_voxels(self, path: str, palette: np.ndarray | None = None):
-        """Uploads a file written by save_voxels; returns (dims, origin)."""
-        with open(path, "rb") as f:
-            if f.read(8) != self.VOXEL_MAGIC:
-                raise DDGIError(capi.E_INVALID, f"{path}: not a voxel file")
-            hdr = np.frombuffer(f.read(24), dtype="<i4")
-            dims, origin = tuple(int(v) for v in hdr[:3]), tuple(int(v) for v in hdr[3:])
-            vox = np.frombuffer(f.read(), dtype=np.uint8)
-        if vox.size != dims[0] * dims[1] * dims[2]:
-            raise DDGIError(capi.E_INVALID, f"{path}: truncated voxel file")
-        self.upload_voxels(vox.reshape(dims[2], dims[1], dims[0]), origin, palette)
-        return dims, origin
+        """Uploads a file written by save_voxels (ddgi_load_voxels); returns (dims, origin)."""
+        d, o = (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        pal = None if palette is None else np.ascontiguousarray(palette, dtype=np.float32)
+        self._check(self._lib.ddgi_load_voxels(self._ctx, str(path).encode(), None if pal is None else pal.ctypes.data, d, o))
+        return tuple(d), tuple(o)
 
     def set_color_mode(self, mode: int):
         """capi.COLOR_PALETTE (flat colours) or capi.COLOR_LITERAL (the reference's procedural textures)."""
@@ -330,33 +318,15 @@ class RVPT:
     # -- checkpoint / resume ----------------------------------------------------------
     # The reference recomputes the probe texture from scratch every frame and has nothing to
     # save; with the hysteresis blend the texture carries state from frame to frame.
-    CHECKPOINT_MAGIC = b"DDGIPTX1"
-
     def save_checkpoint(self, path: str):
-        """Probe-texture dump: magic, (W, H, time) header, albedo plane, distance plane (RGBA8 rows)."""
-        w, h = self.probe_texture_size
-        with open(path, "wb") as f:
-            f.write(self.CHECKPOINT_MAGIC)
-            f.write(np.array([w, h], dtype="<i4").tobytes())
-            f.write(np.array([self.render_settings.time], dtype="<f4").tobytes())
-            f.write(self.read_probe_texture(0).astype("<u4").tobytes())
-            f.write(self.read_probe_texture(1).astype("<u4").tobytes())
+        """Probe-texture dump (ddgi_save_checkpoint): magic, (W, H, time) header, albedo plane, distance plane."""
+        self._check(self._lib.ddgi_save_checkpoint(self._ctx, str(path).encode(), C.c_float(self.render_settings.time)))
 
     def load_checkpoint(self, path: str):
         """Restores both texture planes and render_settings.time; the field must already have the dumped shape."""
-        w, h = self.probe_texture_size
-        with open(path, "rb") as f:
-            if f.read(8) != self.CHECKPOINT_MAGIC:
-                raise DDGIError(capi.E_INVALID, f"{path}: not a probe-texture checkpoint")
-            fw, fh = np.frombuffer(f.read(8), dtype="<i4")
-            if (fw, fh) != (w, h):
-                raise DDGIError(capi.E_INVALID, f"{path}: checkpoint is {fw}x{fh}, the field's texture is {w}x{h}")
-            self.render_settings.time = float(np.frombuffer(f.read(4), dtype="<f4")[0])
-            for which in (0, 1):
-                plane = np.frombuffer(f.read(w * h * 4), dtype="<u4")
-                if plane.size != w * h:
-                    raise DDGIError(capi.E_INVALID, f"{path}: truncated checkpoint")
-                self.write_probe_texture(plane.reshape(h, w), which)
+        t = C.c_float()
+        self._check(self._lib.ddgi_load_checkpoint(self._ctx, str(path).encode(), C.byref(t)))
+        self.render_settings.time = t.value
 
     # -- instrumentation / multi-GPU ------------------------------------------------
     def set_debug(self, on):
@@ -415,13 +385,39 @@ class RVPT:
         return p.value, n.value
 
     def export_texture_handle(self) -> bytes:
-        buf = C.create_string_buffer(64)
-        self._check(self._lib.ddgi_export_texture_handle(self._ctx, buf))
-        return buf.raw
+        """CUDA IPC handle(s) of the texture allocation(s): 64 bytes, or 128 for a double-buffered context."""
+        buf = C.create_string_buffer(128)
+        n = C.c_int32()
+        self._check(self._lib.ddgi_export_texture_handles(self._ctx, buf, C.byref(n)))
+        return buf.raw[:64 * n.value]
 
     def open_peers(self, handles: list[bytes], self_index: int):
+        """handles[g] = what rank g's export_texture_handle returned (every rank configured alike)."""
         blob = b"".join(handles)
         self._check(self._lib.ddgi_open_peers(self._ctx, len(handles), blob, self_index))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte ncclUniqueId (one rank creates it, the host passes it to the others)."""
+        buf = C.create_string_buffer(128)
+        rc = capi.load().ddgi_comm_unique_id(buf)
+        if rc != capi.OK:
+            raise DDGIError(rc, "ddgi_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        self._check(self._lib.ddgi_comm_init(self._ctx, unique_id, rank, world))
+
+    def comm_destroy(self):
+        self._check(self._lib.ddgi_comm_destroy(self._ctx))
+
+    def exchange_allgather(self):
+        """In-place NCCL exchange of the probe rows after probe_update (ddgi_exchange_allgather)."""
+        self._check(self._lib.ddgi_exchange_allgather(self._ctx, self.stream))
+
+    def set_sample_order(self, y_first: bool):
+        """False (default): x jitter drawn first; True: y first, what g++ makes of rvpt.cpp:1161-1162."""
+        self._check(self._lib.ddgi_set_sample_order(self._ctx, 1 if y_first else 0))
 
     def set_frame_band(self, rank: int, world: int):
         """This context renders band `rank` of `world` bands of 16-pixel rows; returns its pixel rows (y0, y1)."""

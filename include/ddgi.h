@@ -172,8 +172,9 @@ DDGI_API int ddgi_set_distance_mode(ddgi_ctx* ctx, int32_t mode, float scale);
 /* Per-frame scene edit (dynamic scenes; the reference's scene is compiled into its shaders and
    cannot change): overwrites the box of voxel ids [origin, origin + dims) with `types` (x fastest)
    and rebuilds only the occupancy bricks it touches.  The box must lie inside the uploaded field.
-   Ordered on `stream` with the dispatches; returns when `types` may be reused.  The cost-ordered
-   schedule keeps its last calibration (results never depend on it). */
+   Ordered on `stream` with the dispatches and asynchronous: pageable `types` may be reused on return,
+   pinned `types` once `stream` has passed the copy.  The cost-ordered schedule keeps its last
+   calibration (results never depend on it). */
 DDGI_API int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[3], const uint8_t* types, void* stream);
 /* Probe-texture layout.  DDGI_LAYOUT_RAY_TILE (default) is the reference: one texel per ray, tile
    rx x ry (probe_pass.comp:269-271).  DDGI_LAYOUT_OCTAHEDRAL is the textbook layout the north star
@@ -192,10 +193,15 @@ DDGI_API int ddgi_set_layout(ddgi_ctx* ctx, int32_t layout, int32_t oct);
 DDGI_API int ddgi_read_voxels(ddgi_ctx* ctx, uint8_t* dst, size_t bytes);
 
 /* ---- probe rays: RVPT::generate_probe_rays (rvpt.h:63, rvpt.cpp:1177-1224) ---- */
-/* Generates the stratified sample set with libc rand() exactly as generate_samples
-   (rvpt.cpp:1147-1173) and keeps only the per-probe direction table on the device; the
-   kernel derives origin / direction / tile offset of ray k itself (no 48 B/ray read).
-   reseed != 0 calls srand(1) first (the state of a fresh process). */
+/* Generates the stratified sample set with libc rand() as generate_samples (rvpt.cpp:1147-1173)
+   and keeps only the per-probe direction table on the device; the kernel derives origin / direction /
+   tile offset of ray k itself (no 48 B/ray read).  reseed != 0 calls srand(1) first (the state of
+   a fresh process).  The reference draws a sample's two jitters as constructor arguments
+   (rvpt.cpp:1161-1162), whose evaluation order C++ leaves open: ddgi_set_sample_order(ctx, 0)
+   (default) draws x then y (SURVEY.md 8c-5's pin, what the committed fixtures hold),
+   ddgi_set_sample_order(ctx, 1) y then x - what g++, the reference's Linux toolchain, compiles that
+   line to; with it the ray list equals the one a g++ build of the reference generates, bit for bit. */
+DDGI_API int ddgi_set_sample_order(ddgi_ctx* ctx, int32_t y_first);
 DDGI_API int ddgi_generate_probe_rays(ddgi_ctx* ctx, int32_t reseed);
 /* Spherical-Fibonacci set of rx*ry directions (north-star ray generator; no reference counterpart —
    the reference draws the stratified rand() set above): cos(theta_i) = 1 - (2i+1)/n, azimuth
@@ -226,18 +232,47 @@ DDGI_API int ddgi_set_probes_cyclic(ddgi_ctx* ctx, int32_t rank, int32_t world, 
 /* Device address and size of probe texture `which` (0 albedo, 1 distance); both live in
    one allocation, albedo first, so one collective can move both. */
 DDGI_API int ddgi_probe_texture_device_ptr(ddgi_ctx* ctx, int32_t which, void** ptr, size_t* bytes);
-/* Fused exchange: 64-byte CUDA IPC handle of the texture allocation / open the peers'.
-   After ddgi_open_peers, ddgi_probe_update stores every texel into all replicas. */
+/* Fused exchange: 64-byte CUDA IPC handles of the texture allocation(s) / open the peers'.
+   After ddgi_open_peers, ddgi_probe_update stores every texel into all replicas.
+   ddgi_export_texture_handles writes *count = 1 handle, or 2 for a double-buffered context
+   (ddgi_set_double_buffer before exporting; ddgi_export_texture_handle is the single-buffer form);
+   ddgi_open_peers takes, rank by rank, as many handles per rank as this context exported - every rank
+   must be configured alike.  Double-buffered replicas are what lets ddgi_read_probe_texture_async
+   overlap the next update under the fused exchange: update i stores into allocation i & 1 of every
+   rank while frame i-1 is still being rendered or read from the other one. */
 DDGI_API int ddgi_export_texture_handle(ddgi_ctx* ctx, void* handle64);
+DDGI_API int ddgi_export_texture_handles(ddgi_ctx* ctx, void* handles, int32_t* count);
 DDGI_API int ddgi_open_peers(ddgi_ctx* ctx, int32_t n_peers, const void* handles64, int32_t self_index);
 DDGI_API int ddgi_close_peers(ddgi_ctx* ctx);
 /* Completion barrier of the fused exchange, on `stream` after ddgi_probe_update: publishes this
    rank's frame epoch in every peer's replica and waits (on the device) until every peer's epoch
    has arrived here, i.e. until their texels are in the local replica.  One small kernel, no
    collective library.  Every rank must call it once per frame.  A peer that does not arrive
-   within 5 s ends the wait (never a hang); ddgi_exchange_status reports it (synchronises). */
+   within 5 s ends the wait (never a hang); ddgi_exchange_status reports it (synchronises).
+   Frames never mix: with single-buffered replicas ddgi_probe_update itself issues a second barrier
+   in front of the kernel, so no rank stores frame i+1 into a replica whose owner has not yet issued
+   its own update i+1 - which its ddgi_render_frame / reads of frame i precede in stream order; with
+   double-buffered replicas frame i+1 goes to the other allocation and that barrier is not needed.
+   Either way render and read frame i on the SAME stream as the update, or through
+   ddgi_read_probe_texture_async (this barrier waits for the last asynchronous read of the
+   allocation the next update will write). */
 DDGI_API int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream);
 DDGI_API int ddgi_exchange_status(ddgi_ctx* ctx);
+
+/* The same exchange over NCCL (the collective SURVEY.md 8e names; what a deployment without CUDA IPC
+   between its processes uses).  libnccl.so.2 is bound at run time (dlopen), a single-GPU host does
+   not need it.  ddgi_comm_unique_id fills a 128-byte ncclUniqueId on one rank; the host passes it to
+   the others by its own means (MPI, a file, torch.distributed) and every rank calls ddgi_comm_init.
+   ddgi_exchange_allgather, on `stream` after ddgi_probe_update, moves the probe rows in place:
+   ONE ncclAllGather per plane for equal contiguous slabs (ddgi_set_probe_rows(rank*Y/world,
+   (rank+1)*Y/world), Y % world == 0: the send buffer is the rank's slab inside the receive buffer),
+   or one group of in-place ncclBroadcasts for block-cyclic rows (ddgi_set_probe_rows_cyclic).  The
+   distance plane travels only once something other than the reference's zeros has been stored in
+   it.  Not for probe-cyclic ownership (scattered tiles): DDGI_E_STATE. */
+DDGI_API int ddgi_comm_unique_id(void* id128);
+DDGI_API int ddgi_comm_init(ddgi_ctx* ctx, const void* id128, int32_t rank, int32_t world);
+DDGI_API int ddgi_comm_destroy(ddgi_ctx* ctx);
+DDGI_API int ddgi_exchange_allgather(ddgi_ctx* ctx, void* stream);
 
 /* Pixel pass across GPUs: every replica holds the whole probe texture after the exchange, so the
    frame splits into `world` bands of 16-pixel workgroup rows with no further collective; this
@@ -251,7 +286,8 @@ DDGI_API int ddgi_frame_band_rows(const ddgi_ctx* ctx, int32_t* y0, int32_t* y1)
 DDGI_API int ddgi_probe_update(ddgi_ctx* ctx, void* stream);
 /* vkCmdDispatch #2, compute_pass.comp (rvpt.cpp:1133-1140) */
 DDGI_API int ddgi_render_frame(ddgi_ctx* ctx, void* stream);
-/* raytrace_work_fence.wait (rvpt.cpp:277) */
+/* raytrace_work_fence.wait (rvpt.cpp:277): waits for the stream of this context's last dispatch and
+   for its asynchronous reads - not for the device (the caller's other streams keep running) */
 DDGI_API int ddgi_sync(ddgi_ctx* ctx);
 
 /* ---- results ---- */
@@ -267,14 +303,27 @@ DDGI_API int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, 
    stream, ordered after the update that produced it (dst should be pinned; it is valid after
    ddgi_read_wait); an update that is about to overwrite a buffer first waits, on the device, for
    the last asynchronous read of it (the next update but one; without double buffering the very
-   next update, so the asynchronous read is then correct but overlaps nothing).  Not with the fused
-   exchange (one mapped allocation per rank).  With partial probe ownership and no exchange the
-   texels a context does not own are one frame older in every other buffer. */
+   next update, so the asynchronous read is then correct but overlaps nothing).  Under the fused
+   exchange turn it on BEFORE exporting the handles (ddgi_export_texture_handles lists both
+   allocations).  With partial probe ownership and no exchange the texels a context does not own
+   are one frame older in every other buffer. */
 DDGI_API int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on);
 DDGI_API int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes);
 DDGI_API int ddgi_read_wait(ddgi_ctx* ctx);
 /* Uploads texture contents (checkpoint / resume, and pixel-pass tests). */
 DDGI_API int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size_t bytes);
+/* On-disk formats (the reference has none: its scene is compiled in and its texture
+   recomputed every frame).  Little-endian.
+   Voxel file: "DDGIVOX1", int32 dims[3] (x, y, z), int32 origin[3], dims product block types, x fastest.
+   ddgi_load_voxels uploads it as ddgi_upload_voxels would (palette may be NULL) and reports dims / origin
+   (either may be NULL).
+   Checkpoint: "DDGIPTX1", int32 W, int32 H, float time, albedo plane, distance plane (RGBA8 rows): the
+   state a hysteresis-blended texture carries from frame to frame, with the caller's render_settings.time.
+   ddgi_load_checkpoint needs the field of the dumped shape to be set already. */
+DDGI_API int ddgi_save_voxels(ddgi_ctx* ctx, const char* path);
+DDGI_API int ddgi_load_voxels(ddgi_ctx* ctx, const char* path, const float* palette, int32_t dims_out[3], int32_t origin_out[3]);
+DDGI_API int ddgi_save_checkpoint(ddgi_ctx* ctx, const char* path, float time);
+DDGI_API int ddgi_load_checkpoint(ddgi_ctx* ctx, const char* path, float* time_out);
 DDGI_API int ddgi_read_frame(ddgi_ctx* ctx, int32_t fmt, void* dst, size_t bytes);
 
 /* ---- instrumentation ---- */

@@ -1,6 +1,7 @@
 // glm/glm.hpp — TEST-ONLY stand-in for the few glm 0.9.9.8 types and functions the reference's
-// HOST ray generator uses (src/rvpt/rvpt.cpp:1145-1224, src/rvpt/probe.h), so that its own text
-// can be compiled where it lies (oracle/ref_glsl/build_ref.py: ref_generate_probe_rays).  glm is not
+// HOST code on the path uses (ray generator src/rvpt/rvpt.cpp:1145-1224, src/rvpt/probe.h, and the vec4 list
+// RVPT::update hands to the camera uniform), so that its own text can be compiled where it lies
+// (oracle/ref_glsl/build_ref.py: ref_generate_probe_rays; build_shim.py: rvpt_shim_main).  glm is not
 // in this image (external/CMakeLists.txt:21-25 fetches it from the network).  Semantics follow
 // glm's published definitions: component-wise operators, int -> float conversion on construction,
 // normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x),
@@ -52,6 +53,11 @@ struct vec3 {
         z += o.z;
         return *this;
     }
+};
+struct vec4 {
+    float x, y, z, w;
+    vec4() : x(0), y(0), z(0), w(0) {}
+    vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
 };
 inline vec3 operator*(const vec3& a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
 inline float dot(const vec3& a, const vec3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }

@@ -4,8 +4,15 @@
 //   host_main frame <scene> <X Y Z> <side> <s> <fx fy fz> <w h> <ox oy oz> <rx ry rz> <frames> <out.bin>
 //        generate_probe_rays / initialize / (update, draw) x frames; writes W, H, w, h (int32), the
 //        albedo probe texture and the frame (RGBA8)
+//   host_main shard <rank> <world> <device> <idfile> <out.bin>
+//        one process per GPU, Cornell with 2x4x2 probes: rank 0 writes an ncclUniqueId to <idfile>, every rank
+//        joins (ddgi_comm_init), updates its slab of probe rows, exchanges the texture in place over NCCL
+//        (ddgi_exchange_allgather) and writes the whole albedo texture; also round-trips a checkpoint file
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
 
 #include "rvpt_ddgi.hpp"
 
@@ -76,6 +83,80 @@ int main(int argc, char** argv)
         rvpt.shutdown();
         return 0;
     }
-    std::fprintf(stderr, "usage: host_main camera ... | frame ...\n");
+    if (argc >= 7 && !std::strcmp(argv[1], "shard")) {
+        int rank = atoi(argv[2]), world = atoi(argv[3]), device = atoi(argv[4]);
+        std::string idfile = argv[5];
+        const char* out = argv[6];
+        ddgi::RVPT rvpt(64, 64, device);
+        rvpt.scene_camera = ddgi::Camera(1.f, {0, 0, -5}, {0, 0, 0});
+        rvpt.render_settings.scene = 1;
+        rvpt.ir.probe_count[0] = 2;
+        rvpt.ir.probe_count[1] = 4;
+        rvpt.ir.probe_count[2] = 2;
+        rvpt.ir.side_length = 7;
+        rvpt.ir.sqrt_rays_per_probe = 8;
+        rvpt.ir.field_origin[0] = 0;
+        rvpt.ir.field_origin[1] = 0;
+        rvpt.ir.field_origin[2] = 15;
+        srand(1);
+        rvpt.generate_probe_rays();
+        if (!rvpt.initialize()) {
+            std::fprintf(stderr, "initialize failed: %s\n", rvpt.last_error().c_str());
+            return 2;
+        }
+        ddgi_ctx* ctx = rvpt.context();
+        unsigned char id[128];
+        if (rank == 0) {
+            if (ddgi_comm_unique_id(id) != DDGI_OK) {
+                std::fprintf(stderr, "ddgi_comm_unique_id failed (no libnccl.so.2?)\n");
+                return 6;
+            }
+            FILE* fp = std::fopen((idfile + ".tmp").c_str(), "wb");
+            if (!fp) return 4;
+            std::fwrite(id, 1, 128, fp);
+            std::fclose(fp);
+            std::rename((idfile + ".tmp").c_str(), idfile.c_str());
+        } else {
+            FILE* fp = nullptr;
+            for (int i = 0; i < 600 && !(fp = std::fopen(idfile.c_str(), "rb")); i++) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            if (!fp || std::fread(id, 1, 128, fp) != 128) return 4;
+            std::fclose(fp);
+        }
+        if (ddgi_comm_init(ctx, id, rank, world) != DDGI_OK) {
+            std::fprintf(stderr, "ddgi_comm_init: %s\n", ddgi_last_error(ctx));
+            return 6;
+        }
+        int Y = rvpt.ir.probe_count[1];
+        if (ddgi_set_probe_rows(ctx, rank * Y / world, (rank + 1) * Y / world) != DDGI_OK) return 3;
+        if (!rvpt.update()) return 3;
+        if (ddgi_probe_update(ctx, nullptr) != DDGI_OK || ddgi_exchange_allgather(ctx, nullptr) != DDGI_OK) {
+            std::fprintf(stderr, "update / exchange: %s\n", ddgi_last_error(ctx));
+            return 3;
+        }
+        ddgi_sync(ctx);
+        std::vector<uint32_t> tex = rvpt.read_probe_texture(0);
+        // checkpoint round trip through the C entry points
+        std::string ck = std::string(out) + ".ckpt";
+        float t = -1.f;
+        if (ddgi_save_checkpoint(ctx, ck.c_str(), rvpt.render_settings.time) != DDGI_OK) return 7;
+        std::vector<uint32_t> zero(tex.size(), 0u);
+        ddgi_write_probe_texture(ctx, 0, zero.data(), zero.size() * 4);
+        if (ddgi_load_checkpoint(ctx, ck.c_str(), &t) != DDGI_OK || t != rvpt.render_settings.time) return 7;
+        if (rvpt.read_probe_texture(0) != tex) return 7;
+        std::remove(ck.c_str());
+        int32_t W = 0, H = 0;
+        ddgi_probe_texture_size(ctx, &W, &H);
+        FILE* fp = std::fopen(out, "wb");
+        if (!fp) return 4;
+        int32_t hdr[4] = {W, H, rank, world};
+        std::fwrite(hdr, 4, 4, fp);
+        std::fwrite(tex.data(), 4, tex.size(), fp);
+        std::fclose(fp);
+        std::printf("ok rank %d of %d, %d probe rays\n", rank, world, (int)ddgi_num_probe_rays(ctx));
+        ddgi_comm_destroy(ctx);
+        rvpt.shutdown();
+        return 0;
+    }
+    std::fprintf(stderr, "usage: host_main camera ... | frame ... | shard ...\n");
     return 1;
 }

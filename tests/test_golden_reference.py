@@ -19,7 +19,7 @@ import util
 from oracle import oracle, ref
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("modes_"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("modes_", "full_")))
 
 
 def _scene(g, screen=None):
@@ -52,6 +52,35 @@ def test_oracle_reproduces_the_reference_shaders(path):
     assert np.array_equal(frame_lk, g["frame_lookups"])
     assert np.array_equal(frame_f32.view(np.uint32), g["frame_f32"].view(np.uint32))
     assert np.array_equal(frame, g["frame"])
+
+
+def test_oracle_reproduces_the_reference_shaders_on_cave_128_at_full_size():
+    """BASELINE.json configs[2] (16^3 probes x 256 rays, 1080p) with the reference's procedural scene and textures: all
+    1 048 576 probe rays and all 2 073 600 pixels of the oracle against the reference's own shaders run at full size
+    (tests/golden/full_cave_128.npz: CRC-32 / SHA-256 of the whole outputs, 94 probe tiles, 64 frame rows)."""
+    import hashlib
+    import zlib
+
+    g = np.load(os.path.join(HERE, "golden", "full_cave_128.npz"))
+    sc = _scene(dict(scene=0, s=g["s"], probe_count=g["probe_count"], side_length=g["side_length"], field_origin=g["field_origin"],
+                     screen=g["screen"]))
+    s = int(g["s"])
+    rays = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True))
+    alb, dist, f32, lk, _ = oracle.probe_update(sc, rays)
+    X, Y, Z = (int(v) for v in g["probe_count"])
+    tiles = alb.reshape(Y, s, X * Z, s).transpose(0, 2, 1, 3).reshape(X * Y * Z, s, s)
+    tiles_f32 = f32.reshape(Y, s, X * Z, s, 4).transpose(0, 2, 1, 3, 4).reshape(X * Y * Z, s, s, 4)
+    assert np.array_equal(tiles[g["probes"]], g["tiles"])
+    assert np.array_equal(tiles_f32[g["probes"]].view(np.uint32), g["tiles_f32"].view(np.uint32))
+    assert np.array_equal(lk.reshape(X * Y * Z, s * s)[g["probes"]], g["tile_lookups"])
+    assert int(lk.sum(dtype=np.uint64)) == int(g["lookups_sum"])
+    assert zlib.crc32(alb.tobytes()) == int(g["albedo_crc32"]) and hashlib.sha256(alb.tobytes()).hexdigest() == str(g["albedo_sha256"])
+    assert (dist == 0).all()
+    frame, _, flk = oracle.render_frame(sc, g["cam"], alb)
+    b0, b1 = (int(v) for v in g["band"])
+    assert np.array_equal(frame[b0:b1], g["frame_band"])
+    assert zlib.crc32(frame.tobytes()) == int(g["frame_crc32"]) and hashlib.sha256(frame.tobytes()).hexdigest() == str(g["frame_sha256"])
+    assert int(flk.sum(dtype=np.uint64)) == int(g["frame_lookups_sum"])
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

@@ -420,6 +420,10 @@ def test_field_32_full_size_sampled_parity_and_properties():
     # --- checksum of checksums (size-independent record of the frame)
     row_sums = full.astype(np.uint64).sum(axis=1)
     total = int((row_sums * (np.arange(H, dtype=np.uint64) + 1)).sum() % (1 << 61))
+    import json, os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "field_32.json")) as f:
+        recorded = json.load(f)
+    assert total == recorded["albedo_row_checksum"], "checksum of row checksums differs from the full-size oracle run"
     print(f"field_32 t=6: mean lookups/ray {mean_lookups:.3f}, checksum of row checksums {total}")
     assert (full >> 24 == 255).all()   # every texel was written (alpha = 1)
 

@@ -66,3 +66,43 @@ def test_cpp_host_main_loop_reproduces_the_reference_fixture(tmp_path):
     frame = raw[4 + W * H:].reshape(h, w)
     assert np.array_equal(tex, g["albedo"])
     assert np.array_equal(frame, g["frame"])
+
+
+def _run_shards(tmp_path, world):
+    idfile = str(tmp_path / "nccl.id")
+    outs = [str(tmp_path / f"rank{r}.bin") for r in range(world)]
+    procs = [subprocess.Popen([build(), "shard", str(r), str(world), str(r), idfile, outs[r]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
+    for r, p in enumerate(procs):
+        so, se = p.communicate(timeout=240)
+        assert p.returncode == 0, f"rank {r}: rc {p.returncode}\n{so}\n{se}"
+        assert so.startswith(f"ok rank {r} of {world}, 1024 probe rays")
+    import util
+    from oracle import oracle
+    cfg = dict(util.configs.CONFIGS["cornell_3x3x3"], probe_count=(2, 4, 2), side_length=7, screen=(64, 64))
+    sc = util.oracle_scene(cfg)
+    rays = oracle.generate_probe_rays(sc, oracle.generate_samples(8, 8, reseed=True))
+    want, *_ = oracle.probe_update(sc, rays)
+    for r in range(world):
+        raw = np.fromfile(outs[r], dtype=np.uint32)
+        W, H, rank, w = (int(v) for v in raw[:4].view(np.int32))
+        assert (H, W, rank, w) == (*want.shape, r, world)
+        assert np.array_equal(raw[4:].reshape(H, W), want), f"rank {r}: the exchanged texture differs from a full update"
+
+
+@pytest.mark.gpu
+def test_cpp_host_nccl_exchange_single_rank(tmp_path):
+    """ddgi_comm_unique_id / ddgi_comm_init / ddgi_exchange_allgather from compiled C++ with one rank (the in-place
+    all-gather of a 1-rank communicator), plus the checkpoint file round trip through the C entry points."""
+    _run_shards(tmp_path, 1)
+
+
+@pytest.mark.gpu
+def test_cpp_host_nccl_exchange_two_gpus(tmp_path):
+    """Two processes, two GPUs: each updates its slab of probe rows, ONE in-place ncclAllGather, every
+    rank ends with the texture a full update gives."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _run_shards(tmp_path, 2)
