@@ -6,7 +6,9 @@
 One step = one frame's probe update over the whole probe field: 4 dynamic lights are
 moved (host), every probe ray is traced (ddgi_probe_update) and, on N > 1 GPUs, the
 shards are exchanged (default: the kernel stores its texels into every replica over NVLink and a
-one-warp epoch-flag kernel is the completion barrier; --exchange nccl: in-place all-gathers).
+one-warp epoch-flag kernel is the completion barrier; --exchange nccl: the engine's in-place
+ncclAllGather, ddgi_exchange_allgather; the fused run also times the NCCL exchange and prints it
+as `exchange_nccl`).
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field; --verify (N > 1)
 checks every replica against a full single-GPU update.
 """
@@ -111,6 +113,77 @@ def run_reference(args, cfg_name):
     print(json.dumps(reference_arm(args, cfg_name)), flush=True)
 
 
+# ----------------------------------------------------------------------------- live ncu pass
+NCU_METRICS = ("dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,"
+               "smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,gpu__time_duration.sum")
+
+
+def traffic_probe(args):
+    """`bench.py --traffic-probe`: the workload's probe update a few times and nothing else - what the ncu pass
+    below profiles (no torch: the engine alone)."""
+    import importlib
+
+    import ddgi_b200
+    from bench_support import workload_config
+
+    configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
+    cfg = workload_config(args.workload)
+    r = ddgi_b200.RVPT(*cfg["screen"])
+    configs.apply(r, cfg, time=0.0)
+    r.generate_probe_rays(reseed=True)
+    r.set_kernel_variant(args.variant)
+    r.update(advance_time=False)
+    for i in range(5):
+        r.render_settings.time = 2.0 * (i + 1)
+        r.lights = configs.lights_for(cfg, r.render_settings.time)
+        r.update(advance_time=False)
+        r.probe_update()
+    r.sync()
+    r.close()
+
+
+def ncu_pass(args, n_rays):
+    """DRAM traffic, issue-slot utilisation and active lanes per instruction of ONE launch of the probe-update kernel,
+    measured now by running this script's --traffic-probe mode under ncu (the 5th launch: schedule calibrated, caches
+    warm as in the timed loop).  Profiler numbers explain the kernel; they are never the bench value.  None if ncu is
+    missing or fails."""
+    import csv
+    import io
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    kernel = "probe_update_wavefront" if args.variant != 0 else "probe_update_direct"
+    cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "-k", f"regex:{kernel}", "-s", "4", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--traffic-probe", "--workload", args.workload, "--variant", str(args.variant)]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+    except Exception:
+        return None
+    vals = {}
+    rows = [l for l in p.stdout.splitlines() if l.startswith('"')]
+    for row in csv.reader(io.StringIO("\n".join(rows))):
+        if len(row) >= 3 and row[-3] in NCU_METRICS:
+            try:
+                v = float(row[-1].replace(",", ""))
+            except ValueError:
+                continue
+            unit = row[-2]
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,   # bytes; durations in ms
+                    "ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}
+            vals[row[-3]] = v * mult.get(unit, 1.0)
+    if "dram__bytes_read.sum" not in vals:
+        return None
+    inst = vals.get("smsp__inst_executed.sum")
+    return {"dram_bytes_per_launch": vals["dram__bytes_read.sum"] + vals.get("dram__bytes_write.sum", 0.0),
+            "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "lanes_per_inst": vals.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "warp_inst_per_ray": inst / n_rays if inst else None,
+            "kernel_ms_under_ncu": vals.get("gpu__time_duration.sum"),
+            "how": "ncu --metrics ... -k regex:" + kernel + " -s 4 -c 1 on `bench.py --traffic-probe` (this run)"}
+
+
 # ----------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -119,24 +192,28 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="field_32")
-    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused", "fused-nccl-barrier"],
-                    help="N > 1: fused = the kernel stores texels into every replica over NVLink, then a device-side epoch-flag "
-                         "barrier (no collective library on the data path); fused-nccl-barrier = the same stores with a 4-byte "
-                         "NCCL all-reduce as the barrier; nccl = in-place all-gathers")
-    ap.add_argument("--sharding", default="cyclic", choices=["cyclic", "slab"],
-                    help="N > 1: cyclic ownership (single probes with the fused exchange, blocks of probe rows with nccl) "
-                         "or one contiguous slab of probe rows per rank")
-    ap.add_argument("--variant", type=int, default=1)
+    ap.add_argument("--exchange", default="fused", choices=["nccl", "fused"],
+                    help="N > 1: fused = the kernel stores texels into every replica over NVLink (double-buffered replicas), then a "
+                         "device-side epoch-flag barrier (no collective library on the data path); nccl = the engine's in-place "
+                         "all-gather (ddgi_exchange_allgather)")
+    ap.add_argument("--sharding", default=None, choices=["cyclic", "slab"],
+                    help="N > 1: cyclic ownership (single probes with the fused exchange, blocks of probe rows with nccl) or one "
+                         "contiguous slab of probe rows per rank (default: cyclic for fused, slab for nccl)")
+    ap.add_argument("--variant", type=int, default=2)
     ap.add_argument("--march-min", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu pass (roofline.traffic falls back to profiles/traffic.json)")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--verify", action="store_true",
                     help="N > 1: after the timed run, check that every rank's replica of both texture planes equals a full "
                          "single-GPU update of the same frame (untimed)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.traffic_probe:
+        return traffic_probe(args)
 
     if args.impl == "reference":
         run_reference(args, args.workload)
@@ -160,6 +237,8 @@ def main():
     import importlib
 
     configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
+    fused = args.exchange == "fused"
+    sharding = args.sharding or ("cyclic" if fused else "slab")
 
     r = ddgi_b200.RVPT(*cfg["screen"], device=local)
     configs.apply(r, cfg, time=0.0)
@@ -170,71 +249,74 @@ def main():
     r.update(advance_time=False)
     stream = torch.cuda.current_stream()
     r.stream = stream.cuda_stream
+    # updates alternate between two texture allocations: frame i can be rendered / copied out while frame i+1 is
+    # traced - on one GPU and, with both allocations mapped by the peers, under the fused exchange
+    r.set_double_buffer(True)
 
     X, Y, Z = cfg["probe_count"]
     rx, ry = cfg["tile"]
     n_rays = X * Y * Z * rx * ry
     W, H = r.probe_texture_size
+    nbytes = W * H * 4
     sh = ddgi_b200.sharding
     n_probes = X * Y * Z
-    probe_owner = np.zeros(n_probes, dtype=np.int32)   # rank that updates each probe
-    block = 0
-    slab = sh.probe_row_shard(Y, rank, world)           # the rows a rank reads back (e2e) in any mode
-    fused = args.exchange.startswith("fused")
-    if world > 1 and args.sharding == "cyclic" and fused:
-        r.set_probes_cyclic(rank, world, 1)
-        probe_owner = (np.arange(n_probes) % world).astype(np.int32)
-        shard_desc = f"{n_probes} probes dealt round-robin to {world} ranks"
-    elif world > 1 and args.sharding == "cyclic":
-        block = sh.cyclic_block(Y, world)
-        r.set_probe_rows_cyclic(rank, world, block)
-        probe_owner = np.repeat((np.arange(Y) // block) % world, X * Z).astype(np.int32)
-        shard_desc = f"probe rows {Y}/{world}, block-cyclic (block {block})"
-    else:
+    row_bytes = W * 4 * ry
+    slab = sh.probe_row_shard(Y, rank, world)           # the probe rows a rank reads back (e2e) in any mode
+
+    def set_ownership(kind):
+        """-> (rank of every probe, description)"""
+        owner = np.zeros(n_probes, dtype=np.int32)
+        if world == 1:
+            return owner, "none"
+        if kind == "probes":
+            r.set_probes_cyclic(rank, world, 1)
+            return (np.arange(n_probes) % world).astype(np.int32), f"{n_probes} probes dealt round-robin to {world} ranks"
+        if kind == "rows":
+            block = sh.cyclic_block(Y, world)
+            r.set_probe_rows_cyclic(rank, world, block)
+            return np.repeat((np.arange(Y) // block) % world, X * Z).astype(np.int32), f"probe rows {Y}/{world}, block-cyclic (block {block})"
         r.set_probe_rows(*slab)
         for g in range(world):
             a, b = sh.probe_row_shard(Y, g, world)
-            probe_owner[a * X * Z:b * X * Z] = g
-        shard_desc = f"probe rows {Y}/{world}, contiguous slabs"
+            owner[a * X * Z:b * X * Z] = g
+        return owner, f"probe rows {Y}/{world}, contiguous slabs"
+
+    probe_owner, shard_desc = set_ownership("slab" if sharding == "slab" else ("probes" if fused else "rows"))
     owned_probes = probe_owner == rank
 
-    # the probe texture as a torch tensor (for the NCCL exchange)
-    ptr, nbytes = r.probe_texture_device_ptr(0)
-    tex = torch.as_tensor(DevPtr(ptr, 2 * nbytes), device=f"cuda:{local}")
-    planes = [tex[:nbytes], tex[nbytes:]]
-    row_bytes = W * 4 * ry
+    def join_nccl():
+        ids = [ddgi_b200.RVPT.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        r.comm_init(ids[0], rank, world)
 
     if world > 1 and fused:
         handles = [None] * world
-        dist.all_gather_object(handles, r.export_texture_handle())
+        dist.all_gather_object(handles, r.export_texture_handle())   # both allocations of the double-buffered context
         r.open_peers(handles, rank)
-    sync_flag = torch.zeros(1, device=f"cuda:{local}")
+    elif world > 1:
+        join_nccl()
 
     def exchange():
         if world == 1:
             return
-        if args.exchange == "fused":
+        if fused:
             # texels were stored into every replica by the kernel; the completion barrier is a
             # one-warp kernel exchanging epoch flags through the same peer mappings
             r.exchange_barrier()
-            return
-        if fused:
-            dist.all_reduce(sync_flag)  # the same, with a 4-byte NCCL all-reduce as the barrier
-            return
-        for pl in planes:
-            if block:
-                sh.allgather_probe_rows_cyclic(pl, Y, row_bytes, rank, world, block)
-            else:
-                sh.allgather_probe_rows(pl, Y, row_bytes, rank, world)
+        else:
+            r.exchange_allgather()   # ncclAllGather (slabs) / grouped ncclBroadcast (block-cyclic rows), in place
 
     frame_no = [0]
 
-    def step():
-        # update_lights: 4 dynamic lights, time += 2 per frame (rvpt.cpp:281)
+    def prep():
+        # update_lights: 4 dynamic lights, time += 2 per frame (rvpt.cpp:281); host work only
         frame_no[0] += 1
         r.render_settings.time = 2.0 * frame_no[0]
         r.lights = configs.lights_for(cfg, r.render_settings.time)
         r.update(advance_time=False)
+
+    def step():
+        prep()
         r.probe_update()
         exchange()
 
@@ -250,39 +332,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n_steps, warm):
+        """-> (ms per step, kernel ms per step), device-timed, max over ranks, L2 flushed between steps"""
+        for _ in range(warm):
+            flush_l2()
+            step()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+                torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        barrier()
+        for a, m, b in evs:
+            flush_l2()
+            a.record(stream)
+            prep()
+            r.probe_update()
+            m.record(stream)
+            exchange()
+            b.record(stream)
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, m, b in evs) / n_steps, sum(a.elapsed_time(m) for a, m, b in evs) / n_steps],
+                         device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    sampler = ClockSampler(local)
     for _ in range(args.warmup):
         flush_l2()
         step()
     barrier()
-
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = r.launch_count
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, m, b in evs:
-        flush_l2()
-        a.record(stream)
-        frame_no[0] += 1
-        r.render_settings.time = 2.0 * frame_no[0]
-        r.lights = configs.lights_for(cfg, r.render_settings.time)
-        r.update(advance_time=False)
-        r.probe_update()
-        m.record(stream)
-        exchange()
-        b.record(stream)
-    barrier()
+    ms_per_step, kernel_ms = timed(args.steps, 0)
     launches = r.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, m, b in evs)
-    kernel_ms = sum(a.elapsed_time(m) for a, m, b in evs) / args.steps
-    t = torch.tensor([total_ms, kernel_ms], device=f"cuda:{local}", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms = float(t[0]), float(t[1])
-    ms_per_step = total_ms / args.steps
     value = n_rays / (ms_per_step * 1e-3)
 
     # ---- FPS at the config's resolution: probe update + exchange + pixel pass.  On N > 1 GPUs every
@@ -309,16 +393,30 @@ def main():
     frame_ms = float(ft[0])
     pixel_ms = pa.elapsed_time(pb)
 
-    # ---- algorithmic bytes: voxel lookups counted by the instrumented kernel (untimed) ----
+    # ---- algorithmic bytes: the voxel lookups of the REFERENCE ALGORITHM per ray, counted by the instrumented kernel in
+    #      variant 1 (every lookup the reference performs; the default variant 2 ends shadow feelers early and performs
+    #      fewer - SURVEY 8d: result-preserving early-outs do not reduce the algorithmic figure).  Untimed. ----
     r.set_debug(True)
+    r.set_kernel_variant(1 if args.variant == 2 else args.variant)
     r.probe_update()
+    exchange()
     r.sync()
-    per_row = X * Z * rx * ry
     lk_all = r.read_lookup_counts(0).reshape(n_probes, rx * ry)
     lk_sum = torch.tensor([float(lk_all[owned_probes].sum(dtype=np.float64))], device=f"cuda:{local}", dtype=torch.float64)
+    performed = None
+    if args.variant == 2:
+        r.set_kernel_variant(2)
+        r.probe_update()
+        exchange()
+        r.sync()
+        performed = torch.tensor([float(r.read_lookup_counts(0).reshape(n_probes, rx * ry)[owned_probes].sum(dtype=np.float64))],
+                                 device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(lk_sum)
+        if performed is not None:
+            dist.all_reduce(performed)
     mean_lookups = float(lk_sum[0]) / n_rays
+    r.set_kernel_variant(args.variant)
     r.set_debug(False)
     bytes_per_ray = 4.0 * mean_lookups + 8.0
     peak, peak_src = load_peaks()
@@ -326,74 +424,50 @@ def main():
     achieved = rays_this_rank * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
 
     # ---- e2e through the C-ABI with host buffers (pinned), per step:
-    #      H2D: ray-sample table + uniforms/lights; D2H: the rank's albedo rows ----
+    #      H2D: ray-sample table + uniforms/lights; D2H: the rank's share of the albedo plane.
+    #      The texture is double-buffered in the engine (under the fused exchange both allocations are mapped by the
+    #      peers), so the D2H of step i (asynchronous, on the engine's copy stream, into one of two pinned buffers)
+    #      overlaps the trace of step i+1 at every N; every step's rows are still read back inside the timed region ----
     e2e = None
     if not args.no_e2e:
         samples = r.ray_samples       # the stratified sample table generate_samples drew
-        rays_host = r.probe_rays      # the reference's std::vector<ProbeRay>
         pinned_samples = torch.from_numpy(samples).pin_memory()
-        host_tex = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         lib = ddgi_b200.capi.load()
         h2d = pinned_samples.numel() * 4 + 32 + 48 + 80 + 4 * 28
-        d2h = nbytes if world == 1 else (slab[1] - slab[0]) * row_bytes
-
-        # 1 GPU: the texture is double-buffered in the engine, so the D2H of step i (asynchronous, on the
-        # engine's copy stream, into one of two pinned buffers) overlaps the trace of step i+1; every
-        # step's whole albedo plane is still read back inside the timed region (read_wait at its end)
-        pipelined = world == 1
-        host_pair = [host_tex, torch.empty(nbytes, dtype=torch.uint8).pin_memory()] if pipelined else [host_tex]
-        if pipelined:
-            r.set_double_buffer(True)
-
-        def e2e_prep():
-            # host side of a step: move the lights, rebuild and hand over the uniforms (no device work)
-            frame_no[0] += 1
-            r.render_settings.time = 2.0 * frame_no[0]
-            r.lights = configs.lights_for(cfg, r.render_settings.time)
-            r.update(advance_time=False)
+        rows = (0, H) if world == 1 else (slab[0] * ry, slab[1] * ry)
+        d2h = (rows[1] - rows[0]) * W * 4
+        host_pair = [torch.empty(max(d2h, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
 
         def e2e_step():
-            if pipelined:
-                e2e_prep()   # overlaps the previous step's trace; set_ray_samples then waits for that trace
+            prep()   # host side; overlaps the previous step's trace (set_ray_samples then waits for that trace)
             rc = lib.ddgi_set_ray_samples(r._ctx, pinned_samples.data_ptr(), rx * ry)
             assert rc == 0
             r.probe_update()
             exchange()
-            if pipelined:
-                r.read_probe_texture_async(host_pair[frame_no[0] & 1].data_ptr(), nbytes, 0)
-            else:
-                # every replica is complete after the exchange: each rank reads back 1/N of the albedo plane;
-                # the next step's host-side uniforms are prepared while this step runs on the device
-                host_tex[:d2h].copy_(planes[0][slab[0] * row_bytes:slab[1] * row_bytes], non_blocking=True)
-                e2e_prep()
-                torch.cuda.current_stream().synchronize()
+            r.read_probe_texture_rows_async(host_pair[frame_no[0] & 1].data_ptr(), rows[0], rows[1], d2h, 0)
 
-        if not pipelined:
-            e2e_prep()
         for _ in range(3):
             e2e_step()
-        if pipelined:
-            r.read_wait()
+        r.read_wait()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
-        if pipelined:
-            r.read_wait()
+        r.read_wait()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local}", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if pipelined:
-            r.set_double_buffer(False)
         e2e = {"value": n_rays * args.steps / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "inputs": "ray-sample table + uniforms + lights (pinned host)",
                "result": "albedo probe texture rows of this rank (pinned host)",
-               "pipelining": "double-buffered texture: the D2H of step i overlaps the trace of step i+1" if pipelined else "none"}
+               "pipelining": "double-buffered texture (replicas mapped pairwise under the fused exchange): the D2H of step i overlaps the trace of step i+1"}
         # literal storage-buffer mode: the whole ProbeRay array re-uploaded every frame, as
         # RVPT::update does (rvpt.cpp:285)
         if world == 1:
+            rays_host = r.probe_rays      # the reference's std::vector<ProbeRay>
             pinned_rays = torch.from_numpy(rays_host).pin_memory()
+            host_tex = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
             def ssbo_step():
                 frame_no[0] += 1
@@ -416,29 +490,67 @@ def main():
                                 "h2d_bytes_per_step": int(n_rays * 48 + 160), "d2h_bytes_per_step": int(nbytes)}
             r.generate_probe_rays(reseed=True)
 
+    def replica():
+        ptr, nb = r.probe_texture_device_ptr(0)   # (the current allocation: it alternates)
+        return torch.as_tensor(DevPtr(ptr, 2 * nb), device=f"cuda:{local}")
+
     # ---- untimed: the exchanged replicas against a full local update of the same frame ----
     verify = None
     if args.verify and world > 1:
         step()
         barrier()
-        got = tex.clone()
+        got = replica().clone()
         if fused:
-            if args.exchange == "fused":
-                r.exchange_status()
+            r.exchange_status()   # raises if any barrier timed out
             r.close_peers()
-        r.set_probe_rows(0, Y)
+            fused = False
+        r.set_probe_rows(0, Y)    # this rank alone, every probe, the same frame (lights unchanged since step())
         r.probe_update()
         barrier()
-        ok = torch.tensor([1 if torch.equal(got, tex) else 0], device=f"cuda:{local}")
+        ok = torch.tensor([1 if torch.equal(got, replica()) else 0], device=f"cuda:{local}")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         verify = {"replicas_equal_full_update": bool(int(ok[0])), "bytes_compared_per_rank": int(got.numel())}
-        fused = False  # peers are closed
+
+    # ---- N > 1, fused default: the same workload once more with the engine's NCCL exchange (contiguous slabs, ONE
+    #      in-place ncclAllGather per plane through ddgi_exchange_allgather), device-timed like the headline ----
+    exchange_nccl = None
+    if world > 1 and args.exchange == "fused":
+        if fused:
+            r.exchange_status()
+            barrier()
+            r.close_peers()
+            fused = False
+        if Y % world == 0:
+            join_nccl()
+            set_ownership("slab")
+            n_nccl = max(3, min(args.steps, 10))
+            ms_nccl, kernel_ms_nccl = timed(n_nccl, 3)
+            exchange_nccl = {"value": n_rays / (ms_nccl * 1e-3), "unit": UNIT, "ms_per_step": ms_nccl, "kernel_ms": kernel_ms_nccl,
+                             "steps": n_nccl, "exchange": "nccl: contiguous slabs of probe rows, one in-place ncclAllGather per plane "
+                                                          "(ddgi_exchange_allgather; the distance plane only holds zeros and is skipped)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r.set_double_buffer(False)
         cpu = cpu_baseline(r, cfg, args.workload)
+    prof = None
+    if rank == 0 and world == 1 and not args.no_ncu:
+        prof = ncu_pass(args, n_rays)
 
     if rank == 0:
+        traffic, traffic_src = None, None
+        if prof:
+            traffic, traffic_src = prof["dram_bytes_per_launch"], prof["how"]
+        elif world == 1:
+            traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(traffic_file):
+                try:
+                    with open(traffic_file) as f:
+                        tj = json.load(f)
+                    if tj.get("workload") == args.workload:
+                        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/traffic.json (committed ncu capture, not this run)"
+                except Exception:
+                    pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -453,29 +565,24 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "probe_update_wavefront" if args.variant == 1 else "probe_update_direct",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "probe_update_wavefront" if args.variant != 0 else "probe_update_direct",
                          "kernel_ms": kernel_ms, "bytes_per_ray": bytes_per_ray, "mean_lookups_per_ray": mean_lookups,
-                         "note": "algorithmic bytes = rays x (4 B x voxel lookups of the reference algorithm + 8 B texel stores), SURVEY 8d"},
+                         "lookups_performed_per_ray": (float(performed[0]) / n_rays) if performed is not None else mean_lookups,
+                         "note": "algorithmic bytes = rays x (4 B x voxel lookups of the reference algorithm + 8 B texel stores), SURVEY 8d; "
+                                 "the kernel is bound by instruction issue, not by HBM: see `issue`"},
+            "issue": None if not prof else {k: prof[k] for k in ("issue_active_pct", "lanes_per_inst", "warp_inst_per_ray", "kernel_ms_under_ncu", "how")},
             "cpu_baseline": cpu,
             "verify": verify,
+            "exchange_nccl": exchange_nccl,
             "fps": {"value": 1000.0 / frame_ms, "frame_ms": frame_ms, "pixel_pass_ms": pixel_ms,
                     "resolution": list(cfg["screen"]), "pixel_rows_rank0": list(band),
                     "note": "probe update + exchange + pixel pass; pixel rows split across ranks"},
         }
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                with open(traffic_file) as f:
-                    tj = json.load(f)
-                if tj.get("workload") == args.workload:
-                    out["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
-            except Exception:
-                pass
         print(json.dumps(out), flush=True)
     if world > 1:
         if fused:
-            if args.exchange == "fused":
-                r.exchange_status()  # raises if any barrier timed out
+            r.exchange_status()  # raises if any barrier timed out
             r.close_peers()
         dist.barrier()
         dist.destroy_process_group()

@@ -141,6 +141,7 @@ PROTOTYPES = {
     "ddgi_read_probe_texture": (C.c_int, [_P, _I32, _I32, _P, _SZ]),
     "ddgi_set_double_buffer": (C.c_int, [_P, _I32]),
     "ddgi_read_probe_texture_async": (C.c_int, [_P, _I32, _P, _SZ]),
+    "ddgi_read_probe_texture_rows_async": (C.c_int, [_P, _I32, _I32, _I32, _P, _SZ]),
     "ddgi_read_wait": (C.c_int, [_P]),
     "ddgi_write_probe_texture": (C.c_int, [_P, _I32, _P, _SZ]),
     "ddgi_read_frame": (C.c_int, [_P, _I32, _P, _SZ]),

@@ -83,6 +83,7 @@ struct ddgi_ctx {
     int cur_tex = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // last asynchronous read of each buffer
+    cudaEvent_t ev_ready = nullptr;                 // what an asynchronous read waits for on the dispatch stream
     float4* d_tex_f32 = nullptr;
     uint32_t* d_ray_lookups = nullptr;
     size_t ray_lookups_cap = 0;  // rays d_ray_lookups was allocated for
@@ -509,6 +510,7 @@ void ddgi_destroy(ddgi_ctx* ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int b = 0; b < 2; b++)
         if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     dfree(ctx->d_tex_f32);
     dfree(ctx->d_ray_lookups);
     dfree(ctx->d_frame);
@@ -1585,20 +1587,32 @@ int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on)
     return DDGI_OK;
 }
 
-int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes)
+int ddgi_read_probe_texture_rows_async(ddgi_ctx* ctx, int32_t which, int32_t row0, int32_t row1, void* dst, size_t bytes)
 {
     if (!ctx) return DDGI_E_INVALID;
     NEED(ctx->d_tex, "no probe texture");
-    NEED(dst && (which == 0 || which == 1) && bytes == tex_texels(ctx) * 4, "expected width*height*4 bytes");
+    NEED(dst && (which == 0 || which == 1) && row0 >= 0 && row0 <= row1 && row1 <= ctx->tex_h, "bad rows");
+    NEED(bytes == (size_t)(row1 - row0) * ctx->tex_w * 4, "expected (row1 - row0) * width * 4 bytes");
     CU(cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int b = ctx->cur_tex;
     if (!ctx->ev_copied[b]) CU(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
-    // after the probe update that produced this buffer, on the engine's own copy stream
-    if (ctx->ev_update) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_update, 0));
-    CU(cudaMemcpyAsync(dst, ctx->d_tex + (which ? tex_texels(ctx) : 0), bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    // after everything the dispatch stream has been given so far (the update that produced this buffer and,
+    // under an exchange, the barrier / collective that completed it), on the engine's own copy stream
+    if (!ctx->ev_ready) CU(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_ready, ctx->last_stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
+    const uint32_t* src = ctx->d_tex + (which ? tex_texels(ctx) : 0) + (size_t)row0 * ctx->tex_w;
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
     return DDGI_OK;
+}
+
+int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(bytes == tex_texels(ctx) * 4, "expected width*height*4 bytes");
+    return ddgi_read_probe_texture_rows_async(ctx, which, 0, ctx->tex_h, dst, bytes);
 }
 
 int ddgi_read_wait(ddgi_ctx* ctx)

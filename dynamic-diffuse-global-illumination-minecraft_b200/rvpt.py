@@ -301,6 +301,10 @@ class RVPT:
         """Enqueues the copy of the latest frame into (pinned) host memory at out_ptr; valid after read_wait()."""
         self._check(self._lib.ddgi_read_probe_texture_async(self._ctx, which, out_ptr, nbytes))
 
+    def read_probe_texture_rows_async(self, out_ptr: int, row0: int, row1: int, nbytes: int, which: int = 0):
+        """The same for texture rows [row0, row1), ordered after this frame's exchange too."""
+        self._check(self._lib.ddgi_read_probe_texture_rows_async(self._ctx, which, row0, row1, out_ptr, nbytes))
+
     def read_wait(self):
         self._check(self._lib.ddgi_read_wait(self._ctx))
 

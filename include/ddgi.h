@@ -309,6 +309,10 @@ DDGI_API int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, 
    are one frame older in every other buffer. */
 DDGI_API int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on);
 DDGI_API int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes);
+/* The same for texture rows [row0, row1) only (a rank's share of the replica it holds after an exchange);
+   ordered after everything given to the dispatch stream so far, i.e. also after ddgi_exchange_barrier /
+   ddgi_exchange_allgather of this frame. */
+DDGI_API int ddgi_read_probe_texture_rows_async(ddgi_ctx* ctx, int32_t which, int32_t row0, int32_t row1, void* dst, size_t bytes);
 DDGI_API int ddgi_read_wait(ddgi_ctx* ctx);
 /* Uploads texture contents (checkpoint / resume, and pixel-pass tests). */
 DDGI_API int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size_t bytes);
