@@ -234,10 +234,21 @@ DDGI_HD uint32_t pack_rgba8(float r, float g, float b, float a)
 {
     return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(a) << 24);
 }
+// imageLoad of an rgba8 texel: byte / 255.0f.  The IEEE division is replaced by the FMA-corrected
+// reciprocal form (q = b*r, q += (b - 255 q) r with r = RN(1/255)), which returns the same float for each
+// of the 256 possible bytes - checked exhaustively by tests/test_oracle_math.py; the pixel pass unpacks
+// up to 8 x 26 x 3 channels per pixel.
+DDGI_HD float unorm8_to_float(uint32_t b)
+{
+    const float r = 0.0039215688593685627f;  // RN(1 / 255)
+    float x = (float)b;
+    float q = x * r;
+    float e = fmaf(-255.0f, q, x);
+    return fmaf(e, r, q);
+}
 DDGI_HD v3 unpack_rgb8(uint32_t v)
 {
-    return V3((float)(v & 255u) / 255.0f, (float)((v >> 8) & 255u) / 255.0f,
-              (float)((v >> 16) & 255u) / 255.0f);
+    return V3(unorm8_to_float(v & 255u), unorm8_to_float((v >> 8) & 255u), unorm8_to_float((v >> 16) & 255u));
 }
 
 }  // namespace ddgi

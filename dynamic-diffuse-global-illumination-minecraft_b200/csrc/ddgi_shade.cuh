@@ -37,35 +37,48 @@ DDGI_HD v3 sample_tile_oct(const FrameParams& P, const uint32_t* tex, int W, int
     return oct_sample_tile(tex, W, cx, cy, P.oct, dir);
 }
 
-// Direction -> texel of the probe tile, then the mean of the centre texel plus the
-// in-tile part of the 5x5 window around it (centre counted twice).  `taps` is the image the
-// window is read from: the albedo texture, or the distance texture for texture_to_sample = 1 —
-// the centre texel comes from the ALBEDO texture either way (intersection.glsl:1213).
-DDGI_HD v3 sample_tile(const FrameParams& P, const uint32_t* tex, const uint32_t* taps, int W, int p, v3 dir)
+// Direction -> texel of a probe tile (intersection.glsl:1196-1207): depends on the direction alone, so the
+// cage sample evaluates it ONCE for its eight probes (the reference recomputes it, acos included, per probe).
+DDGI_HD void tile_texel(const FrameParams& P, v3 dir, int* relx, int* rely)
 {
     const float pi = 3.1415926535897932384626433832795f;
+    v3 d = normalize(dir);
+    *relx = f2i(((-1.0f * (d.z - 1.0f)) / 2.0f) * (float)P.rx);
+    if (*relx == P.rx) *relx = 0;
+    float sq = sqrtf(1.0f - (d.z * d.z));
+    *rely = f2i((pin_acos(d.x / sq) / (2.0f * pi)) * (float)P.ry);
+}
+
+// The mean of the centre texel plus the in-tile part of the 5x5 window around it (centre counted
+// twice).  `taps` is the image the window is read from: the albedo texture, or the distance texture for
+// texture_to_sample = 1 — the centre texel comes from the ALBEDO texture either way (intersection.glsl:1213).
+DDGI_HD v3 gather_tile(const FrameParams& P, const uint32_t* tex, const uint32_t* taps, int W, int p, int relx, int rely)
+{
     int cx, cy;
     tile_origin(P, p, &cx, &cy);
     if (cx == -1 && cy == -1) return V3(1, 0, 1);
-    v3 d = normalize(dir);
-    int relx = f2i(((-1.0f * (d.z - 1.0f)) / 2.0f) * (float)P.rx);
-    if (relx == P.rx) relx = 0;
-    float sq = sqrtf(1.0f - (d.z * d.z));
-    int rely = f2i((pin_acos(d.x / sq) / (2.0f * pi)) * (float)P.ry);
     int sx = cx + relx, sy = cy + rely;
     v3 sum = unpack_rgb8(tex[(size_t)sy * W + sx]);
+    // the in-tile part of the window [-2, 2]^2 around (relx, rely): the same taps in the same order as the
+    // reference's two loops with their four range tests per tap (intersection.glsl:1218-1236)
+    const int x0 = relx < 2 ? -relx : -2, x1 = relx + 2 > P.rx - 1 ? P.rx - 1 - relx : 2;
+    const int y0 = rely < 2 ? -rely : -2, y1 = rely + 2 > P.ry - 1 ? P.ry - 1 - rely : 2;
     int count = 0;
-    for (int x = -2; x <= 2; x++) {
-        int tx = sx + x;
-        if (tx < cx || tx >= cx + P.rx) continue;
-        for (int y = -2; y <= 2; y++) {
-            int ty = sy + y;
-            if (ty < cy || ty >= cy + P.ry) continue;
+    for (int x = x0 < -2 ? -2 : x0; x <= x1; x++) {
+        const uint32_t* col = taps + (size_t)(sy + (y0 < -2 ? -2 : y0)) * W + (sx + x);
+        for (int y = y0 < -2 ? -2 : y0; y <= y1; y++) {
             count++;
-            sum = sum + unpack_rgb8(taps[(size_t)ty * W + tx]);
+            sum = sum + unpack_rgb8(*col);
+            col += W;
         }
     }
     return sum / (float)count;
+}
+DDGI_HD v3 sample_tile(const FrameParams& P, const uint32_t* tex, const uint32_t* taps, int W, int p, v3 dir)
+{
+    int relx, rely;
+    tile_texel(P, dir, &relx, &rely);
+    return gather_tile(P, tex, taps, W, p, relx, rely);
 }
 
 // pow(x, 3) of intersection.glsl:1379: the cube in fp64 rounded once (oracle PIN 11)
@@ -95,6 +108,8 @@ DDGI_HD v3 cage_irradiance(const FrameParams& P, const uint32_t* tex, const uint
     int X = P.probe_count[0], Y = P.probe_count[1], Z = P.probe_count[2];
     v3 irradiance = V3(0, 0, 0);
     float sum_w = 0.0f;
+    int relx = 0, rely = 0;
+    if (!(kExt && P.layout == 1)) tile_texel(P, N, &relx, &rely);  // the same texel of every probe's tile
     for (int i = 0; i < 8; i++) {
         int ox = (i >> 2) & 1, oy = (i >> 1) & 1, oz = i & 1;
         int sx = base[0] + ox + X / 2, sy = base[1] + oy + Y / 2, sz = base[2] + oz + Z / 2;
@@ -124,7 +139,7 @@ DDGI_HD v3 cage_irradiance(const FrameParams& P, const uint32_t* tex, const uint
         const float crush = 0.2f;
         if (w < crush) w *= w * w * (1.f / (crush * crush));
         w *= tri.x * tri.y * tri.z;
-        v3 e = (kExt && P.layout == 1) ? sample_tile_oct(P, tex, W, p, N) : sample_tile(P, tex, tex, W, p, N);
+        v3 e = (kExt && P.layout == 1) ? sample_tile_oct(P, tex, W, p, N) : gather_tile(P, tex, tex, W, p, relx, rely);
         irradiance = irradiance + e * w;
         sum_w += w;
     }
@@ -174,7 +189,7 @@ DDGI_HD int pixel_direct_term(const FrameParams& P, const Hit& info, v3* direct,
         const Light& l = P.lights[i];
         v3 to_light = normalize(lpos(l) - info.pos);
         Hit fh;
-        if (nearest_hit(P, info.pos, to_light, fh, lookups) && fh.type == 2) {
+        if (nearest_hit_marchfirst(P, info.pos, to_light, fh, lookups, false) && fh.type == 2) {
             float lambert = gclamp(dot(normalize(info.normal), to_light), 0.0f, 1.0f);
             float dist = length(lpos(l) - info.pos);
             *direct = *direct + ((lcol(l) * lambert) * l.intensity) / dist;
@@ -189,7 +204,7 @@ DDGI_HD v3 shade_ddgi(const FrameParams& P, const uint32_t* tex, const uint32_t*
                       uint32_t& lookups)
 {
     Hit info;
-    bool hit = nearest_hit(P, origin, direction, info, lookups);
+    bool hit = nearest_hit_marchfirst(P, origin, direction, info, lookups);
     if (kExt && probe_marker_in_front(P, origin, direction, info)) return V3(0, 1, 1);
     if (!hit) return V3(0.898f, 0.968f, 1.0f);
     if (info.type == 2) return info.emissive;
@@ -205,7 +220,7 @@ DDGI_HD v3 shade_ddgi(const FrameParams& P, const uint32_t* tex, const uint32_t*
 DDGI_HD v3 shade_direct(const FrameParams& P, v3 origin, v3 direction, uint32_t& lookups)
 {
     Hit info;
-    if (!nearest_hit(P, origin, direction, info, lookups)) return V3(0, 0, 0);
+    if (!nearest_hit_marchfirst(P, origin, direction, info, lookups)) return V3(0, 0, 0);
     v3 direct;
     int visible = pixel_direct_term(P, info, &direct, lookups);
     if (visible != 0) return (info.base_color * 0.5f) * (direct / (float)visible);
@@ -217,7 +232,7 @@ DDGI_HD v3 shade_indirect(const FrameParams& P, const uint32_t* tex, const uint3
                           uint32_t& lookups)
 {
     Hit info;
-    bool hit = nearest_hit(P, origin, direction, info, lookups);
+    bool hit = nearest_hit_marchfirst(P, origin, direction, info, lookups);
     if (probe_marker_in_front(P, origin, direction, info)) return V3(0, 1, 1);
     if (!hit) return V3(0, 0, 0);
     return cage_irradiance<true>(P, tex, dist_tex, W, info) * 0.5f;
@@ -227,20 +242,20 @@ DDGI_HD v3 shade_indirect(const FrameParams& P, const uint32_t* tex, const uint3
 DDGI_HD v3 shade_color(const FrameParams& P, v3 origin, v3 direction, uint32_t& lookups)
 {
     Hit info;
-    if (!nearest_hit(P, origin, direction, info, lookups)) return V3(0, 0, 0);
+    if (!nearest_hit_marchfirst(P, origin, direction, info, lookups)) return V3(0, 0, 0);
     return info.base_color;
 }
 DDGI_HD v3 shade_depth(const FrameParams& P, v3 origin, v3 direction, uint32_t& lookups)
 {
     Hit info;
-    nearest_hit(P, origin, direction, info, lookups);
+    nearest_hit_marchfirst(P, origin, direction, info, lookups);
     float inv_dist = 1.0f / (length(direction) * info.t);
     return V3(inv_dist, inv_dist, inv_dist);
 }
 DDGI_HD v3 shade_normal(const FrameParams& P, v3 origin, v3 direction, uint32_t& lookups)
 {
     Hit info;
-    float isect = nearest_hit(P, origin, direction, info, lookups) ? 1.0f : 0.0f;
+    float isect = nearest_hit_marchfirst(P, origin, direction, info, lookups) ? 1.0f : 0.0f;
     float h = 0.5f * isect;
     return info.normal * 0.5f + V3(h, h, h);
 }

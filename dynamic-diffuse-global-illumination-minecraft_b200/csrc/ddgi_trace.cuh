@@ -246,7 +246,8 @@ DDGI_HD void march_advance(v3 origin, v3 dir, float& t, v3& p)
 // kernel: max((-f)/d, (1-f)/d) = (sel - f)/d with sel = 1 for d > 0 else 0, the division by the
 // FMA-corrected reciprocal, floor / ceil by directed-rounding adds.  Bit-identical to the literal
 // form below (tests/hostsim on the CPU, tests/selftest_div.cu exhaustively on the GPU).
-DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32_t& lookups)
+// `want_surface` false (shadow feelers): only out.t is filled - no block type fetch, normal or colour.
+DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32_t& lookups, bool want_surface = true)
 {
     v3 dir = normalize(direction);
     v3 p = origin;
@@ -281,9 +282,10 @@ DDGI_HD bool march(const SceneView& S, v3 origin, v3 direction, Hit& out, uint32
         }
     }
     if (!hit) return false;
+    out.t = t;
+    if (!want_surface) return true;
     v3 cell = V3(ceilf(p.x), ceilf(p.y), ceilf(p.z));
     int type = scene_type_at(S, cell);
-    out.t = t;
     v3 n = face_normal(p, cell);
     out.normal = normalize(n);
     out.base_color = scene_color(S, p, type, out.normal);
@@ -325,6 +327,104 @@ DDGI_HD bool nearest_hit(const FrameParams& P, v3 origin, v3 direction, Hit& inf
         }
     }
     bool hit = closest < inf_f();
+    info.normal = hit ? normalize(info.normal) : V3(0, 0, 0);
+    info.pos = hit ? origin + direction * info.t : V3(0, 0, 0);
+    info.pos = info.pos + info.normal * 0.001f;
+    return hit;
+}
+
+// Light-sphere test of a query: nearest t over all lights, exactly as the loop of
+// intersect_scene (intersection.glsl:1262-1279) evaluates it, except that it runs AFTER
+// the march and skips lights that cannot beat the block hit at t_block:
+// a root of |w + dir*t| = 0.1 (w = origin - light) has t*|dir| >= |w| - 0.1, and the
+// reference's fp32 evaluation of it is within 1e-5 of that for |w| >= 0.101 (no
+// cancellation: B^2/(A*C) <= 50), so with |w| > 1.01*t_block*|dir| + 0.101 every root it
+// could report is > t_block: the block wins whatever the light's t is.  Skipping a light
+// only widens the (0, closest) window of later ones by values > t_block, which lose
+// to the block as well; with no block hit (t_block = INF) nothing is skipped.
+// `dir_len` = sqrtf(dot(direction, direction)).
+// `normal` (optional) receives the un-normalised sphere normal of the winning light.
+DDGI_HD float light_test(const FrameParams& P, v3 origin, v3 direction, float dir_len, float t_block, int* which, v3* normal)
+{
+    float closest = inf_f();
+    *which = -1;
+    float reach2 = inf_f();
+    unsigned near = 0xffu;  // bit i: light i may beat the block hit
+    if (t_block < inf_f()) {
+        float reach = (t_block * dir_len) * 1.01f + 0.101f;
+        reach2 = reach * reach;
+        // all lights at once: they lie within lights_radius of lights_centre, so
+        // |w_i| >= |origin - centre| - radius for every i; 1.0001 covers the fp32 evaluation
+        v3 wc = origin - V3(P.lights_centre[0], P.lights_centre[1], P.lights_centre[2]);
+        float far = reach + P.lights_radius;
+        if (dot(wc, wc) > (far * far) * 1.0001f) return closest;
+        // light by light, without a branch per light (the loop count is the same for every lane)
+        near = 0u;
+        for (int i = 0; i < P.n_lights; i++) {
+            v3 w = origin - lpos(P.lights[i]);
+            near |= (dot(w, w) > reach2 ? 0u : 1u) << i;
+        }
+        if (near == 0u) return closest;
+    }
+    v3 d = div_tenth(direction);
+    float A = dot(d, d);
+    for (int i = 0; i < P.n_lights; i++) {
+        if (!((near >> i) & 1u)) continue;
+        v3 o = div_tenth(origin - lpos(P.lights[i]));
+        float B = -dot(d, o);
+        float C = dot(o, o) - 1.0f;
+        float D = B * B - A * C;
+        if (!(D > 0)) continue;  // D -> INF: both roots fail the (0, maxt) window, t = INF
+        D = sqrtf(D);
+        float t1 = (B - D) / A;
+        float t2 = (B + D) / A;
+        t1 = (0.0f < t1 && t1 < closest) ? t1 : inf_f();
+        t2 = (0.0f < t2 && t2 < closest) ? t2 : inf_f();
+        float t = gmin(t1, t2);
+        if (t < closest) {
+            *which = i;
+            if (normal) *normal = o + d * t;
+        }
+        closest = gmin(t, closest);
+    }
+    return closest;
+}
+
+// nearest_hit with the voxel march FIRST and the light spheres tested afterwards by light_test (only those that
+// could beat the block hit): the same `info` and the same voxel lookups as nearest_hit - the reference's march
+// does not depend on the lights, the block wins iff m.t < closest either way, and light_test reports the
+// reference loop's winner (first light on ties) with its un-normalised normal - for a fraction of the
+// light arithmetic.  `want_surface` false (shadow feelers): info.type and info.t only.
+DDGI_HD bool nearest_hit_marchfirst(const FrameParams& P, v3 origin, v3 direction, Hit& info, uint32_t& lookups, bool want_surface = true)
+{
+    info.pos = V3(0, 0, 0);
+    info.normal = V3(0, 0, 0);
+    info.base_color = V3(0, 0, 0);
+    info.emissive = V3(0, 0, 0);
+    info.type = 0;
+    Hit m;
+    const bool block = march(P.scene, origin, direction, m, lookups, want_surface);
+    const float t_block = block ? m.t : inf_f();
+    int which;
+    v3 n = V3(0, 0, 0);
+    float closest = light_test(P, origin, direction, sqrtf(dot(direction, direction)), t_block, &which, want_surface ? &n : nullptr);
+    info.t = closest;
+    if (t_block < closest) {
+        info.t = t_block;
+        closest = t_block;
+        info.type = 3;
+        if (want_surface) {
+            info.normal = m.normal;
+            info.base_color = m.base_color;
+            info.emissive = m.emissive;
+        }
+    } else if (closest < inf_f()) {
+        info.type = 2;
+        info.normal = n;
+        if (want_surface) info.emissive = lcol(P.lights[which]);
+    }
+    const bool hit = closest < inf_f();
+    if (!want_surface) return hit;
     info.normal = hit ? normalize(info.normal) : V3(0, 0, 0);
     info.pos = hit ? origin + direction * info.t : V3(0, 0, 0);
     info.pos = info.pos + info.normal * 0.001f;

@@ -88,63 +88,6 @@ struct WfRay {
     uint32_t lookups;
 };
 
-// Light-sphere test of a query: nearest t over all lights, exactly as the loop of
-// intersect_scene (intersection.glsl:1262-1279) evaluates it, except that it runs AFTER
-// the march and skips lights that cannot beat the block hit at t_block:
-// a root of |w + dir*t| = 0.1 (w = origin - light) has t*|dir| >= |w| - 0.1, and the
-// reference's fp32 evaluation of it is within 1e-5 of that for |w| >= 0.101 (no
-// cancellation: B^2/(A*C) <= 50), so with |w| > 1.01*t_block*|dir| + 0.101 every root it
-// could report is > t_block: the block wins whatever the light's t is.  Skipping a light
-// only widens the (0, closest) window of later ones by values > t_block, which lose
-// to the block as well; with no block hit (t_block = INF) nothing is skipped.
-// `dir_len` = sqrtf(dot(direction, direction)).
-// `normal` (optional) receives the un-normalised sphere normal of the winning light.
-DDGI_HD float light_test(const FrameParams& P, v3 origin, v3 direction, float dir_len, float t_block, int* which, v3* normal)
-{
-    float closest = inf_f();
-    *which = -1;
-    float reach2 = inf_f();
-    unsigned near = 0xffu;  // bit i: light i may beat the block hit
-    if (t_block < inf_f()) {
-        float reach = (t_block * dir_len) * 1.01f + 0.101f;
-        reach2 = reach * reach;
-        // all lights at once: they lie within lights_radius of lights_centre, so
-        // |w_i| >= |origin - centre| - radius for every i; 1.0001 covers the fp32 evaluation
-        v3 wc = origin - V3(P.lights_centre[0], P.lights_centre[1], P.lights_centre[2]);
-        float far = reach + P.lights_radius;
-        if (dot(wc, wc) > (far * far) * 1.0001f) return closest;
-        // light by light, without a branch per light (the loop count is the same for every lane)
-        near = 0u;
-        for (int i = 0; i < P.n_lights; i++) {
-            v3 w = origin - lpos(P.lights[i]);
-            near |= (dot(w, w) > reach2 ? 0u : 1u) << i;
-        }
-        if (near == 0u) return closest;
-    }
-    v3 d = div_tenth(direction);
-    float A = dot(d, d);
-    for (int i = 0; i < P.n_lights; i++) {
-        if (!((near >> i) & 1u)) continue;
-        v3 o = div_tenth(origin - lpos(P.lights[i]));
-        float B = -dot(d, o);
-        float C = dot(o, o) - 1.0f;
-        float D = B * B - A * C;
-        if (!(D > 0)) continue;  // D -> INF: both roots fail the (0, maxt) window, t = INF
-        D = sqrtf(D);
-        float t1 = (B - D) / A;
-        float t2 = (B + D) / A;
-        t1 = (0.0f < t1 && t1 < closest) ? t1 : inf_f();
-        t2 = (0.0f < t2 && t2 < closest) ? t2 : inf_f();
-        float t = gmin(t1, t2);
-        if (t < closest) {
-            *which = i;
-            if (normal) *normal = o + d * t;
-        }
-        closest = gmin(t, closest);
-    }
-    return closest;
-}
-
 // The march flavour of the current query: the fast step (ddgi_fastmath.cuh) needs regular direction
 // components, no origin component in (0, 2^-70) so that a position is either 0 or >= 2^-98 in
 // magnitude, and |origin| < 2^20 so that |p| stays below 2^22 over 125 cells (floor_small /

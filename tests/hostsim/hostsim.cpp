@@ -235,6 +235,10 @@ void sim_regular_checks(const float* x, int n, uint8_t* component, uint8_t* orig
         org3[i / 3] = regular_origin3(x[i], x[i + 1], x[i + 2]);
     }
 }
+void sim_unorm8(float* out256)
+{
+    for (uint32_t b = 0; b < 256; b++) out256[b] = unorm8_to_float(b);
+}
 void sim_face_normals(const float* p, const float* cell, int n, float* fast, float* literal)
 {
     for (int i = 0; i < n; i++) {

@@ -168,3 +168,16 @@ def test_face_normal_shortcut_equals_the_literal_normal():
     hs.sim_face_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     hs.sim_face_normals(p.ctypes.data, cell.ctypes.data, n, fast.ctypes.data, lit.ctypes.data)
     assert np.array_equal(fast.view(np.uint32), lit.view(np.uint32))
+
+
+def test_byte_unpack_equals_the_division_for_every_byte():
+    """ddgi_math.cuh: unorm8_to_float (imageLoad of an rgba8 channel without the IEEE division) == float32(b) / 255 for
+    all 256 bytes."""
+    import ctypes as C
+    import util
+    out = np.zeros(256, dtype=np.float32)
+    hs = util.hostsim()
+    hs.sim_unorm8.argtypes = [C.c_void_p]
+    hs.sim_unorm8(out.ctypes.data)
+    want = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
