@@ -204,6 +204,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=None, choices=[1, 2],
+                    help="2 (default for --gpus > 1): consecutive updates overlap on the engine's own two streams "
+                         "(ddgi_set_frames_in_flight), which hides the drain of the persistent kernel on a 1/N share; "
+                         "1 (default on one GPU, where the drain is 3 %% of the kernel: profiles/r2_ab.md f)")
     ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu pass (roofline.traffic falls back to profiles/traffic.json)")
     ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--verify", action="store_true",
@@ -356,15 +360,45 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
+    def timed_in_flight(n_steps, warm):
+        """-> ms per step with two frames in flight (ddgi_set_frames_in_flight): the updates run on the engine's own
+        two streams, so per-step events on this stream would bracket nothing; K steps between two events, the second
+        behind a fence on every frame in flight.  The L2 flush of every step is INSIDE the timed region (the update
+        that follows is ordered behind it)."""
+        for _ in range(warm):
+            flush_l2()
+            step()
+        r.frame_fence()
+        barrier()
+        if n_steps == 0:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n_steps):
+            flush_l2()
+            step()
+        r.frame_fence()
+        b.record(stream)
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / n_steps], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    if args.frames_in_flight is None:
+        args.frames_in_flight = 2 if world > 1 else 1
     sampler = ClockSampler(local)
-    for _ in range(args.warmup):
-        flush_l2()
-        step()
-    barrier()
+    # one frame at a time first: the kernel's own duration (what the roofline line is built on) ...
+    ms_serial, kernel_ms = timed(max(5, args.steps // 2), args.warmup)
+    # ... then the measurement proper: two frames in flight, as the reference keeps (MAX_FRAMES_IN_FLIGHT, rvpt.h:23)
+    r.set_frames_in_flight(args.frames_in_flight)
+    in_flight = args.frames_in_flight == 2
+    if in_flight:
+        timed_in_flight(0, args.warmup)
     if rank == 0:
         sampler.start()
     launches0 = r.launch_count
-    ms_per_step, kernel_ms = timed(args.steps, 0)
+    ms_per_step = timed_in_flight(args.steps, 0) if in_flight else timed(args.steps, 0)[0]
     launches = r.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     value = n_rays / (ms_per_step * 1e-3)
@@ -380,10 +414,12 @@ def main():
     for _ in range(n_frames):
         step()
         r.render_frame()
+    r.frame_fence()
     fb.record(stream)
     barrier()
     ft = torch.tensor([fa.elapsed_time(fb) / n_frames], device=f"cuda:{local}", dtype=torch.float64)
     pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r.frame_fence()
     pa.record(stream)
     r.render_frame()
     pb.record(stream)
@@ -524,6 +560,7 @@ def main():
             join_nccl()
             set_ownership("slab")
             n_nccl = max(3, min(args.steps, 10))
+            r.set_frames_in_flight(1)
             ms_nccl, kernel_ms_nccl = timed(n_nccl, 3)
             exchange_nccl = {"value": n_rays / (ms_nccl * 1e-3), "unit": UNIT, "ms_per_step": ms_nccl, "kernel_ms": kernel_ms_nccl,
                              "steps": n_nccl, "exchange": "nccl: contiguous slabs of probe rows, one in-place ncclAllGather per plane "
@@ -531,6 +568,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r.set_frames_in_flight(1)
         r.set_double_buffer(False)
         cpu = cpu_baseline(r, cfg, args.workload)
     prof = None
@@ -558,7 +596,9 @@ def main():
             "config": {"workload": args.workload, "probes": [X, Y, Z], "rays_per_probe": rx * ry,
                        "probe_rays": n_rays, "voxels": list(cfg["voxels"][1]), "lights": 4 if cfg["lights"] == "cave4" else 1,
                        "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"]),
-                       "l2": "flushed between timed steps (256 MiB write)" if flush_buf is not None else "not flushed",
+                       "l2": ("flushed before every timed update (256 MiB write, inside the timed region)" if in_flight else
+                              "flushed between timed steps (256 MiB write)") if flush_buf is not None else "not flushed",
+                       "frames_in_flight": args.frames_in_flight,
                        "kernel_variant": args.variant, "exchange": args.exchange if world > 1 else "none",
                        "sharding": shard_desc if world > 1 else "none"},
             "clocks": clocks,
@@ -572,6 +612,9 @@ def main():
                          "note": "algorithmic bytes = rays x (4 B x voxel lookups of the reference algorithm + 8 B texel stores), SURVEY 8d; "
                                  "the kernel is bound by instruction issue, not by HBM: see `issue`"},
             "issue": None if not prof else {k: prof[k] for k in ("issue_active_pct", "lanes_per_inst", "warp_inst_per_ray", "kernel_ms_under_ncu", "how")},
+            "one_frame_at_a_time": {"value": n_rays / (ms_serial * 1e-3), "unit": UNIT, "ms_per_step": ms_serial, "kernel_ms": kernel_ms,
+                                    "note": "the same loop with ddgi_set_frames_in_flight(1): per-step CUDA events, L2 flushed between steps "
+                                            "outside the timed brackets; roofline.kernel_ms is this pass's"},
             "cpu_baseline": cpu,
             "verify": verify,
             "exchange_nccl": exchange_nccl,

@@ -140,6 +140,9 @@ PROTOTYPES = {
     "ddgi_probe_texture_size": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
     "ddgi_read_probe_texture": (C.c_int, [_P, _I32, _I32, _P, _SZ]),
     "ddgi_set_double_buffer": (C.c_int, [_P, _I32]),
+    "ddgi_set_frames_in_flight": (C.c_int, [_P, _I32]),
+    "ddgi_frame_fence": (C.c_int, [_P, _P]),
+    "ddgi_last_update_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ddgi_read_probe_texture_async": (C.c_int, [_P, _I32, _P, _SZ]),
     "ddgi_read_probe_texture_rows_async": (C.c_int, [_P, _I32, _I32, _I32, _P, _SZ]),
     "ddgi_read_wait": (C.c_int, [_P]),

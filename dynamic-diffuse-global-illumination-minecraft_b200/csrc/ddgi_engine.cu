@@ -38,7 +38,16 @@ struct ddgi_ctx {
     int slot_pref = 32;  // schedule granularity in rays (0 = a whole probe): one warp's fetch measured best
     unsigned long long* d_warp_times = nullptr;  // debug level 2
     size_t warp_times_cap = 0, warp_times_n = 0;
-    uint32_t* d_counter = nullptr;
+    uint32_t* d_counter = nullptr;   // two ray counters: one per frame in flight
+    // Frames in flight (ddgi_set_frames_in_flight): with 2, the update (and exchange) of frame i runs on
+    // the engine's own stream frame_stream[i & 1], so the first blocks of update i+1 start while the
+    // persistent kernel of update i drains - the reference keeps two frames in flight too
+    // (MAX_FRAMES_IN_FLIGHT, src/rvpt/rvpt.h:23).  ev_frame[b]: the frame in texture allocation b is complete.
+    int in_flight = 1;
+    cudaStream_t frame_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_frame[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr;                        // the caller's stream at the time of a dispatch
+    cudaEvent_t ev_k0[2] = {nullptr, nullptr}, ev_k1[2] = {nullptr, nullptr};  // around the update kernel (timing)
 
     ddgi_render_settings rs{};
     ddgi_irradiance_field field{};
@@ -59,8 +68,15 @@ struct ddgi_ctx {
 
     // rays
     std::vector<float> samples;  // rx*ry raw sphere samples (xyz)
-    float* d_dirs = nullptr;     // normalised, generated mode
+    // normalised directions, generated mode: a ring of three tables, so that a new sample set (one per
+    // frame in bench.py's e2e loop) is uploaded - on the engine's own small upload stream - while the
+    // update launched last still reads its own; `ev_dirs[b]` = the last update that read table b
+    float* d_dirs = nullptr;     // = d_dirs_ring[dirs_cur]
+    float* d_dirs_ring[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_dirs[3] = {nullptr, nullptr, nullptr};
+    int dirs_cur = 0;
     size_t dirs_cap = 0;
+    cudaStream_t up_stream = nullptr;
     cudaEvent_t ev_update = nullptr;  // recorded after every probe update: what a new ray table must wait for
     float4* d_rays = nullptr;    // literal storage-buffer mode
     size_t n_rays_ssbo = 0;
@@ -194,6 +210,8 @@ static size_t num_slots(const ddgi_ctx* c) { return num_probes(c) * ((size_t)(c-
 static int schedule(ddgi_ctx* ctx)
 {
     if (!ctx->order_dirty && ctx->d_order) return DDGI_OK;
+    for (int b = 0; b < 2; b++)  // (an update in flight on the engine's own streams still reads the old list)
+        if (ctx->frame_stream[b]) CU(cudaStreamSynchronize(ctx->frame_stream[b]));
     size_t np = num_probes(ctx), ns = num_slots(ctx);
     uint32_t spp = (uint32_t)(ns / np);
     ctx->order.clear();
@@ -453,16 +471,47 @@ static int upload_dirs(ddgi_ctx* ctx)
         dirs[3 * i + 1] = d.y;
         dirs[3 * i + 2] = d.z;
     }
-    // the last probe update may still be reading the table (a cudaFree here used to hide that by
-    // stalling the whole device every frame): wait for exactly that launch
-    if (ctx->ev_update) CU(cudaEventSynchronize(ctx->ev_update));
     if (n > ctx->dirs_cap) {
-        dfree(ctx->d_dirs);
-        CU(cudaMalloc(&ctx->d_dirs, n * 3 * sizeof(float)));
+        // (growing: every update that may read an old table must be over)
+        for (int b = 0; b < 3; b++) {
+            if (ctx->ev_dirs[b]) CU(cudaEventSynchronize(ctx->ev_dirs[b]));
+            dfree(ctx->d_dirs_ring[b]);
+            CU(cudaMalloc(&ctx->d_dirs_ring[b], n * 3 * sizeof(float)));
+        }
         ctx->dirs_cap = n;
     }
-    CU(cudaMemcpy(ctx->d_dirs, dirs.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    // the next table of the ring: the update that read it last was launched at least two uploads ago
+    // (waited for, normally long over); the updates in flight keep reading theirs
+    if (!ctx->up_stream) CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+    int b = (ctx->dirs_cur + 1) % 3;
+    if (ctx->ev_dirs[b]) CU(cudaEventSynchronize(ctx->ev_dirs[b]));
+    CU(cudaMemcpyAsync(ctx->d_dirs_ring[b], dirs.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->up_stream));
+    CU(cudaStreamSynchronize(ctx->up_stream));  // (`dirs` is a local; 3 KB)
+    ctx->dirs_cur = b;
+    ctx->d_dirs = ctx->d_dirs_ring[b];
     ctx->ray_mode = 1;
+    return DDGI_OK;
+}
+
+// The stream the work of the frame in texture allocation `b` runs on: the caller's, or with two frames
+// in flight the engine's own frame_stream[b].
+static cudaStream_t work_stream(ddgi_ctx* ctx, int b, cudaStream_t caller) { return ctx->in_flight == 2 ? ctx->frame_stream[b] : caller; }
+
+// Makes the work stream of frame b follow everything the caller's stream has been given so far (the
+// caller's uploads, edits and - what matters under an exchange - its readers of older frames).
+static int follow_caller(ddgi_ctx* ctx, int b, cudaStream_t caller)
+{
+    if (ctx->in_flight != 2) return DDGI_OK;
+    CU(cudaEventRecord(ctx->ev_in, caller));
+    CU(cudaStreamWaitEvent(ctx->frame_stream[b], ctx->ev_in, 0));
+    return DDGI_OK;
+}
+
+// Waits (host) for the engine's own streams.
+static int drain_frames(ddgi_ctx* ctx)
+{
+    for (int b = 0; b < 2; b++)
+        if (ctx->frame_stream[b]) CU(cudaStreamSynchronize(ctx->frame_stream[b]));
     return DDGI_OK;
 }
 
@@ -483,7 +532,7 @@ int ddgi_create(ddgi_ctx** out, int device)
     if (prop.major != 10) return DDGI_E_CUDA;  // sm_100a code only
     ddgi_ctx* ctx = new ddgi_ctx();
     ctx->device = device;
-    if (cudaMalloc(&ctx->d_counter, sizeof(uint32_t)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->d_counter, 2 * sizeof(uint32_t)) != cudaSuccess) {
         delete ctx;
         return DDGI_E_CUDA;
     }
@@ -503,7 +552,18 @@ void ddgi_destroy(ddgi_ctx* ctx)
     dfree(ctx->d_occ);
     dfree(ctx->d_edit);
     dfree(ctx->d_palette);
-    dfree(ctx->d_dirs);
+    for (int b = 0; b < 3; b++) {
+        dfree(ctx->d_dirs_ring[b]);
+        if (ctx->ev_dirs[b]) cudaEventDestroy(ctx->ev_dirs[b]);
+    }
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->frame_stream[b]) cudaStreamDestroy(ctx->frame_stream[b]);
+        if (ctx->ev_frame[b]) cudaEventDestroy(ctx->ev_frame[b]);
+        if (ctx->ev_k0[b]) cudaEventDestroy(ctx->ev_k0[b]);
+        if (ctx->ev_k1[b]) cudaEventDestroy(ctx->ev_k1[b]);
+    }
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     dfree(ctx->d_rays);
     dfree(ctx->d_tex_pair[0]);
     dfree(ctx->d_tex_pair[1]);
@@ -754,6 +814,10 @@ int ddgi_edit_voxels(ddgi_ctx* ctx, const int32_t origin[3], const int32_t dims[
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
+    {   // updates in flight on the engine's own streams still read the field: the edit follows them
+        int rc = ddgi_frame_fence(ctx, stream);
+        if (rc) return rc;
+    }
     size_t n = (size_t)ext[0] * ext[1] * ext[2];
     if (n > ctx->edit_cap) {
         CU(cudaStreamSynchronize(s));  // an earlier edit may still read the old staging buffer
@@ -1060,9 +1124,13 @@ int ddgi_exchange_barrier(ddgi_ctx* ctx, void* stream)
     // asynchronous read of that allocation (ddgi_read_probe_texture_async, on the copy stream) must
     // be over before any peer may start: this rank only arrives at the barrier once it is.
     int next = ctx->double_buffer ? ctx->cur_tex ^ 1 : ctx->cur_tex;
-    if (ctx->ev_copied[next]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_copied[next], 0));
-    ctx->last_stream = (cudaStream_t)stream;
-    return issue_barrier(ctx, 0, (cudaStream_t)stream);
+    cudaStream_t w = work_stream(ctx, ctx->cur_tex, (cudaStream_t)stream);  // behind the update it completes
+    if (ctx->ev_copied[next]) CU(cudaStreamWaitEvent(w, ctx->ev_copied[next], 0));
+    ctx->last_stream = w;
+    int rc = issue_barrier(ctx, 0, w);
+    if (rc) return rc;
+    if (ctx->ev_frame[ctx->cur_tex]) CU(cudaEventRecord(ctx->ev_frame[ctx->cur_tex], w));
+    return DDGI_OK;
 }
 
 int ddgi_exchange_status(ddgi_ctx* ctx)
@@ -1203,7 +1271,7 @@ int ddgi_exchange_allgather(ddgi_ctx* ctx, void* stream)
     const size_t row_bytes = (size_t)ctx->tex_w * 4 * tile_h(ctx);  // one probe row of one plane
     const size_t plane = tex_texels(ctx) * 4;
     const int planes = ctx->distance_dirty[ctx->cur_tex] ? 2 : 1;
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t s = work_stream(ctx, ctx->cur_tex, (cudaStream_t)stream);  // behind the update it completes
     ctx->last_stream = s;
     if (ctx->cyc_world == 0) {
         if (Y % G != 0 || ctx->row0 != r * (Y / G) || ctx->row1 != (r + 1) * (Y / G))
@@ -1214,6 +1282,7 @@ int ddgi_exchange_allgather(ddgi_ctx* ctx, void* stream)
             char* base = (char*)ctx->d_tex + p * plane;
             NCCLCHK(N.AllGather(base + r * chunk, base, chunk, kNcclUint8, ctx->nccl_comm, s));
         }
+        if (ctx->ev_frame[ctx->cur_tex]) CU(cudaEventRecord(ctx->ev_frame[ctx->cur_tex], s));
         return DDGI_OK;
     }
     if (ctx->cyc_unit != 0 || ctx->cyc_world != G || ctx->cyc_rank != r)
@@ -1232,6 +1301,7 @@ int ddgi_exchange_allgather(ddgi_ctx* ctx, void* stream)
         }
     }
     NCCLCHK(N.GroupEnd());
+    if (ctx->ev_frame[ctx->cur_tex]) CU(cudaEventRecord(ctx->ev_frame[ctx->cur_tex], s));
     return DDGI_OK;
 }
 
@@ -1351,6 +1421,15 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     if (rc) return rc;
     FrameParams P;
     fill_params(ctx, &P);
+    // the allocation this update writes (the other one under double buffering) and the stream it runs on
+    const int target = ctx->double_buffer ? ctx->cur_tex ^ 1 : ctx->cur_tex;
+    const cudaStream_t caller = (cudaStream_t)stream;
+    stream = (void*)work_stream(ctx, target, caller);
+    rc = follow_caller(ctx, target, caller);
+    if (rc) return rc;
+    if (ctx->in_flight == 2 && (ctx->blend_mode || ctx->debug || ctx->layout == DDGI_LAYOUT_OCTAHEDRAL) && ctx->ev_frame[target ^ 1])
+        // the blend reads the previous frame, the debug and ray-result buffers are shared: no overlap then
+        CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_frame[target ^ 1], 0));
     ProbeJob J;
     memset(&J, 0, sizeof(J));
     J.rays = ctx->ray_mode == 2 ? ctx->d_rays : nullptr;
@@ -1373,9 +1452,7 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     J.tex_h = ctx->tex_h;
     const uint32_t* old_tex = ctx->d_tex;
     {
-        // the allocation this update writes (the other one under double buffering): the last
-        // asynchronous read of it must have finished before the kernel may overwrite it
-        int target = ctx->double_buffer ? ctx->cur_tex ^ 1 : ctx->cur_tex;
+        // the last asynchronous read of the allocation must have finished before the kernel may overwrite it
         if (ctx->ev_copied[target]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_copied[target], 0));
         ctx->cur_tex = target;
         ctx->d_tex = ctx->d_tex_pair[target];
@@ -1399,13 +1476,16 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
         J.peer_distance[J.n_peers] = (uint32_t*)ctx->peer_base[peer_buf][g] + tex_texels(ctx);
         J.n_peers++;
     }
-    if (ctx->n_peers > 1 && ctx->peer_buffers == 1) {
+    if (ctx->n_peers > 1 && (ctx->peer_buffers == 1 || ctx->in_flight == 2)) {
         // Single-buffered replicas: a faster rank's update i+1 would store into this rank's texture
         // while it still renders or reads frame i.  A second epoch barrier in front of every update
         // closes that window: nobody starts update i+1 before everybody has issued - in stream order,
         // behind its readers of frame i - its own.  (A double-buffered context does not need it: update
         // i+1 writes the other allocation, and update i+2 cannot start before this rank has passed
-        // the completion barrier of i+1, which its readers of frame i precede in stream order.)
+        // the completion barrier of i+1, which its readers of frame i precede in stream order.  With two
+        // frames in flight that chain is gone - update i+2 runs on another stream than barrier i+1 - and
+        // this barrier, issued behind the caller's stream (follow_caller), restores it without tying
+        // update i+2 to the END of update i+1: a rank arrives here when its readers of frame i are done.)
         rc = issue_barrier(ctx, 1, (cudaStream_t)stream);
         if (rc) return rc;
     }
@@ -1430,7 +1510,11 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     }
     if (skip_distance && ctx->layout != DDGI_LAYOUT_OCTAHEDRAL) J.distance = nullptr;
     int l = 0;
-    CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter, ctx->march_min, ctx->grid_limit, (cudaStream_t)stream, &l));
+    for (cudaEvent_t* e : {&ctx->ev_k0[target], &ctx->ev_k1[target]})
+        if (!*e) CU(cudaEventCreate(e));
+    CU(cudaEventRecord(ctx->ev_k0[target], (cudaStream_t)stream));
+    CU(launch_probe_update(P, J, ctx->variant, ctx->d_counter + target, ctx->march_min, ctx->grid_limit, (cudaStream_t)stream, &l));
+    CU(cudaEventRecord(ctx->ev_k1[target], (cudaStream_t)stream));
     if (!J.distance) J.distance = ctx->d_tex + tex_texels(ctx);
     if (ctx->layout == 1) {
         OctJob O;
@@ -1459,6 +1543,12 @@ int ddgi_probe_update(ddgi_ctx* ctx, void* stream)
     ctx->last_stream = (cudaStream_t)stream;
     if (!ctx->ev_update) CU(cudaEventCreateWithFlags(&ctx->ev_update, cudaEventDisableTiming));
     CU(cudaEventRecord(ctx->ev_update, (cudaStream_t)stream));
+    if (ctx->ray_mode == 1) {
+        if (!ctx->ev_dirs[ctx->dirs_cur]) CU(cudaEventCreateWithFlags(&ctx->ev_dirs[ctx->dirs_cur], cudaEventDisableTiming));
+        CU(cudaEventRecord(ctx->ev_dirs[ctx->dirs_cur], (cudaStream_t)stream));
+    }
+    if (!ctx->ev_frame[target]) CU(cudaEventCreateWithFlags(&ctx->ev_frame[target], cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_frame[target], (cudaStream_t)stream));  // (an exchange records it again behind itself)
     if (calibrate) {
         // First update after the scene / rays / field changed: this launch also recorded the largest
         // voxel-lookup count per slot.  Read them once (the only synchronising probe update) and
@@ -1500,6 +1590,7 @@ int ddgi_render_frame(ddgi_ctx* ctx, void* stream)
     J.frame_f32 = ctx->debug ? ctx->d_frame_f32 : nullptr;
     J.lookups = ctx->debug ? ctx->d_px_lookups : nullptr;
     int l = 0;
+    if (ctx->in_flight == 2 && ctx->ev_frame[ctx->cur_tex]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_frame[ctx->cur_tex], 0));
     CU(launch_render_frame(P, J, (cudaStream_t)stream, &l));
     ctx->launches += l;
     ctx->last_stream = (cudaStream_t)stream;
@@ -1531,6 +1622,8 @@ int ddgi_sync(ddgi_ctx* ctx)
     // the stream of the last dispatch and the engine's own copy stream - not the device: the caller's
     // other streams keep running (raytrace_work_fence.wait, rvpt.cpp:277, waits for one submission too)
     CU(cudaStreamSynchronize(ctx->last_stream));
+    int rc = drain_frames(ctx);
+    if (rc) return rc;
     if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
     return DDGI_OK;
 }
@@ -1569,6 +1662,7 @@ int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on)
 {
     if (!ctx) return DDGI_E_INVALID;
     NEED(ctx->n_peers == 0, "close peers first: the peers have mapped this context's allocations");
+    NEED(on || ctx->in_flight == 1, "two frames are in flight: ddgi_set_frames_in_flight(ctx, 1) first");
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
     bool want = on != 0;
@@ -1629,6 +1723,11 @@ int ddgi_write_probe_texture(ddgi_ctx* ctx, int32_t which, const void* src, size
     NEED(ctx->d_tex, "no probe texture");
     NEED(src && (which == 0 || which == 1) && bytes == tex_texels(ctx) * 4, "expected width*height*4 bytes");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));
+    {
+        int rc = drain_frames(ctx);
+        if (rc) return rc;
+    }
     CU(cudaMemcpy(ctx->d_tex + (which ? tex_texels(ctx) : 0), src, bytes, cudaMemcpyHostToDevice));
     if (which == 1) ctx->distance_dirty[ctx->cur_tex] = true;
     return DDGI_OK;
@@ -1755,6 +1854,45 @@ int ddgi_set_distance_mode(ddgi_ctx* ctx, int32_t mode, float scale)
     NEED(scale > 0.0f && scale < 1e30f, "distance scale must be positive and finite");
     ctx->distance_mode = mode;
     ctx->distance_scale = scale;
+    return DDGI_OK;
+}
+
+int ddgi_set_frames_in_flight(ddgi_ctx* ctx, int32_t n)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(n == 1 || n == 2, "1 or 2 frames in flight");
+    NEED(n == 1 || ctx->double_buffer, "two frames in flight need the double-buffered texture (ddgi_set_double_buffer)");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->last_stream));
+    int rc = drain_frames(ctx);
+    if (rc) return rc;
+    if (n == 2) {
+        for (int b = 0; b < 2; b++)
+            if (!ctx->frame_stream[b]) CU(cudaStreamCreateWithFlags(&ctx->frame_stream[b], cudaStreamNonBlocking));
+        if (!ctx->ev_in) CU(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+    }
+    ctx->in_flight = n;
+    return DDGI_OK;
+}
+
+int ddgi_frame_fence(ddgi_ctx* ctx, void* stream)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->in_flight == 2)
+        for (int b = 0; b < 2; b++)
+            if (ctx->ev_frame[b]) CU(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_frame[b], 0));
+    return DDGI_OK;
+}
+
+int ddgi_last_update_ms(ddgi_ctx* ctx, float* ms)
+{
+    if (!ctx) return DDGI_E_INVALID;
+    NEED(ms, "null ms");
+    NEED(ctx->ev_k0[ctx->cur_tex] && ctx->ev_k1[ctx->cur_tex], "no probe update yet");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_k1[ctx->cur_tex]));
+    CU(cudaEventElapsedTime(ms, ctx->ev_k0[ctx->cur_tex], ctx->ev_k1[ctx->cur_tex]));
     return DDGI_OK;
 }
 

@@ -141,7 +141,7 @@ template <bool kLiteral, bool kTimed>
 __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_wavefront(const __grid_constant__ FrameParams P,
                                                                      const __grid_constant__ ProbeJob J,
                                                                      uint32_t* __restrict__ next_ray,
-                                                                     int march_min)
+                                                                     int march_min, int lanes_used)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     float* stash = s_base + (kLiteral ? threadIdx.x : 0);
     const bool want_first_t = J.distance_mode == 1 || J.ray_out != nullptr;
     WfRay R;
-    R.mode = WF_FETCH;
+    // (a workload with fewer rays than the GPU has resident lanes is bound by the longest warp, not by
+    // throughput: it is spread over all resident warps with only `lanes_used` lanes of each holding rays)
+    R.mode = lane < lanes_used ? WF_FETCH : WF_IDLE;
     uint32_t k = 0xffffffffu;  // no ray yet
     int tx = 0, ty = 0;
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: ray indices already reserved
@@ -166,9 +168,10 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     } while (0)
     if (lane == 0) DDGI_WARP_TIME(0);
 
+    int round = 0;
+    int n_live = lanes_used;  // lanes that hold a ray or may still take one (warp-uniform; FETCH retires lanes)
     for (;;) {
         // ---- march while at least march_min/32 of the lanes holding a ray are marching ----
-        const int n_live = __popc(__ballot_sync(full, R.mode != WF_IDLE));
         if (n_live == 0) break;
         const int enough = (n_live * march_min + 31) >> 5 > 1 ? (n_live * march_min + 31) >> 5 : 1;  // lanes
         while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) >= enough) {
@@ -184,9 +187,14 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         const int n_hit_b = __popc(__ballot_sync(full, hit_bounce));
         const unsigned fetching = __ballot_sync(full, R.mode == WF_FETCH);
         const int n_fetch = __popc(fetching);
-        const int n_slow = __popc(__ballot_sync(full, R.mode == WF_MARCH_SLOW));
         const int n_hit = n_hit_f > n_hit_b ? n_hit_f : n_hit_b;
-        if (n_hit + n_fetch + n_slow == 0) continue;  // (only marching lanes: cannot be fewer than `enough`)
+        // (marches with the literal arithmetic - axis-parallel or degenerate rays - are rare: they are only looked
+        // for when nothing else waits, or once in a while so that they cannot starve)
+        int n_slow = 0;
+        if (n_hit + n_fetch == 0 || (++round & 7) == 0) {
+            n_slow = __popc(__ballot_sync(full, R.mode == WF_MARCH_SLOW));
+            if (n_hit + n_fetch + n_slow == 0) continue;  // (only marching lanes: cannot be fewer than `enough`)
+        }
 
         if (n_slow > n_hit && n_slow > n_fetch) {
             if (R.mode == WF_MARCH_SLOW) {
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                 // number asked for once fewer than two rays per resident lane remain — a warp
                 // must not sit on reserved rays while others run dry, or it alone is the tail.
                 const uint32_t more = cnt - avail;
-                const uint32_t take = (n_rays - chunk_end <= 2u * gridDim.x * kWfThreads) ? more : 32u;
+                const uint32_t take = (n_rays - chunk_end <= 2u * gridDim.x * kWfThreads) ? more : (uint32_t)lanes_used;
                 uint32_t base = n_rays;
                 if (!exhausted) {
                     if (lane == 0) base = atomicAdd(next_ray, take);
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                     R.mode = WF_IDLE;
                 }
             }
+            n_live -= __popc(__ballot_sync(full, need && R.mode == WF_IDLE));
         }
         // a finished bounce scatters at once, and every state above hands over to WF_QUERY or
         // ends the ray: arm the new queries right away.  Neither is scheduled as a state of
@@ -338,7 +347,9 @@ __global__ void peer_barrier_kernel(PeerBarrier B)
     const int g = threadIdx.x;
     if (g >= B.n_ranks || g == B.self) return;
     __threadfence_system();
-    *reinterpret_cast<volatile uint32_t*>(B.peer_flags[g] + B.self) = B.epoch;
+    // (a maximum, not a store: with two frames in flight the barriers of consecutive frames run on two
+    // streams and may publish out of order; epochs only grow)
+    atomicMax_system(B.peer_flags[g] + B.self, B.epoch);
     __threadfence_system();
     const volatile uint32_t* mine = B.local_flags + g;
     const unsigned long long t0 = globaltimer_ns();
@@ -472,8 +483,12 @@ __global__ void edit_voxels_kernel(int dx, int dy, int x0, int y0, int z0, int e
 }
 
 // ------------------------------------------------------------------ launchers
-// Warps the wavefront kernel would launch for n rays (debug level 2 sizes its timing buffer by it).
-uint32_t wavefront_warps(uint32_t n, int grid_limit)
+// Launch shape of the wavefront kernel for n rays: the resident grid (148 SMs x blocks per SM) when there is
+// enough work to give every lane a ray; fewer blocks than that only when even 8 rays per warp do not fill them.
+// *lanes = lanes per warp that hold rays: 32, or fewer (a multiple of 4, at least 8) when n is below the number
+// of resident lanes, so that a small workload uses every resident warp with few rays each instead of a quarter
+// of the warps with 32 each (cave_64: 65 536 rays on 132 608 resident lanes).
+uint32_t wavefront_warps(uint32_t n, int grid_limit, int* lanes)
 {
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
@@ -483,9 +498,17 @@ uint32_t wavefront_warps(uint32_t n, int grid_limit)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false, false>, kWfThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    uint32_t warps_needed = (n + 31) / 32;
-    uint32_t blocks_needed = (warps_needed + kWfThreads / 32 - 1) / (kWfThreads / 32);
     int per_sm = grid_limit > 0 && grid_limit < blocks_per_sm ? grid_limit : blocks_per_sm;
+    uint32_t resident_warps = (uint32_t)(sms * per_sm) * (kWfThreads / 32);
+    int use = 32;
+    if (n < resident_warps * 32u) {
+        use = (int)((n + resident_warps - 1) / resident_warps);
+        use = (use + 3) & ~3;
+        use = use < 8 ? 8 : (use > 32 ? 32 : use);
+    }
+    if (lanes) *lanes = use;
+    uint32_t warps_needed = (n + use - 1) / use;
+    uint32_t blocks_needed = (warps_needed + kWfThreads / 32 - 1) / (kWfThreads / 32);
     uint32_t grid = (uint32_t)(sms * per_sm);
     if (grid > blocks_needed) grid = blocks_needed;
     return grid * (kWfThreads / 32);
@@ -504,12 +527,13 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    uint32_t grid = wavefront_warps(n, grid_limit) / (kWfThreads / 32);
+    int lanes = 32;
+    uint32_t grid = wavefront_warps(n, grid_limit, &lanes) / (kWfThreads / 32);
     const bool literal = P.scene.color_mode != 0, timed = J.warp_times != nullptr;
-    if (literal && timed) probe_update_wavefront<true, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
-    else if (literal) probe_update_wavefront<true, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
-    else if (timed) probe_update_wavefront<false, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
-    else probe_update_wavefront<false, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min);
+    if (literal && timed) probe_update_wavefront<true, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
+    else if (literal) probe_update_wavefront<true, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
+    else if (timed) probe_update_wavefront<false, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
+    else probe_update_wavefront<false, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -297,6 +297,19 @@ class RVPT:
     def set_double_buffer(self, on: bool):
         self._check(self._lib.ddgi_set_double_buffer(self._ctx, 1 if on else 0))
 
+    def set_frames_in_flight(self, n: int):
+        """2: updates run on the engine's own streams so that consecutive frames overlap (needs set_double_buffer)."""
+        self._check(self._lib.ddgi_set_frames_in_flight(self._ctx, n))
+
+    def frame_fence(self):
+        """Makes self.stream wait for every frame in flight."""
+        self._check(self._lib.ddgi_frame_fence(self._ctx, self.stream))
+
+    def last_update_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.ddgi_last_update_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
     def read_probe_texture_async(self, out_ptr: int, nbytes: int, which: int = 0):
         """Enqueues the copy of the latest frame into (pinned) host memory at out_ptr; valid after read_wait()."""
         self._check(self._lib.ddgi_read_probe_texture_async(self._ctx, which, out_ptr, nbytes))

@@ -308,6 +308,20 @@ DDGI_API int ddgi_read_probe_texture(ddgi_ctx* ctx, int32_t which, int32_t fmt, 
    allocations).  With partial probe ownership and no exchange the texels a context does not own
    are one frame older in every other buffer. */
 DDGI_API int ddgi_set_double_buffer(ddgi_ctx* ctx, int32_t on);
+/* Frames in flight: 1 (default) - every dispatch runs on the caller's stream.  2 (needs the double-buffered
+   texture) - the reference keeps two frames in flight as well (MAX_FRAMES_IN_FLIGHT, src/rvpt/rvpt.h:23): the
+   probe update of frame i, and the exchange that completes it, run on the engine's own stream i & 1, ordered
+   behind everything the caller's stream held when ddgi_probe_update was called.  Consecutive updates write
+   different allocations and do not depend on each other (unless the hysteresis blend is on: then they
+   serialise), so the first blocks of update i+1 fill the SMs the persistent kernel of update i leaves idle
+   while it drains - what separates 8 GPUs from 8x on a 1/8 share.  ddgi_render_frame and the reads wait for the
+   frame they use; ddgi_frame_fence makes a stream of the caller's wait for every frame in flight (e.g. before an
+   event that times a run); under the fused exchange every update is preceded by a barrier that keeps a rank
+   from storing frame i+2 into a replica whose owner still reads frame i (see ddgi_exchange_barrier). */
+DDGI_API int ddgi_set_frames_in_flight(ddgi_ctx* ctx, int32_t n);
+DDGI_API int ddgi_frame_fence(ddgi_ctx* ctx, void* stream);
+/* Device time of the latest probe-update kernel (CUDA events on the stream it ran on); synchronises with it. */
+DDGI_API int ddgi_last_update_ms(ddgi_ctx* ctx, float* ms);
 DDGI_API int ddgi_read_probe_texture_async(ddgi_ctx* ctx, int32_t which, void* dst, size_t bytes);
 /* The same for texture rows [row0, row1) only (a rank's share of the replica it holds after an exchange);
    ordered after everything given to the dispatch stream so far, i.e. also after ddgi_exchange_barrier /

@@ -1,0 +1,248 @@
+// tma_march.cu — EXPERIMENT (not part of libddgi_b200.so): does staging the probe-local occupancy bricks in shared memory
+// with TMA make the DDA march faster?  (BASELINE.json north star: "TMA staging of probe-local voxel bricks into shared
+// memory"; VERDICT r1 "What's missing" #1.)
+//
+// The part of the probe update a probe-local tile can serve is the march of each ray's FIRST query (the ray from the
+// probe itself); after a bounce the query starts wherever the ray hit.  So the experiment isolates exactly that: one block
+// per probe, one thread per probe ray, every thread marches its primary ray with the engine's own exact DDA step
+// (ddgi_wavefront.cuh arithmetic) until it hits a solid cell or has taken 125 steps, and writes (t, steps).
+//   kernel <false>: every step reads its brick word from global memory (L1 / L2), as the engine does;
+//   kernel <true> : thread 0 first issues ONE cp.async.bulk.tensor.3d (TMA) of the 64 x 16 x 8 brick words = 64^3 cells
+//                   around the probe (32 KB, out-of-grid bricks zero-filled by the TMA unit) into shared memory and the
+//                   block waits on its mbarrier; steps inside the tile read shared memory, steps outside fall back to global.
+// Both kernels must produce identical (t, steps); the program times them with CUDA events (median of 15, cold L2) and is
+// profiled with ncu for the stall picture.  Build + run: see Makefile / profiles/r2_tma_staging.md.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../../include/ddgi.h"
+#include "../../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_wavefront.cuh"
+
+using namespace ddgi;
+
+constexpr int kTileX = 64, kTileY = 16, kTileZ = 8;  // brick words (1 x 4 x 8 cells each): 64^3 cells
+constexpr int kTileBytes = kTileX * kTileY * kTileZ * 4;
+static_assert(kBrickLx == 0 && kBrickLy == 2 && kBrickLz == 3, "the experiment assumes the 1x4x8 brick shape");
+
+#define CK(x)                                                                         \
+    do {                                                                              \
+        cudaError_t e_ = (x);                                                         \
+        if (e_ != cudaSuccess) {                                                      \
+            fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_));                  \
+            exit(1);                                                                  \
+        }                                                                             \
+    } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct MarchJob {
+    SceneView scene;
+    const float* dirs;   // rays per probe x 3
+    int n_dirs;
+    int probe_count[3];
+    int side;
+    float2* out;         // per ray (t, steps)
+};
+
+template <bool kStaged>
+__global__ void __launch_bounds__(256) primary_march(const __grid_constant__ MarchJob J, const __grid_constant__ CUtensorMap tmap)
+{
+    __shared__ alignas(128) uint32_t tile[kStaged ? kTileX * kTileY * kTileZ : 1];
+    __shared__ alignas(8) unsigned long long mbar;
+    const int p = blockIdx.x;
+    const int X = J.probe_count[0], Y = J.probe_count[1], Z = J.probe_count[2];
+    const int py = p / (X * Z), rest = p - py * X * Z, pz = rest / X, px = rest - pz * X;
+    const v3 origin = V3((float)((px - (X - 1) / 2) * J.side), (float)((py - (Y - 1) / 2) * J.side), (float)((pz - (Z - 1) / 2) * J.side));
+    // tile origin in brick coordinates: the probe's brick minus half a tile
+    const int cgx = (int)origin.x - J.scene.borg[0], cgy = (int)origin.y - J.scene.borg[1], cgz = (int)origin.z - J.scene.borg[2];
+    const int tx0 = (cgx >> kBrickLx) - kTileX / 2, ty0 = (cgy >> kBrickLy) - kTileY / 2, tz0 = (cgz >> kBrickLz) - kTileZ / 2;
+    if (kStaged) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(kTileBytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(tile)),
+                "l"(&tmap), "r"(tx0), "r"(ty0), "r"(tz0), "r"(smem_u32(&mbar))
+                : "memory");
+        }
+        // every thread waits for phase 0 of the barrier
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(&mbar))
+                : "memory");
+        }
+    }
+    for (int i = threadIdx.x; i < J.n_dirs; i += blockDim.x) {
+        v3 qd = V3(J.dirs[3 * i], J.dirs[3 * i + 1], J.dirs[3 * i + 2]);
+        float qlen = sqrtf(dot(qd, qd));
+        v3 md = qd * rcp_exact(qlen);
+        v3 inv = V3(rcp_regular(md.x), rcp_regular(md.y), rcp_regular(md.z));
+        v3 sel = V3(md.x > 0 ? 1.0f : 0.0f, md.y > 0 ? 1.0f : 0.0f, md.z > 0 ? 1.0f : 0.0f);
+        v3 pos = origin;
+        float t = 0.0f;
+        int steps = 0;
+        bool hit = false;
+        // (directions of the stratified table are regular: the fast step applies)
+        while (steps < kMarchSteps && !hit) {
+            float ax = div_markstein(sel.x - (pos.x - floor_small(pos.x)), md.x, inv.x);
+            float ay = div_markstein(sel.y - (pos.y - floor_small(pos.y)), md.y, inv.y);
+            float az = div_markstein(sel.z - (pos.z - floor_small(pos.z)), md.z, inv.z);
+            t += gmin(gmin(ax, ay), az) + 0.0001f;
+            pos = origin + md * t;
+            steps++;
+            int gx = float_bits(add_round_up(pos.x, kCellMagic)) + J.scene.kneg[0];
+            int gy = float_bits(add_round_up(pos.y, kCellMagic)) + J.scene.kneg[1];
+            int gz = float_bits(add_round_up(pos.z, kCellMagic)) + J.scene.kneg[2];
+            unsigned bx = (unsigned)gx >> kBrickLx, by = (unsigned)gy >> kBrickLy, bz = (unsigned)gz >> kBrickLz;
+            uint32_t word;
+            unsigned lx = bx - (unsigned)tx0, ly = by - (unsigned)ty0, lz = bz - (unsigned)tz0;
+            if (kStaged && lx < (unsigned)kTileX && ly < (unsigned)kTileY && lz < (unsigned)kTileZ) {
+                word = tile[(lz * kTileY + ly) * kTileX + lx];
+            } else {
+                bool inside = (bx < (unsigned)J.scene.nb[0]) & (by < (unsigned)J.scene.nb[1]) & (bz < (unsigned)J.scene.nb[2]);
+                word = occ_word(J.scene.occ, (bz * (unsigned)J.scene.nb[1] + by) * (unsigned)J.scene.nb[0] + bx, inside);
+            }
+            hit = (shr_wrap(word, occ_shift(gx, gy, gz)) & 1u) != 0;
+        }
+        J.out[(size_t)p * J.n_dirs + i] = make_float2(hit ? t : inf_f(), (float)steps);
+    }
+}
+
+int main(int argc, char** argv)
+{
+    const int probes_axis = argc > 1 ? atoi(argv[1]) : 32;   // probe field probes_axis^3, side 16, 512^3 voxels
+    const int reps = argc > 2 ? atoi(argv[2]) : 15;
+    ddgi_ctx* ctx = nullptr;
+    if (ddgi_create(&ctx, 0) != DDGI_OK) {
+        fprintf(stderr, "no sm_100 device\n");
+        return 2;
+    }
+    // the bench workload's voxel field (field_32): read the block types back and build the occupancy words here
+    int32_t dims[3] = {512, 512, 512}, org[3] = {-256, -256, -256};
+    if (ddgi_bake_synthetic(ctx, dims, org, 50, 0x9E3779B9u) != DDGI_OK) return 3;
+    std::vector<uint8_t> vox((size_t)512 * 512 * 512);
+    if (ddgi_read_voxels(ctx, vox.data(), vox.size()) != DDGI_OK) return 3;
+    SceneView S;
+    memset(&S, 0, sizeof(S));
+    int nb[3];
+    for (int a = 0; a < 3; a++) {
+        S.vorg[a] = org[a];
+        S.vdim[a] = dims[a];
+        S.borg[a] = org[a] & ~(kBrickAlign - 1);
+        S.kneg[a] = -(kCellBias + S.borg[a]);
+        int cells = 1 << (a == 0 ? kBrickLx : a == 1 ? kBrickLy : kBrickLz);
+        nb[a] = S.nb[a] = (org[a] + dims[a] - S.borg[a] + cells - 1) / cells;
+    }
+    std::vector<uint32_t> occ((size_t)nb[0] * nb[1] * nb[2], 0u);
+    for (int z = 0; z < 512; z++)
+        for (int y = 0; y < 512; y++)
+            for (int x = 0; x < 512; x++)
+                if (vox[((size_t)z * 512 + y) * 512 + x]) {
+                    int gx = x + org[0] - S.borg[0], gy = y + org[1] - S.borg[1], gz = z + org[2] - S.borg[2];
+                    occ[((size_t)(gz >> kBrickLz) * nb[1] + (gy >> kBrickLy)) * nb[0] + (gx >> kBrickLx)] |= 1u << (occ_shift(gx, gy, gz) & 31);
+                }
+    uint32_t* d_occ;
+    CK(cudaMalloc(&d_occ, occ.size() * 4));
+    CK(cudaMemcpy(d_occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice));
+    S.occ = d_occ;
+    // the engine's stratified ray table (16 x 16)
+    ddgi_irradiance_field f;
+    memset(&f, 0, sizeof(f));
+    f.probe_count[0] = f.probe_count[1] = f.probe_count[2] = probes_axis;
+    f.side_length = 16;
+    f.sqrt_rays_per_probe = 16;
+    ddgi_set_irradiance_field(ctx, &f);
+    srand(1);
+    ddgi_generate_probe_rays(ctx, 1);
+    std::vector<float> samples(256 * 3), dirs(256 * 3);
+    ddgi_get_ray_samples(ctx, samples.data(), 256);
+    for (int i = 0; i < 256; i++) {
+        v3 d = normalize(V3(samples[3 * i], samples[3 * i + 1], samples[3 * i + 2]));
+        dirs[3 * i] = d.x;
+        dirs[3 * i + 1] = d.y;
+        dirs[3 * i + 2] = d.z;
+    }
+    float* d_dirs;
+    CK(cudaMalloc(&d_dirs, dirs.size() * 4));
+    CK(cudaMemcpy(d_dirs, dirs.data(), dirs.size() * 4, cudaMemcpyHostToDevice));
+    const int n_probes = probes_axis * probes_axis * probes_axis;
+    float2 *d_a, *d_b;
+    CK(cudaMalloc(&d_a, (size_t)n_probes * 256 * sizeof(float2)));
+    CK(cudaMalloc(&d_b, (size_t)n_probes * 256 * sizeof(float2)));
+
+    // tensor map over the occupancy words: 3-D uint32 [nbz][nby][nbx], box 64 x 16 x 8, zero fill outside
+    CUtensorMap tmap;
+    {
+        typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        cuuint64_t gdim[3] = {(cuuint64_t)nb[0], (cuuint64_t)nb[1], (cuuint64_t)nb[2]};
+        cuuint64_t gstride[2] = {(cuuint64_t)nb[0] * 4, (cuuint64_t)nb[0] * nb[1] * 4};
+        cuuint32_t box[3] = {kTileX, kTileY, kTileZ}, estride[3] = {1, 1, 1};
+        CUresult r = ((encode_t)fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_occ, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "cuTensorMapEncodeTiled failed: %d\n", (int)r);
+            return 4;
+        }
+    }
+    MarchJob J;
+    memset(&J, 0, sizeof(J));
+    J.scene = S;
+    J.dirs = d_dirs;
+    J.n_dirs = 256;
+    J.probe_count[0] = J.probe_count[1] = J.probe_count[2] = probes_axis;
+    J.side = 16;
+    uint8_t* flush;
+    CK(cudaMalloc(&flush, 256u << 20));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    auto run = [&](bool staged, float2* out) {
+        std::vector<float> ms;
+        J.out = out;
+        for (int r = 0; r < reps + 2; r++) {
+            CK(cudaMemset(flush, r, 256u << 20));
+            CK(cudaEventRecord(e0));
+            if (staged) primary_march<true><<<n_probes, 256>>>(J, tmap);
+            else primary_march<false><<<n_probes, 256>>>(J, tmap);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float t;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (r >= 2) ms.push_back(t);
+        }
+        std::sort(ms.begin(), ms.end());
+        return ms[ms.size() / 2];
+    };
+    float t_global = run(false, d_a), t_staged = run(true, d_b);
+    std::vector<float2> a((size_t)n_probes * 256), b(a.size());
+    CK(cudaMemcpy(a.data(), d_a, a.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), d_b, b.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    size_t diff = 0;
+    double steps = 0;
+    for (size_t i = 0; i < a.size(); i++) {
+        diff += memcmp(&a[i], &b[i], sizeof(float2)) != 0;
+        steps += a[i].y;
+    }
+    printf("primary marches of %d probes x 256 rays, %.1f steps per ray: global %.3f ms, TMA-staged %.3f ms (%.2fx), %zu of %zu results differ\n",
+           n_probes, steps / a.size(), t_global, t_staged, t_global / t_staged, diff, a.size());
+    ddgi_destroy(ctx);
+    return diff ? 5 : 0;
+}

@@ -352,6 +352,50 @@ def test_double_buffered_async_reads_match_single_buffered_frames():
     assert np.array_equal(frame_s, frame_d)
 
 
+@pytest.mark.parametrize("blend", [False, True])
+def test_two_frames_in_flight_give_the_same_frames(blend):
+    """ddgi_set_frames_in_flight(2): updates run on the engine's own two streams and overlap; six frames with moving
+    lights (and, with the hysteresis blend, a dependency between consecutive frames), each rendered and read back
+    asynchronously, and a voxel edit in the middle, equal the frames of the plain single-stream engine."""
+    cfg = CFG["field_8"]
+    frames = 6
+    edit_at = 3
+    box = np.full((6, 6, 6), 4, dtype=np.uint8)
+
+    def run(in_flight):
+        with make_engine(cfg, debug=False) as r:
+            if blend:
+                r.ir.hysteresis = 0.6
+                r.set_blend_mode(ddgi_b200.capi.BLEND_HYSTERESIS)
+            r.set_double_buffer(True)
+            r.set_frames_in_flight(in_flight)
+            W, H = r.probe_texture_size
+            w, h = cfg["screen"]
+            tex = [np.zeros((H, W), dtype=np.uint32) for _ in range(frames)]
+            img = []
+            for f in range(frames):
+                r.render_settings.time = 2.0 * (f + 1)
+                r.lights = util.configs.lights_for(cfg, r.render_settings.time)
+                r.update(advance_time=False)
+                if f == edit_at:
+                    r.edit_voxels(box, (2, 3, -4))   # must follow the updates in flight, precede this one
+                r.probe_update()
+                r.read_probe_texture_async(tex[f].ctypes.data, tex[f].nbytes, 0)
+                r.render_frame()
+                img.append(r.read_frame().copy())    # (synchronous: waits for the frame's render)
+            r.read_wait()
+            r.sync()
+            assert np.array_equal(r.read_probe_texture(0), tex[-1])
+            return [t.copy() for t in tex], img
+
+    tex1, img1 = run(1)
+    tex2, img2 = run(2)
+    for f in range(frames):
+        assert np.array_equal(tex1[f], tex2[f]), f"texture of frame {f}"
+        assert np.array_equal(img1[f], img2[f]), f"image of frame {f}"
+    assert not np.array_equal(tex1[edit_at - 1], tex1[edit_at])
+
+
 def test_field_32_full_size_sampled_parity_and_properties():
     """BASELINE configs[3] at its FULL size (32^3 probes x 256 rays = 8 388 608 probe rays, 512^3
     voxels, 4 moving lights).  The oracle cannot trace the whole field in seconds, so:
