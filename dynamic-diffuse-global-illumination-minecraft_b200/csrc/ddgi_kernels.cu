@@ -133,6 +133,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#ifndef DDGI_ENOUGH_HOISTED
+#define DDGI_ENOUGH_HOISTED 1
+#endif
 #ifndef DDGI_WF_MIN_BLOCKS
 #define DDGI_WF_MIN_BLOCKS 7  // 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
@@ -170,10 +173,19 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
 
     int round = 0;
     int n_live = lanes_used;  // lanes that hold a ray or may still take one (warp-uniform; FETCH retires lanes)
+    // lanes that must be marching for the march loop to go on: march_min/32 of the live lanes, at least one.
+    // (Kept in a register the compiler cannot re-derive - DDGI_OPAQUE - or it recomputes the five
+    // instructions from n_live and march_min in EVERY march step to save that register.)
+#if DDGI_ENOUGH_HOISTED
+#define DDGI_OPAQUE(x) asm volatile("" : "+r"(x))
+#else
+#define DDGI_OPAQUE(x)
+#endif
+    int enough = (n_live * march_min + 31) >> 5 > 1 ? (n_live * march_min + 31) >> 5 : 1;
+    DDGI_OPAQUE(enough);
     for (;;) {
         // ---- march while at least march_min/32 of the lanes holding a ray are marching ----
         if (n_live == 0) break;
-        const int enough = (n_live * march_min + 31) >> 5 > 1 ? (n_live * march_min + 31) >> 5 : 1;  // lanes
         while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) >= enough) {
             if (R.mode == WF_MARCH) wf_step(P, R);
         }
@@ -253,7 +265,12 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                     R.mode = WF_IDLE;
                 }
             }
-            n_live -= __popc(__ballot_sync(full, need && R.mode == WF_IDLE));
+            const int retired = __popc(__ballot_sync(full, need && R.mode == WF_IDLE));
+            if (retired) {
+                n_live -= retired;
+                enough = (n_live * march_min + 31) >> 5 > 1 ? (n_live * march_min + 31) >> 5 : 1;
+                DDGI_OPAQUE(enough);
+            }
         }
         // a finished bounce scatters at once, and every state above hands over to WF_QUERY or
         // ends the ray: arm the new queries right away.  Neither is scheduled as a state of
@@ -464,7 +481,7 @@ __global__ void build_occupancy_kernel(int dx, int dy, int dz, int sx, int sy, i
                     int gx = cx - sx, gy = cy - sy, gz = cz - sz;
                     if (gx >= 0 && gy >= 0 && gz >= 0 && gx < dx && gy < dy && gz < dz &&
                         types[((size_t)gz * dy + gy) * dx + gx] != 0)
-                        w |= 1u << (occ_shift(cx, cy, cz) & 31);
+                        w |= occ_mask(occ_shift(cx, cy, cz));
                 }
         occ[((size_t)bz * nby + by) * nbx + bx] = w;
     }

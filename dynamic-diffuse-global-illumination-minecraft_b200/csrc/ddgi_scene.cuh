@@ -91,6 +91,33 @@ DDGI_HD int occ_shift(int gx, int gy, int gz)
 #endif
 }
 
+// Where a cell's bit sits in its word.  DDGI_OCC_MSB (default): counted from the top, bit 31 - (shift mod 32), so
+// that the test is a wrapping left shift and a sign test (2 instructions of the march step instead of shift,
+// mask, compare).  Writers use occ_mask, readers occ_test: one definition.
+#ifndef DDGI_OCC_MSB
+#define DDGI_OCC_MSB 1
+#endif
+DDGI_HD uint32_t occ_mask(int shift)
+{
+#if DDGI_OCC_MSB
+    return 0x80000000u >> ((unsigned)shift & 31u);
+#else
+    return 1u << ((unsigned)shift & 31u);
+#endif
+}
+DDGI_HD bool occ_test(uint32_t word, int shift)
+{
+#if DDGI_OCC_MSB
+#ifdef __CUDA_ARCH__
+    return (int)__funnelshift_l(0u, word, (unsigned)shift) < 0;  // SHF.L.W: the count is taken mod 32
+#else
+    return (int)(word << ((unsigned)shift & 31u)) < 0;
+#endif
+#else
+    return (bool)(shr_wrap(word, shift) & 1u);
+#endif
+}
+
 // The occupancy word `idx` when `inside`, else 0 (bricks outside the grid are empty): one
 // predicated load, no branch, no divergence.
 DDGI_HD uint32_t occ_word(const uint32_t* occ, unsigned idx, bool inside)
@@ -114,7 +141,7 @@ DDGI_HD bool cell_solid(const SceneView& S, int kx, int ky, int kz)
     unsigned bx = (unsigned)gx >> kBrickLx, by = (unsigned)gy >> kBrickLy, bz = (unsigned)gz >> kBrickLz;  // (negative: huge)
     bool inside = (bx < (unsigned)S.nb[0]) & (by < (unsigned)S.nb[1]) & (bz < (unsigned)S.nb[2]);
     uint32_t word = occ_word(S.occ, (bz * (unsigned)S.nb[1] + by) * (unsigned)S.nb[0] + bx, inside);
-    return (bool)(shr_wrap(word, occ_shift(gx, gy, gz)) & 1u);
+    return occ_test(word, occ_shift(gx, gy, gz));
 }
 
 // Block type of an occupied cell (only called after its occupancy bit tested set).

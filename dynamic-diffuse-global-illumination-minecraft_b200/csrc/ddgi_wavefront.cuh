@@ -47,6 +47,10 @@
 #include "ddgi_fastmath.cuh"
 #include "ddgi_trace.cuh"
 
+#ifndef DDGI_STEP_TAIL
+#define DDGI_STEP_TAIL 1
+#endif
+
 namespace ddgi {
 
 enum : int {
@@ -178,10 +182,16 @@ DDGI_HD bool wf_step(const FrameParams& P, WfRay& R)
     // |p| < 2^22: p + 1.5*2^23 rounded up IS ceil(p) + 1.5*2^23 (one directed-rounding add)
     const bool solid = cell_solid(P.scene, float_bits(add_round_up(R.p.x, kCellMagic)), float_bits(add_round_up(R.p.y, kCellMagic)),
                                   float_bits(add_round_up(R.p.z, kCellMagic)));
+#if DDGI_STEP_TAIL == 1
+    const bool limit = (R.steps >= kMarchSteps) | (R.t > R.t_stop);
+    R.mode = solid ? WF_HIT : (limit ? WF_LIMIT : WF_MARCH);
+    return !(solid | limit);
+#else
     const bool limit = R.steps >= kMarchSteps || R.t > R.t_stop;
     if (solid) R.mode = WF_HIT;
     else if (limit) R.mode = WF_LIMIT;
     return !(solid || limit);
+#endif
 }
 
 // WF_MARCH_SLOW: the literal two-division form.

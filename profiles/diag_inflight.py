@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Diagnostic (1 GPU): ms per probe update of ONE rank's 1/world share of a workload with one and with two frames in
+flight (ddgi_set_frames_in_flight) - what overlapping the drain of the persistent kernel with the next update's first
+blocks is worth before any exchange cost.  K updates between two events, lights moved every step.  Not a bench value.
+
+    python profiles/diag_inflight.py [workload=field_32] [worlds=1,2,4,8] [steps=40]
+"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ddgi_b200  # noqa: E402
+from bench_support import workload_config  # noqa: E402
+
+configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
+name = sys.argv[1] if len(sys.argv) > 1 else "field_32"
+worlds = [int(w) for w in (sys.argv[2] if len(sys.argv) > 2 else "1,2,4,8").split(",")]
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+cfg = workload_config(name)
+r = ddgi_b200.RVPT(*cfg["screen"])
+configs.apply(r, cfg)
+r.generate_probe_rays(reseed=True)
+r.update(advance_time=False)
+stream = torch.cuda.current_stream()
+r.stream = stream.cuda_stream
+r.set_double_buffer(True)
+X, Y, Z = cfg["probe_count"]
+n = X * Y * Z * cfg["tile"][0] * cfg["tile"][1]
+frame = [0]
+
+
+def step():
+    frame[0] += 1
+    r.render_settings.time = 2.0 * frame[0]
+    r.lights = configs.lights_for(cfg, r.render_settings.time)
+    r.update(advance_time=False)
+    r.probe_update()
+
+
+for world in worlds:
+    r.set_frames_in_flight(1)
+    r.set_probes_cyclic(0, world, 1)
+    res = {}
+    for fl in (1, 2, 1, 2):
+        r.set_frames_in_flight(fl)
+        for _ in range(5):
+            step()
+        r.frame_fence()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(K):
+            step()
+        r.frame_fence()
+        b.record(stream)
+        torch.cuda.synchronize()
+        res.setdefault(fl, []).append(a.elapsed_time(b) / K)
+    r.set_frames_in_flight(1)
+    m1, m2 = min(res[1]), min(res[2])
+    print(f"{name} 1/{world} share ({n // world} rays): one frame at a time {m1:.3f} ms, two in flight {m2:.3f} ms ({m1 / m2:.3f}x); "
+          f"x{world} = {n / m1 / 1e3:.0f} -> {n / m2 / 1e3:.0f} M probe-rays/s if the exchange were free", flush=True)
+r.close()

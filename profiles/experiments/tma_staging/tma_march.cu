@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) primary_march(const __grid_constant__ Mar
                 bool inside = (bx < (unsigned)J.scene.nb[0]) & (by < (unsigned)J.scene.nb[1]) & (bz < (unsigned)J.scene.nb[2]);
                 word = occ_word(J.scene.occ, (bz * (unsigned)J.scene.nb[1] + by) * (unsigned)J.scene.nb[0] + bx, inside);
             }
-            hit = (shr_wrap(word, occ_shift(gx, gy, gz)) & 1u) != 0;
+            hit = occ_test(word, occ_shift(gx, gy, gz));
         }
         J.out[(size_t)p * J.n_dirs + i] = make_float2(hit ? t : inf_f(), (float)steps);
     }
@@ -152,7 +152,7 @@ int main(int argc, char** argv)
             for (int x = 0; x < 512; x++)
                 if (vox[((size_t)z * 512 + y) * 512 + x]) {
                     int gx = x + org[0] - S.borg[0], gy = y + org[1] - S.borg[1], gz = z + org[2] - S.borg[2];
-                    occ[((size_t)(gz >> kBrickLz) * nb[1] + (gy >> kBrickLy)) * nb[0] + (gx >> kBrickLx)] |= 1u << (occ_shift(gx, gy, gz) & 31);
+                    occ[((size_t)(gz >> kBrickLz) * nb[1] + (gy >> kBrickLy)) * nb[0] + (gx >> kBrickLx)] |= occ_mask(occ_shift(gx, gy, gz));
                 }
     uint32_t* d_occ;
     CK(cudaMalloc(&d_occ, occ.size() * 4));

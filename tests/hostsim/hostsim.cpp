@@ -67,7 +67,7 @@ static void build(const SimParams* S, const float* cam, Built* B)
             for (int x = 0; x < S->vdim[0]; x++)
                 if (S->vox[((size_t)z * S->vdim[1] + y) * S->vdim[0] + x]) {
                     int bx = x + sh[0], by = y + sh[1], bz = z + sh[2];
-                    B->occ[((size_t)(bz >> kBrickLz) * nb[1] + (by >> kBrickLy)) * nb[0] + (bx >> kBrickLx)] |= 1u << (occ_shift(bx, by, bz) & 31);
+                    B->occ[((size_t)(bz >> kBrickLz) * nb[1] + (by >> kBrickLy)) * nb[0] + (bx >> kBrickLx)] |= occ_mask(occ_shift(bx, by, bz));
                 }
     P.scene.occ = B->occ.data();
     P.scene.types = S->vox;
