@@ -126,7 +126,12 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // is issued once for both.
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
-constexpr int kWfThreads = 128;
+#ifndef DDGI_WF_THREADS
+#define DDGI_WF_THREADS 128
+#endif
+constexpr int kWfThreads = DDGI_WF_THREADS;  // (the warps of a block share nothing: the block size only decides how many
+                                             // warps must have drained before the SM takes the next block; 32 / 64 / 128
+                                             // measured within 0.6 % of each other, profiles/r2_ab.md h)
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
@@ -137,7 +142,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 #define DDGI_ENOUGH_HOISTED 1
 #endif
 #ifndef DDGI_WF_MIN_BLOCKS
-#define DDGI_WF_MIN_BLOCKS 7  // 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
+#define DDGI_WF_MIN_BLOCKS (896 / DDGI_WF_THREADS)  // 7 blocks of 128: 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
 
 template <bool kLiteral, bool kTimed>

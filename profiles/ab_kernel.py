@@ -14,7 +14,7 @@ names = (sys.argv[1] if len(sys.argv) > 1 else "field_32").split(",")
 variants = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "2").split(",")]
 mms = [int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else "16").split(",")]
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 15
-lib = os.path.basename(os.environ.get("DDGI_LIB", "default"))
+lib = os.path.basename(os.environ.get("DDGI_LIB") or "default")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for name in names:
     cfg = workload_config(name)

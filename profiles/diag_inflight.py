@@ -8,6 +8,7 @@ blocks is worth before any exchange cost.  K updates between two events, lights 
 import importlib
 import os
 import sys
+import time
 
 import torch
 
@@ -44,7 +45,7 @@ def step():
 for world in worlds:
     r.set_frames_in_flight(1)
     r.set_probes_cyclic(0, world, 1)
-    res = {}
+    res, host = {}, {}
     for fl in (1, 2, 1, 2):
         r.set_frames_in_flight(fl)
         for _ in range(5):
@@ -53,14 +54,17 @@ for world in worlds:
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
+        t0 = time.perf_counter()
         for _ in range(K):
             step()
+        host[fl] = (time.perf_counter() - t0) / K * 1e3
         r.frame_fence()
         b.record(stream)
         torch.cuda.synchronize()
         res.setdefault(fl, []).append(a.elapsed_time(b) / K)
     r.set_frames_in_flight(1)
     m1, m2 = min(res[1]), min(res[2])
-    print(f"{name} 1/{world} share ({n // world} rays): one frame at a time {m1:.3f} ms, two in flight {m2:.3f} ms ({m1 / m2:.3f}x); "
+    print(f"{os.path.basename(os.environ.get('DDGI_LIB', '') or 'default'):20s} host enqueue {host[1]:.3f} / {host[2]:.3f} ms per step; "
+          f"{name} 1/{world} share ({n // world} rays): one frame at a time {m1:.3f} ms, two in flight {m2:.3f} ms ({m1 / m2:.3f}x); "
           f"x{world} = {n / m1 / 1e3:.0f} -> {n / m2 / 1e3:.0f} M probe-rays/s if the exchange were free", flush=True)
 r.close()
