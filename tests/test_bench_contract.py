@@ -53,3 +53,9 @@ def test_gpu_arm_line_has_the_contract_keys():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 1024 * 64 * 4
     assert e["value"] != d["value"]
+    # one GPU: one frame at a time unless asked for; the pipeline behind `value` is named
+    assert d["config"]["frames_in_flight"] == 1 and d["pipelines"]["value_is"] == "one_frame_at_a_time"
+    assert d["pipelines"]["two_frames_in_flight"] is None
+    d2 = run("--workload", "cave_64", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-ncu", "--frames-in-flight", "2")
+    assert d2["config"]["frames_in_flight"] == 2 and d2["pipelines"]["value_is"] == "two_frames_in_flight"
+    assert d2["gpu_launches"] == d2["steps"] and d2["ms_per_step"] == d2["pipelines"]["two_frames_in_flight"]["ms_per_step"]
