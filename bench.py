@@ -470,6 +470,19 @@ def main():
         if performed is not None:
             dist.all_reduce(performed)
     mean_lookups = float(lk_sum[0]) / n_rays
+    # the pixel pass against SURVEY 8d's bytes per pixel: 4 B x voxel lookups (primary + feelers, counted by the
+    # instrumented kernel) + 8 probes x (1 + taps) x 4 B + the 4-B store, taps at their upper bound of 25
+    pixel_roofline = None
+    if world == 1:
+        r.render_frame()
+        r.sync()
+        w_px, h_px = cfg["screen"]
+        px_lk = r.read_lookup_counts(1).reshape(h_px, w_px)[band[0]:band[1], :(w_px // 16) * 16]
+        bytes_px = 4.0 * float(px_lk.mean()) + 8 * 26 * 4 + 4
+        px_gbs = px_lk.size * bytes_px / (pixel_ms * 1e-3) / 1e9
+        pixel_roofline = {"bound": "hbm", "kernel": "render_frame_kernel", "kernel_ms": pixel_ms, "pixels": int(px_lk.size),
+                          "mean_lookups_per_pixel": float(px_lk.mean()), "bytes_per_pixel": bytes_px, "achieved": px_gbs,
+                          "unit": "GB/s", "note": "SURVEY 8d bytes per pixel with the tile gathers at their upper bound (25 taps)"}
     r.set_kernel_variant(args.variant)
     r.set_debug(False)
     bytes_per_ray = 4.0 * mean_lookups + 8.0
@@ -657,6 +670,7 @@ def main():
             "exchange_nccl": exchange_nccl,
             "fps": {"value": 1000.0 / frame_ms, "frame_ms": frame_ms, "pixel_pass_ms": pixel_ms,
                     "resolution": list(cfg["screen"]), "pixel_rows_rank0": list(band),
+                    "pixel_roofline": None if not pixel_roofline else dict(pixel_roofline, peak=peak, frac=pixel_roofline["achieved"] / peak),
                     "note": "probe update + exchange + pixel pass; pixel rows split across ranks"},
         }
         print(json.dumps(out), flush=True)

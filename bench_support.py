@@ -96,15 +96,20 @@ def _time_oracle(cfg, voxels, steps, warmup, time0=0.0, budget_s=200.0):
 def _reference_shaders_available(cfg):
     """oracle/_ref (the reference's own shaders transpiled to C++) has the reference's scenes, light
     tables and square ray tiles compiled in: it can run a workload only if that is what the workload is
-    (the Cornell configs; the cave workloads use flat colours and field_32 a synthetic voxel field)."""
+    (the Cornell configs, and the cave with a square tile - cave_128, sweep_64 / 256 / 1024 - where the shaders run
+    their own procedural, unbounded scene 0 with its procedural colours, intersection.glsl:699-756, 872-1047: the
+    same algorithm and ray set as the workload the GPU arm times over the baked box; field_32 is a synthetic
+    voxel field no shader text describes)."""
     from oracle import ref
 
-    return ref.available() and cfg["scene"] == 1 and cfg["lights"] == "default" and cfg["tile"][0] == cfg["tile"][1]
+    return ref.available() and cfg["scene"] in (0, 1) and cfg["lights"] == "default" and cfg["tile"][0] == cfg["tile"][1]
 
 
-def _time_reference_shaders(cfg, steps, warmup):
-    """probe_pass.comp itself (transpiled, 1 thread: the shader's globals are process-wide) over ALL
-    probe rays of the workload."""
+def _time_reference_shaders(cfg, steps, warmup, budget_s=150.0):
+    """probe_pass.comp itself (transpiled, 1 thread: the shader's globals are process-wide) over the probe rays
+    of the workload: all of them if `warmup + steps` passes fit in `budget_s` (the Cornell configs), else over every
+    k-th probe (all rays of a sampled probe; k chosen from a first pass over every 64th probe), so that the run
+    stays bounded whatever K / W the caller asks for."""
     from oracle import oracle, ref
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -112,24 +117,48 @@ def _time_reference_shaders(cfg, steps, warmup):
 
     s = cfg["tile"][0]
     sc = util.oracle_scene(cfg, procedural=True)
-    rays = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True))
-    times = []
-    for i in range(warmup + steps):
+    rays_all = oracle.generate_probe_rays(sc, oracle.generate_samples(s, s, reseed=True))
+    n_probes = rays_all.shape[0] // (s * s)
+
+    def run(rays):
         t0 = time.perf_counter()
         out = ref.probe_pass(scene=cfg["scene"], probe_count=cfg["probe_count"], side_length=cfg["side_length"],
                              field_origin=cfg["field_origin"], s=s, rays=rays, max_bounces=cfg.get("max_bounces", 8))
+        return time.perf_counter() - t0, out
+
+    def every(k):
+        return np.ascontiguousarray(rays_all.reshape(n_probes, s * s, -1)[k // 2::k].reshape(-1, rays_all.shape[1]))
+
+    stride = 1
+    if n_probes > 64:
+        probe = every(64)
+        dt, _ = run(probe)
+        per_ray = dt / probe.shape[0]
+        while stride < n_probes and per_ray * (rays_all.shape[0] / stride) * (warmup + steps) > budget_s:
+            stride *= 2
+    rays = rays_all if stride == 1 else every(stride)
+    times = []
+    for i in range(warmup + steps):
+        dt, out = run(rays)
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return {"rays": rays.shape[0], "seconds": float(np.mean(times)), "mean_lookups": float(out[3].mean())}
+            times.append(dt)
+    return {"rays": rays.shape[0], "seconds": float(np.mean(times)), "mean_lookups": float(out[3].mean()),
+            "of": rays_all.shape[0], "stride": stride}
+
+
+def _shader_sample(res):
+    if res["stride"] == 1:
+        return f"all {res['rays']} probe rays"
+    return f"every {res['stride']}th probe = {res['rays']} of {res['of']} probe rays"
 
 
 def cpu_baseline(rvpt, cfg, name):
     """The CPU side of the comparison on the host cores: the reference's own shaders (oracle/_ref,
     kind "reference") where they can run the workload, else the oracle ("port") over a bounded sample."""
     if _reference_shaders_available(cfg):
-        res = _time_reference_shaders(cfg, steps=3, warmup=1)
+        res = _time_reference_shaders(cfg, steps=3, warmup=1, budget_s=30.0)
         return {"value": res["rays"] / res["seconds"], "unit": "probe-rays/s", "cores": 1, "kind": "reference",
-                "sample": f"all {res['rays']} probe rays per step, mean of 3 steps: the reference's probe_pass.comp transpiled "
+                "sample": f"{_shader_sample(res)} per step, mean of 3 steps: the reference's probe_pass.comp transpiled "
                           f"to C++ (oracle/_ref), single thread",
                 "mean_lookups_per_ray_in_sample": res["mean_lookups"]}
     X, Y, Z = cfg["probe_count"]
@@ -155,7 +184,7 @@ def reference_arm(args, name):
     if _reference_shaders_available(cfg):
         res = _time_reference_shaders(cfg, steps=steps, warmup=warmup)
         kind, cores = "reference", 1
-        sample = (f"all {res['rays']} probe rays per step: the reference's own probe_pass.comp transpiled to C++ "
+        sample = (f"{_shader_sample(res)} per step: the reference's own probe_pass.comp transpiled to C++ "
                   f"(oracle/_ref), single thread (its globals are process-wide)")
     else:
         vox, _ = util.oracle_voxels(cfg)

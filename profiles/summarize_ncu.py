@@ -2,6 +2,7 @@
 """Writes the judged summary of one `ncu --set full` capture (read here, no GPU needed).
 
     python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep probe_update_wavefront field_32 8388608 > profiles/<name>.txt
+    python profiles/summarize_ncu.py gpurun_out/prof_px.ncu-rep render_frame_kernel field_32 2058240 > profiles/<name>.txt   (pixels)
 
 Also refreshes profiles/traffic.json (dram bytes per launch; bench.py copies it into
 roofline.traffic for the same workload).
@@ -42,13 +43,18 @@ def main():
     h, u, d = rows[0], rows[1], rows[2]
     m = {n: (d[i], u[i]) for i, n in enumerate(h)}
     print(f"# ncu --set full --clock-control none --import-source on, kernel {m['Kernel Name'][0][:70]}")
-    print(f"# capture {os.path.basename(rep)}; workload {workload}; {int(n_rays)} probe rays per launch")
+    unit_name = "probe ray" if kernel.startswith("probe_update") else "pixel"
+    print(f"# capture {os.path.basename(rep)}; workload {workload}; {int(n_rays)} {unit_name}s per launch")
     for k in KEYS:
         if k in m:
             print(f"{k:70s} {m[k][0]:>18s} {m[k][1]}")
     rd = to_bytes(*m["dram__bytes_read.sum"])
     wr = to_bytes(*m["dram__bytes_write.sum"])
-    print(f"{'dram bytes per launch (read + write)':70s} {rd + wr:18.0f} byte  = {(rd + wr) / n_rays:.1f} B / probe ray")
+    print(f"{'dram bytes per launch (read + write)':70s} {rd + wr:18.0f} byte  = {(rd + wr) / n_rays:.1f} B / {unit_name}")
+    if not kernel.startswith("probe_update"):
+        # the pixel pass: no state machine to split by; the per-function split of the source page instead
+        lib = os.path.join(ROOT, "dynamic-diffuse-global-illumination-minecraft_b200", "libddgi_b200.so")
+        return
     with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
         json.dump({"workload": workload, "kernel": kernel, "capture": os.path.basename(rep),
                    "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr}, f, indent=1)
