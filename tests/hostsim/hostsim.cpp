@@ -10,7 +10,6 @@
 #include <vector>
 
 #include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_shade.cuh"
-#include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_overlap.cuh"
 #include "../../dynamic-diffuse-global-illumination-minecraft_b200/csrc/ddgi_wavefront.cuh"
 
 using namespace ddgi;
@@ -113,12 +112,7 @@ void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32
 {
     Built B;
     build(S, nullptr, &B);
-    // variants 3 / 4: the two-slot state machine of ddgi_overlap.cuh (feelers of bounce k marched together with the
-    // ray of bounce k+1) without / with the early-out; 13 and 23: variant 3 with three feeler steps per bounce step
-    // and the other way round (any interleaving of the two slots must give the same result)
-    B.P.early_out = variant == 2 || variant == 4;
-    const bool overlap = variant >= 3;
-    const int f_steps = variant == 13 ? 3 : 1, b_steps = variant == 23 ? 3 : 1;
+    B.P.early_out = variant == 2;
     const FrameParams& P = B.P;
     int W = P.probe_count[0] * P.probe_count[2] * P.rx;
     int tiles_x = P.probe_count[0] * P.probe_count[2];
@@ -132,8 +126,7 @@ void sim_probe_update(const SimParams* S, const float* rays /* R x 12 */, uint32
         uint32_t n = 0;
         float first_t = 0.0f;
         v3 c = variant == 0 ? trace_probe_ray(P, o, d, (uint32_t)k, n, &first_t)
-               : overlap   ? overlap_trace_scalar(P, o, d, (uint32_t)k, n, &first_t, f_steps, b_steps)
-                           : wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
+                            : wavefront_trace_scalar(P, o, d, (uint32_t)k, n, &first_t);
         size_t t = (size_t)ty * W + tx;
         if (S->blend_mode) c = blend_hysteresis(albedo[t], c, S->hysteresis);
         albedo[t] = pack_rgba8(c.x, c.y, c.z, 1.0f);
