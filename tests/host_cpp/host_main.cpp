@@ -61,6 +61,13 @@ int main(int argc, char** argv)
             std::fprintf(stderr, "initialize failed: %s\n", rvpt.last_error().c_str());
             return 2;
         }
+        if (const char* fl = std::getenv("DDGI_FRAMES_IN_FLIGHT")) {
+            // the reference keeps MAX_FRAMES_IN_FLIGHT = 2 (src/rvpt/rvpt.h:23): updates on the engine's own two streams
+            if (ddgi_set_double_buffer(rvpt.context(), 1) != DDGI_OK || ddgi_set_frames_in_flight(rvpt.context(), atoi(fl)) != DDGI_OK) {
+                std::fprintf(stderr, "frames in flight: %s\n", ddgi_last_error(rvpt.context()));
+                return 2;
+            }
+        }
         for (int f = 0; f < frames; f++) {
             if (!rvpt.update() || rvpt.draw() != ddgi::RVPT::draw_return::success) {
                 std::fprintf(stderr, "frame %d failed: %s\n", f, rvpt.last_error().c_str());

@@ -49,15 +49,21 @@ def test_cpp_host_reports_a_missing_device_instead_of_falling_back():
 
 
 @pytest.mark.gpu
-def test_cpp_host_main_loop_reproduces_the_reference_fixture(tmp_path):
+@pytest.mark.parametrize("in_flight", [None, 2])
+def test_cpp_host_main_loop_reproduces_the_reference_fixture(tmp_path, in_flight):
     """generate_probe_rays() / initialize() / update() / draw() from C++ on Cornell 3x3x3: probe texture
     and frame must equal the reference-shader fixture (the texture does not depend on the frame
-    number: static lights, frame-invariant RNG)."""
+    number: static lights, frame-invariant RNG) - one frame at a time and with two frames in flight
+    (ddgi_set_frames_in_flight, as the reference's MAX_FRAMES_IN_FLIGHT = 2)."""
     g = np.load(os.path.join(HERE, "golden", "cornell_3x3x3.npz"))
     w, h = (int(v) for v in g["screen"])
     out = str(tmp_path / "frame.bin")
     args = ["frame", "1", "3", "3", "3", "11", "8", "0", "0", "15", str(w), str(h), "0", "0", "-5", "0", "0", "0", "3", out]
-    msg = subprocess.check_output([build(), *args], text=True)
+    env = dict(os.environ)
+    env.pop("DDGI_FRAMES_IN_FLIGHT", None)
+    if in_flight:
+        env["DDGI_FRAMES_IN_FLIGHT"] = str(in_flight)
+    msg = subprocess.check_output([build(), *args], text=True, env=env)
     assert msg.startswith("ok 1728 probe rays, time 6.0")
     raw = np.fromfile(out, dtype=np.uint32)
     W, H, fw, fh = (int(v) for v in raw[:4].view(np.int32))
