@@ -30,6 +30,10 @@ r.update(advance_time=False)
 stream = torch.cuda.current_stream()
 r.stream = stream.cuda_stream
 r.set_double_buffer(True)
+if os.environ.get('AUTO') == '0':
+    r.set_auto_schedule(False)   # natural probe order instead of most expensive first
+if os.environ.get('SLOT'):
+    r.set_schedule_slot(int(os.environ['SLOT']))
 X, Y, Z = cfg["probe_count"]
 n = X * Y * Z * cfg["tile"][0] * cfg["tile"][1]
 frame = [0]
@@ -89,6 +93,6 @@ for world, limit in [(w, l) for w in worlds for l in limits]:
     r.set_frames_in_flight(1)
     m1, m2 = min(res[1]), min(res[2])
     print(f"{os.path.basename(os.environ.get('DDGI_LIB', '') or 'default'):20s} host enqueue {host[1]:.3f} / {host[2]:.3f} ms per step; "
-          f"flush {mode} grid limit {limit}: {name} 1/{world} share ({n // world} rays): one frame at a time {m1:.3f} ms, two in flight {m2:.3f} ms ({m1 / m2:.3f}x); "
+          f"auto {os.environ.get('AUTO', '1')} slot {os.environ.get('SLOT', '32')} flush {mode} grid limit {limit}: {name} 1/{world} share ({n // world} rays): one frame at a time {m1:.3f} ms, two in flight {m2:.3f} ms ({m1 / m2:.3f}x); "
           f"x{world} = {n / m1 / 1e3:.0f} -> {n / m2 / 1e3:.0f} M probe-rays/s if the exchange were free", flush=True)
 r.close()
