@@ -327,7 +327,10 @@ def main():
         r.probe_update()
         exchange()
 
-    flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    # the L2 flush: one write of a buffer 1.25 x the L2 (rounded up to 32 MiB: 160 MiB for B200's 126 MB)
+    l2_bytes = int(torch.cuda.get_device_properties(local).L2_cache_size)
+    flush_mib = max(64, -(-(l2_bytes * 5 // 4) // (32 << 20)) * 32)
+    flush_buf = None if args.no_flush else torch.empty(flush_mib << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
     def flush_l2():
         if flush_buf is not None:
@@ -373,7 +376,7 @@ def main():
         """-> ms per step with two frames in flight (ddgi_set_frames_in_flight): the updates run on the engine's own
         two streams, so per-step events on this stream would bracket nothing; K steps between two events, the second
         behind a fence on every frame in flight.  Consecutive updates overlap in time and share the L2 by
-        construction, so "cold L2 per step" has no meaning here; the same 256 MiB write is still issued once per step,
+        construction, so "cold L2 per step" has no meaning here; the same write (1.25 x the L2) is still issued once per step,
         on a side stream and inside the timed region (ordered in front of an update it would hold the update back
         until the previous one has drained - the overlap this mode exists for)."""
         def run(n):
@@ -646,8 +649,8 @@ def main():
                        "probe_rays": n_rays, "voxels": list(cfg["voxels"][1]), "lights": 4 if cfg["lights"] == "cave4" else 1,
                        "max_bounces": cfg.get("max_bounces", 8), "resolution": list(cfg["screen"]),
                        "l2": ("not flushed" if flush_buf is None else
-                              "one 256 MiB write per step on a side stream, inside the timed region (two frames in flight share the L2)" if in_flight else
-                              "flushed between timed steps (256 MiB write)"),
+                              f"one {flush_mib} MiB write (L2 = {l2_bytes / 1e6:.0f} MB) per step on a side stream, inside the timed region (two frames in flight share the L2)" if in_flight else
+                              f"flushed between timed steps ({flush_mib} MiB write, L2 = {l2_bytes / 1e6:.0f} MB)"),
                        "frames_in_flight": args.frames_in_flight,
                        "kernel_variant": args.variant, "exchange": args.exchange if world > 1 else "none",
                        "sharding": shard_desc if world > 1 else "none"},
