@@ -293,7 +293,11 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
 // the rays (ddgi_octahedral.cuh: oct_lane_partial), the partial sums meet in an xor-butterfly
 // of warp shuffles — the north star's "warp-shuffle reduction of ray radiance into texels" — and
 // lane 0 blends and stores the two texels (into every replica under the fused exchange).
+#ifndef DDGI_OCT_TMA
+#define DDGI_OCT_TMA 1
+#endif
 constexpr int kOctThreads = 128;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ OctAcc oct_shuffle_xor(OctAcc a, int off)
 {
     OctAcc b;
@@ -308,20 +312,52 @@ __device__ __forceinline__ OctAcc oct_shuffle_xor(OctAcc a, int off)
 __global__ void __launch_bounds__(kOctThreads) probe_blend_octahedral(const __grid_constant__ FrameParams P,
                                                                       const __grid_constant__ OctJob J)
 {
-    extern __shared__ float s_oct[];
+    extern __shared__ __align__(16) float s_oct[];
+    __shared__ __align__(8) unsigned long long s_bar;
     float* s_dirs = s_oct;                 // n x 3
     float* s_rad = s_oct + 3 * J.n_rays;   // n x 4
     const uint32_t p = J.probes[blockIdx.x];
-    for (int i = threadIdx.x; i < 3 * J.n_rays; i += kOctThreads) s_dirs[i] = J.dirs[i];
     const float4* mine = J.ray_out + (size_t)p * J.n_rays;
-    for (int i = threadIdx.x; i < J.n_rays; i += kOctThreads) {
-        float4 v = mine[i];
-        s_rad[4 * i] = v.x;
-        s_rad[4 * i + 1] = v.y;
-        s_rad[4 * i + 2] = v.z;
-        s_rad[4 * i + 3] = v.w;
+    if (DDGI_OCT_TMA && J.n_rays % 4 == 0) {
+        // TMA staging: the probe's ray directions (12 n bytes) and ray results (16 n bytes) are two contiguous,
+        // 16-byte aligned ranges that every warp of the block reads for every texel of the tile.  One thread
+        // issues two bulk copies (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier);
+        // the block waits on the barrier's first phase - no per-thread load / store loop, no register staging.
+        const uint32_t bar = smem_u32(&s_bar);
+        const uint32_t bytes_dirs = 12u * (uint32_t)J.n_rays, bytes_rad = 16u * (uint32_t)J.n_rays;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_dirs + bytes_rad) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_dirs)),
+                         "l"(J.dirs), "r"(bytes_dirs), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_rad)),
+                         "l"(mine), "r"(bytes_rad), "r"(bar)
+                         : "memory");
+        }
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(done)
+                         : "r"(bar)
+                         : "memory");
+        }
+    } else {
+        // (a ray count that is not a multiple of 4 breaks the 16-byte granularity of the bulk copy: plain loads)
+        for (int i = threadIdx.x; i < 3 * J.n_rays; i += kOctThreads) s_dirs[i] = J.dirs[i];
+        for (int i = threadIdx.x; i < J.n_rays; i += kOctThreads) {
+            float4 v = mine[i];
+            s_rad[4 * i] = v.x;
+            s_rad[4 * i + 1] = v.y;
+            s_rad[4 * i + 2] = v.z;
+            s_rad[4 * i + 3] = v.w;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int cx, cy;
     tile_origin(P, (int)p, &cx, &cy);
