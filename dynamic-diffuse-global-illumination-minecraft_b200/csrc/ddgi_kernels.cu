@@ -55,6 +55,30 @@ __device__ __forceinline__ RayIn fetch_ray(const FrameParams& P, const ProbeJob&
     return r;
 }
 
+// Destination texel of ray k (what fetch_ray also returns): the wavefront kernel recomputes it when the ray is
+// stored instead of holding two registers for the ray's whole life.
+__device__ __forceinline__ void texel_of_ray(const FrameParams& P, const ProbeJob& J, uint32_t k, int* tx, int* ty)
+{
+    int tiles_x = P.probe_count[0] * P.probe_count[2];
+    int p, x, y;
+    if (J.rays) {
+        float4 c = __ldg(J.rays + 3 * (size_t)k + 2);
+        p = f2i(c.x);
+        x = f2i(c.y);
+        y = f2i(c.z);
+    } else {
+        int n = P.rx * P.ry;
+        p = (int)(k / (uint32_t)n);
+        int i = (int)(k - (uint32_t)p * (uint32_t)n);
+        y = i / P.rx;
+        x = i - y * P.rx;
+    }
+    int yp = p / tiles_x;
+    int xp = p - yp * tiles_x;
+    *tx = xp * P.rx + x;
+    *ty = yp * P.ry + y;
+}
+
 // Linear ray index (the reference's position in the ProbeRay list) of the idx-th ray of this shard.
 __device__ __forceinline__ uint32_t shard_ray(const ProbeJob& J, uint32_t idx)
 {
@@ -145,7 +169,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 #define DDGI_WF_MIN_BLOCKS (896 / DDGI_WF_THREADS)  // 7 blocks of 128: 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
 
-template <bool kLiteral, bool kTimed>
+// kCount: the per-ray voxel-lookup count is kept (debug buffers, the calibration launch of the schedule); the
+// normal launch does not carry the counter.
+template <bool kLiteral, bool kTimed, bool kCount>
 __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_wavefront(const __grid_constant__ FrameParams P,
                                                                      const __grid_constant__ ProbeJob J,
                                                                      uint32_t* __restrict__ next_ray,
@@ -163,7 +189,6 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     // throughput: it is spread over all resident warps with only `lanes_used` lanes of each holding rays)
     R.mode = lane < lanes_used ? WF_FETCH : WF_IDLE;
     uint32_t k = 0xffffffffu;  // no ray yet
-    int tx = 0, ty = 0;
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: ray indices already reserved
     bool exhausted = false;
     // debug level 2 (kTimed instantiation only — measured: even a never-taken test of
@@ -176,8 +201,9 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     } while (0)
     if (lane == 0) DDGI_WARP_TIME(0);
 
-    int round = 0;
-    int n_live = lanes_used;  // lanes that hold a ray or may still take one (warp-uniform; FETCH retires lanes)
+    // lanes that hold a ray or may still take one (FETCH retires lanes) in the low byte, the number of scheduling
+    // rounds above it; warp-uniform, one register
+    int n_live = lanes_used;
     // lanes that must be marching for the march loop to go on: march_min/32 of the live lanes, at least one.
     // (Kept in a register the compiler cannot re-derive - DDGI_OPAQUE - or it recomputes the five
     // instructions from n_live and march_min in EVERY march step to save that register.)
@@ -190,7 +216,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
     DDGI_OPAQUE(enough);
     for (;;) {
         // ---- march while at least march_min/32 of the lanes holding a ray are marching ----
-        if (n_live == 0) break;
+        if ((n_live & 255) == 0) break;
         while (__popc(__ballot_sync(full, R.mode == WF_MARCH)) >= enough) {
             if (R.mode == WF_MARCH) wf_step(P, R);
         }
@@ -208,7 +234,8 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
         // (marches with the literal arithmetic - axis-parallel or degenerate rays - are rare: they are only looked
         // for when nothing else waits, or once in a while so that they cannot starve)
         int n_slow = 0;
-        if (n_hit + n_fetch == 0 || (++round & 7) == 0) {
+        n_live += 256;
+        if (n_hit + n_fetch == 0 || (n_live & 0x700) == 0) {
             n_slow = __popc(__ballot_sync(full, R.mode == WF_MARCH_SLOW));
             if (n_hit + n_fetch + n_slow == 0) continue;  // (only marching lanes: cannot be fewer than `enough`)
         }
@@ -222,12 +249,16 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
             if (n_hit_f >= n_hit_b ? hit_feeler : hit_bounce) {
                 float* first_t = (want_first_t && R.bounce == 0 && R.phase == 0) ? &s_first_t[threadIdx.x] : nullptr;
                 wf_resolve_hit<kLiteral>(P, R, stash, kWfThreads, first_t);
+                if (!kCount) R.lookups = 0;
             }
         } else {
             // WF_FETCH: store the finished ray, take the next one
             const bool need = R.mode == WF_FETCH;
-            if (need && k != 0xffffffffu)
-                store_texel(J, tx, ty, wf_final_color(P, R), k, R.lookups, want_first_t ? s_first_t[threadIdx.x] : 0.0f);
+            if (need && k != 0xffffffffu) {
+                int tx, ty;
+                texel_of_ray(P, J, k, &tx, &ty);
+                store_texel(J, tx, ty, wf_final_color(P, R), k, kCount ? R.lookups : 0u, want_first_t ? s_first_t[threadIdx.x] : 0.0f);
+            }
             const unsigned want = fetching;
             uint32_t cnt = (uint32_t)__popc(want);
             uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
@@ -263,8 +294,6 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                     DDGI_WARP_TIME(1);  // (any lane: the last writer wins, same instant)
                     k = shard_ray(J, idx);
                     RayIn r = fetch_ray(P, J, k);
-                    tx = r.tx;
-                    ty = r.ty;
                     wf_init(R, r.origin, r.direction, k);
                 } else {
                     R.mode = WF_IDLE;
@@ -273,7 +302,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
             const int retired = __popc(__ballot_sync(full, need && R.mode == WF_IDLE));
             if (retired) {
                 n_live -= retired;
-                enough = (n_live * march_min + 31) >> 5 > 1 ? (n_live * march_min + 31) >> 5 : 1;
+                enough = ((n_live & 255) * march_min + 31) >> 5 > 1 ? ((n_live & 255) * march_min + 31) >> 5 : 1;
                 DDGI_OPAQUE(enough);
             }
         }
@@ -553,7 +582,7 @@ uint32_t wavefront_warps(uint32_t n, int grid_limit, int* lanes)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false, false>, kWfThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false, false, false>, kWfThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     int per_sm = grid_limit > 0 && grid_limit < blocks_per_sm ? grid_limit : blocks_per_sm;
@@ -588,10 +617,15 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
     int lanes = 32;
     uint32_t grid = wavefront_warps(n, grid_limit, &lanes) / (kWfThreads / 32);
     const bool literal = P.scene.color_mode != 0, timed = J.warp_times != nullptr;
-    if (literal && timed) probe_update_wavefront<true, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
-    else if (literal) probe_update_wavefront<true, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
-    else if (timed) probe_update_wavefront<false, true><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
-    else probe_update_wavefront<false, false><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes);
+    const bool count = J.lookups != nullptr || J.slot_cost != nullptr;  // (the timed instantiation always counts)
+#define DDGI_LAUNCH_WF(L, T, C) probe_update_wavefront<L, T, C><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes)
+    if (literal && timed) DDGI_LAUNCH_WF(true, true, true);
+    else if (literal && count) DDGI_LAUNCH_WF(true, false, true);
+    else if (literal) DDGI_LAUNCH_WF(true, false, false);
+    else if (timed) DDGI_LAUNCH_WF(false, true, true);
+    else if (count) DDGI_LAUNCH_WF(false, false, true);
+    else DDGI_LAUNCH_WF(false, false, false);
+#undef DDGI_LAUNCH_WF
     (*launches)++;
     return cudaGetLastError();
 }

@@ -22,6 +22,7 @@ for name in names:
     configs.apply(r, cfg)
     r.generate_probe_rays(reseed=True)
     r.update(advance_time=False)
+    if os.environ.get('SLOT'): r.set_schedule_slot(int(os.environ['SLOT']))
     stream = torch.cuda.current_stream(); r.stream = stream.cuda_stream
     rays = r.num_probe_rays
     for variant in variants:

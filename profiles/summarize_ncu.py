@@ -70,7 +70,7 @@ def main():
         print("# split by state of the per-lane state machine (profiles/prof_by_state.py; the library must be the profiled build)")
         sys.stdout.flush()
         # the palette instantiation <false> is the one the bench runs: select it by its mangled name
-        mangled = kernel + "ILb0ELb0E" if kernel == "probe_update_wavefront" else kernel
+        mangled = kernel + "ILb0ELb0ELb0E" if kernel == "probe_update_wavefront" else kernel
         subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "prof_by_state.py"), os.path.join(t, "src.csv"),
                         os.path.join(t, "k.dis"), mangled, str(n_rays)])
 
