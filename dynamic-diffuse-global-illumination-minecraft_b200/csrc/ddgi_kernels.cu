@@ -166,7 +166,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 #define DDGI_ENOUGH_HOISTED 1
 #endif
 #ifndef DDGI_WF_MIN_BLOCKS
-#define DDGI_WF_MIN_BLOCKS (896 / DDGI_WF_THREADS)  // 7 blocks of 128: 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
+#define DDGI_WF_MIN_BLOCKS (768 / DDGI_WF_THREADS)  // asks for 6 blocks of 128; the kernel needs 72 registers, so 7 are resident (with a bound of 7 ptxas works AT its register limit and generates two more instructions in the march loop): 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
 
 // kCount: the per-ray voxel-lookup count is kept (debug buffers, the calibration launch of the schedule); the
