@@ -288,7 +288,7 @@ def main():
             owner[a * X * Z:b * X * Z] = g
         return owner, f"probe rows {Y}/{world}, contiguous slabs"
 
-    probe_owner, shard_desc = set_ownership("slab" if sharding == "slab" else ("probes" if fused else "rows"))
+    probe_owner, shard_desc = set_ownership("slab" if sharding == "slab" else "probes")
     owned_probes = probe_owner == rank
 
     def join_nccl():
@@ -599,8 +599,10 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         verify = {"replicas_equal_full_update": bool(int(ok[0])), "bytes_compared_per_rank": int(got.numel())}
 
-    # ---- N > 1, fused default: the same workload once more with the engine's NCCL exchange (contiguous slabs, ONE
-    #      in-place ncclAllGather per plane through ddgi_exchange_allgather), device-timed like the headline ----
+    # ---- N > 1, fused default: the same workload once more with the engine's NCCL exchange (ddgi_exchange_allgather),
+    #      device-timed like the headline: (a) the balanced probe ownership of the headline, each rank's tiles packed
+    #      into one chunk, ONE ncclAllGather, unpacked; (b) contiguous slabs of probe rows, ONE in-place ncclAllGather
+    #      per plane and no packing (SURVEY 8e's layout; the slabs are not equally expensive) ----
     exchange_nccl = None
     if world > 1 and args.exchange == "fused":
         if fused:
@@ -608,15 +610,20 @@ def main():
             barrier()
             r.close_peers()
             fused = False
+        join_nccl()
+        n_nccl = max(3, min(args.steps, 10))
+        r.set_frames_in_flight(1)
+        set_ownership("probes")
+        ms_nccl, kernel_ms_nccl = timed(n_nccl, 3)
+        exchange_nccl = {"value": n_rays / (ms_nccl * 1e-3), "unit": UNIT, "ms_per_step": ms_nccl, "kernel_ms": kernel_ms_nccl,
+                         "steps": n_nccl, "exchange": "nccl: probes dealt round-robin in blocks of 5 (the headline's ownership), the rank's "
+                                                      "tiles packed into one chunk, ONE ncclAllGather, unpacked (ddgi_exchange_allgather; the "
+                                                      "distance plane only holds zeros and is skipped)"}
         if Y % world == 0:
-            join_nccl()
             set_ownership("slab")
-            n_nccl = max(3, min(args.steps, 10))
-            r.set_frames_in_flight(1)
-            ms_nccl, kernel_ms_nccl = timed(n_nccl, 3)
-            exchange_nccl = {"value": n_rays / (ms_nccl * 1e-3), "unit": UNIT, "ms_per_step": ms_nccl, "kernel_ms": kernel_ms_nccl,
-                             "steps": n_nccl, "exchange": "nccl: contiguous slabs of probe rows, one in-place ncclAllGather per plane "
-                                                          "(ddgi_exchange_allgather; the distance plane only holds zeros and is skipped)"}
+            ms_slab, kernel_ms_slab = timed(n_nccl, 3)
+            exchange_nccl["slabs"] = {"value": n_rays / (ms_slab * 1e-3), "unit": UNIT, "ms_per_step": ms_slab, "kernel_ms": kernel_ms_slab,
+                                      "exchange": "nccl: contiguous slabs of probe rows, one in-place ncclAllGather per plane, no packing"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

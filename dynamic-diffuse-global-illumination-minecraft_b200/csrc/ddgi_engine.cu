@@ -27,7 +27,9 @@ struct ddgi_ctx {
     int layout = 0, oct = 8;  // probe-texture layout: 0 the reference's ray tile, 1 octahedral oct x oct tiles
     float4* d_ray_out = nullptr;     // octahedral layout: per-ray (radiance, first-hit t)
     size_t ray_out_cap = 0;
-    uint32_t* d_owned = nullptr;     // octahedral layout: the owned probes
+    uint32_t* d_owned = nullptr;     // the owned probes, ascending (octahedral blend, packed all-gather)
+    uint32_t* d_pack = nullptr;      // gather buffer of the packed all-gather: comm_world chunks of tiles
+    size_t pack_cap = 0;
     size_t owned_cap = 0;
     std::vector<uint32_t> owned;
     int weight_mode = 0;    // 1: Chebyshev visibility weight restored in the cage sample
@@ -223,6 +225,7 @@ static int schedule(ddgi_ctx* ctx)
         }
     if (ctx->owned.size() > ctx->owned_cap) {
         dfree(ctx->d_owned);
+    dfree(ctx->d_pack);
         CU(cudaMalloc(&ctx->d_owned, ctx->owned.size() * sizeof(uint32_t)));
         ctx->owned_cap = ctx->owned.size();
     }
@@ -1285,8 +1288,58 @@ int ddgi_exchange_allgather(ddgi_ctx* ctx, void* stream)
         if (ctx->ev_frame[ctx->cur_tex]) CU(cudaEventRecord(ctx->ev_frame[ctx->cur_tex], s));
         return DDGI_OK;
     }
-    if (ctx->cyc_unit != 0 || ctx->cyc_world != G || ctx->cyc_rank != r)
-        return fail(ctx, DDGI_E_STATE, "ddgi_exchange_allgather moves probe rows: probe-cyclic ownership scatters tiles, use the fused exchange");
+    if (ctx->cyc_unit != 0) {
+        // Probe-cyclic ownership (the balanced one): a rank's tiles are scattered over the texture, so they are
+        // packed into one chunk per rank, gathered with ONE ncclAllGather and scattered again (ddgi_kernels.cu:
+        // pack_tiles / unpack_tiles; both planes travel when the distance plane is in use).
+        if (ctx->cyc_world != G || ctx->cyc_rank != r)
+            return fail(ctx, DDGI_E_STATE, "probe ownership (rank %d of %d) does not match the communicator (rank %d of %d)", ctx->cyc_rank,
+                        ctx->cyc_world, r, G);
+        int rc = schedule(ctx);  // (the owned-probe list)
+        if (rc) return rc;
+        const int B = ctx->cyc_block, n_probes = (int)num_probes(ctx);
+        const int blocks = (n_probes + B - 1) / B;
+        // rank 0 owns the most: ceil(blocks / G) blocks, the last of which may be short only if it is the field's last
+        const int most_blocks = (blocks + G - 1) / G;
+        int max_owned = most_blocks * B;
+        if (max_owned > n_probes) max_owned = n_probes;
+        TilePack T;
+        memset(&T, 0, sizeof(T));
+        T.tw = tile_w(ctx);
+        T.th = tile_h(ctx);
+        T.planes = planes;
+        T.plane = tex_texels(ctx);
+        T.max_owned = max_owned;
+        T.chunk_texels = (size_t)max_owned * T.tw * T.th * planes;
+        const size_t need = T.chunk_texels * G;
+        if (need > ctx->pack_cap) {
+            CU(cudaStreamSynchronize(s));
+            dfree(ctx->d_pack);
+            ctx->pack_cap = 0;
+            CU(cudaMalloc(&ctx->d_pack, need * sizeof(uint32_t)));
+            ctx->pack_cap = need;
+        }
+        T.tex = ctx->d_tex;
+        T.pack = ctx->d_pack;
+        T.owned = ctx->d_owned;
+        T.n_owned = (int)ctx->owned.size();
+        T.tiles_x = ctx->field.probe_count[0] * ctx->field.probe_count[2];
+        T.tex_w = ctx->tex_w;
+        T.G = G;
+        T.self = r;
+        T.B = B;
+        T.n_probes = n_probes;
+        int l = 0;
+        CU(launch_pack_tiles(T, false, s, &l));
+        NCCLCHK(N.AllGather((char*)ctx->d_pack + (size_t)r * T.chunk_texels * 4, ctx->d_pack, T.chunk_texels * 4, kNcclUint8, ctx->nccl_comm, s));
+        CU(launch_pack_tiles(T, true, s, &l));
+        ctx->launches += l;
+        if (ctx->ev_frame[ctx->cur_tex]) CU(cudaEventRecord(ctx->ev_frame[ctx->cur_tex], s));
+        return DDGI_OK;
+    }
+    if (ctx->cyc_world != G || ctx->cyc_rank != r)
+        return fail(ctx, DDGI_E_STATE, "probe-row ownership (rank %d of %d) does not match the communicator (rank %d of %d)", ctx->cyc_rank,
+                    ctx->cyc_world, r, G);
     NCCLCHK(N.GroupStart());
     for (int p = 0; p < planes; p++) {
         char* base = (char*)ctx->d_tex + p * plane;

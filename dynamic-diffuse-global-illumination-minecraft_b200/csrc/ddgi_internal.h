@@ -73,6 +73,18 @@ struct OctJob {
     uint32_t* peer_albedo[kMaxPeers];
     uint32_t* peer_distance[kMaxPeers];
 };
+struct TilePack {
+    uint32_t* tex;          // albedo plane; the distance plane follows at `plane` texels
+    uint32_t* pack;         // G chunks of chunk_texels
+    const uint32_t* owned;  // pack only
+    int n_owned;
+    int planes;
+    size_t plane, chunk_texels;
+    int tiles_x, tw, th, tex_w;
+    int G, self, B, n_probes, max_owned;
+};
+cudaError_t launch_pack_tiles(const TilePack& T, bool unpack, cudaStream_t s, int* launches);
+
 cudaError_t launch_probe_blend_octahedral(const FrameParams& P, const OctJob& J, cudaStream_t s, int* launches);
 
 struct PixelJob {

@@ -458,6 +458,51 @@ cudaError_t launch_peer_barrier(const PeerBarrier& B, cudaStream_t s, int* launc
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ packed all-gather (probe-cyclic ownership)
+// Probes dealt round-robin in blocks of B to G ranks scatter a rank's tiles over the whole texture; the collective
+// wants ONE contiguous chunk per rank.  pack_tiles copies the tiles of the owned probes (list `owned`, ascending)
+// into the rank's chunk of the gather buffer, tile after tile (both planes when the distance plane is in use);
+// after the in-place ncclAllGather unpack_tiles scatters every OTHER rank's chunk to its tiles: the j-th probe of
+// rank g is probe ((j / B) * G + g) * B + j % B.
+__device__ __forceinline__ void copy_tile(const TilePack& T, int p, size_t slot, bool to_pack)
+{
+    const int n = T.tw * T.th;
+    const int ox = (p % T.tiles_x) * T.tw, oy = (p / T.tiles_x) * T.th;
+    for (int pl = 0; pl < T.planes; pl++) {
+        uint32_t* tex = T.tex + pl * T.plane;
+        uint32_t* pk = T.pack + slot + (size_t)pl * T.max_owned * n;
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int row = t / T.tw, col = t - row * T.tw;
+            const size_t at = (size_t)(oy + row) * T.tex_w + ox + col;
+            if (to_pack) pk[t] = tex[at];
+            else tex[at] = pk[t];
+        }
+    }
+}
+__global__ void __launch_bounds__(128) pack_tiles_kernel(const __grid_constant__ TilePack T)
+{
+    const int j = blockIdx.x;
+    if (j >= T.n_owned) return;
+    copy_tile(T, (int)T.owned[j], (size_t)T.self * T.chunk_texels + (size_t)j * T.tw * T.th, true);
+}
+__global__ void __launch_bounds__(128) unpack_tiles_kernel(const __grid_constant__ TilePack T)
+{
+    const int j = blockIdx.x, g = blockIdx.y;
+    if (g == T.self) return;
+    const int p = ((j / T.B) * T.G + g) * T.B + j % T.B;
+    if (p >= T.n_probes) return;
+    copy_tile(T, p, (size_t)g * T.chunk_texels + (size_t)j * T.tw * T.th, false);
+}
+cudaError_t launch_pack_tiles(const TilePack& T, bool unpack, cudaStream_t s, int* launches)
+{
+    if (T.max_owned == 0) return cudaSuccess;
+    if (unpack) unpack_tiles_kernel<<<dim3(T.max_owned, T.G), 128, 0, s>>>(T);
+    else if (T.n_owned) pack_tiles_kernel<<<T.n_owned, 128, 0, s>>>(T);
+    else return cudaSuccess;
+    (*launches)++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ pixel pass
 // The reference dispatches floor(w/16) x floor(h/16) groups of 16x16: pixels beyond
 // that are never written (src/rvpt/rvpt.cpp:1139-1140).

@@ -266,9 +266,11 @@ DDGI_API int ddgi_exchange_status(ddgi_ctx* ctx);
    ddgi_exchange_allgather, on `stream` after ddgi_probe_update, moves the probe rows in place:
    ONE ncclAllGather per plane for equal contiguous slabs (ddgi_set_probe_rows(rank*Y/world,
    (rank+1)*Y/world), Y % world == 0: the send buffer is the rank's slab inside the receive buffer),
-   or one group of in-place ncclBroadcasts for block-cyclic rows (ddgi_set_probe_rows_cyclic).  The
-   distance plane travels only once something other than the reference's zeros has been stored in
-   it.  Not for probe-cyclic ownership (scattered tiles): DDGI_E_STATE. */
+   one group of in-place ncclBroadcasts for block-cyclic rows (ddgi_set_probe_rows_cyclic), or - probe-cyclic
+   ownership (ddgi_set_probes_cyclic: the balanced one, scattered tiles) - the rank's tiles packed into one
+   chunk, ONE ncclAllGather of the chunks, and a scatter of the other ranks' tiles (two small kernels around
+   the collective).  The distance plane travels only once something other than the reference's zeros has
+   been stored in it.  The ownership must match the communicator's rank and size: DDGI_E_STATE otherwise. */
 DDGI_API int ddgi_comm_unique_id(void* id128);
 DDGI_API int ddgi_comm_init(ddgi_ctx* ctx, const void* id128, int32_t rank, int32_t world);
 DDGI_API int ddgi_comm_destroy(ddgi_ctx* ctx);

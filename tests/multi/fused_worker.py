@@ -3,7 +3,9 @@
 into every peer's replica, epoch barriers), renders its band of every frame and reads the whole replica back
 asynchronously every frame - the pattern in which a faster rank could store frame i+1 into a replica whose owner still
 reads frame i (round 1's ADVICE).  Everything read is written to `out` for the parent to compare with a single-GPU run.
-    python fused_worker.py rank world frames_in_flight double_buffer exchange_dir out.npz"""
+With exchange = nccl the same loop runs over ddgi_exchange_allgather instead (probe-cyclic ownership: tiles packed into one
+chunk per rank, ONE ncclAllGather, unpacked), no peer mappings.
+    python fused_worker.py rank world frames_in_flight double_buffer exchange_dir out.npz [fused|nccl]"""
 import importlib
 import os
 import pickle
@@ -19,6 +21,7 @@ import ddgi_b200  # noqa: E402
 
 rank, world, in_flight, double_buffer = (int(v) for v in sys.argv[1:5])
 xdir, out = sys.argv[5], sys.argv[6]
+nccl = len(sys.argv) > 7 and sys.argv[7] == "nccl"
 configs = importlib.import_module(ddgi_b200._pkg.__name__ + ".configs")
 cfg = configs.CONFIGS["field_8"]
 FRAMES = 8
@@ -50,8 +53,12 @@ with ddgi_b200.RVPT(*cfg["screen"], device=rank) as r:
         r.set_double_buffer(True)
     r.set_probes_cyclic(rank, world, 5)
     band = r.set_frame_band(rank, world)
-    handles = exchange_files("handle", r.export_texture_handle())
-    r.open_peers(handles, rank)
+    if nccl:
+        ids = exchange_files("id", ddgi_b200.RVPT.comm_unique_id() if rank == 0 else b"")
+        r.comm_init(ids[0], rank, world)
+    else:
+        handles = exchange_files("handle", r.export_texture_handle())
+        r.open_peers(handles, rank)
     if in_flight == 2:
         r.set_frames_in_flight(2)
     W, H = r.probe_texture_size
@@ -62,7 +69,10 @@ with ddgi_b200.RVPT(*cfg["screen"], device=rank) as r:
         r.lights = configs.lights_for(cfg, r.render_settings.time)
         r.update(advance_time=False)
         r.probe_update()
-        r.exchange_barrier()
+        if nccl:
+            r.exchange_allgather()
+        else:
+            r.exchange_barrier()
         if rank == 0:
             for _ in range(40):   # rank 0 reads frame f for a long time on the device: the peers must not run ahead into its replica
                 r.render_frame()
@@ -78,9 +88,11 @@ with ddgi_b200.RVPT(*cfg["screen"], device=rank) as r:
     r.read_wait()
     r.frame_fence()
     r.sync()
-    r.exchange_status()
+    if not nccl:
+        r.exchange_status()
     exchange_files("done", b"")   # nobody unmaps while a peer may still store
     r.set_frames_in_flight(1)
-    r.close_peers()
+    if not nccl:
+        r.close_peers()
     np.savez(out, tex=np.stack(tex), frames=np.stack(frames), band=np.array(band))
 print("ok", rank)

@@ -2,7 +2,8 @@
 epoch barriers) under the access pattern that can mix frames - moving lights, a render and a read of the whole replica
 every frame, one rank lagging on the host - for single- and double-buffered replicas and with two frames in flight.
 Every texture and every rendered band any rank ever read must equal the single-GPU engine's for that frame (round 1's
-ADVICE: `bench --verify` only compares replicas at a quiescent point).  Skipped on a box with one GPU (gpurun --gpus 2)."""
+ADVICE: `bench --verify` only compares replicas at a quiescent point).  The same loop also runs over the NCCL exchange of probe-cyclic ownership (tiles packed into one chunk per rank, ONE
+ncclAllGather, unpacked: ddgi_exchange_allgather).  Skipped on a box with one GPU (gpurun --gpus 2)."""
 import os
 import subprocess
 import sys
@@ -37,8 +38,8 @@ def reference_frames():
 
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("in_flight,double_buffer", [(1, 0), (1, 1), (2, 1)])
-def test_fused_exchange_never_mixes_frames(tmp_path, in_flight, double_buffer):
+@pytest.mark.parametrize("in_flight,double_buffer,exchange", [(1, 0, "fused"), (1, 1, "fused"), (2, 1, "fused"), (1, 0, "nccl"), (1, 1, "nccl")])
+def test_fused_exchange_never_mixes_frames(tmp_path, in_flight, double_buffer, exchange):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -48,7 +49,7 @@ def test_fused_exchange_never_mixes_frames(tmp_path, in_flight, double_buffer):
     assert not np.array_equal(tex[0], tex[1]), "the lights must move between frames for the test to mean anything"
     outs = [str(tmp_path / f"rank{r}.npz") for r in range(world)]
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "multi", "fused_worker.py"), str(r), str(world), str(in_flight),
-                               str(double_buffer), str(tmp_path), outs[r]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                               str(double_buffer), str(tmp_path), outs[r], exchange], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
              for r in range(world)]
     for r, p in enumerate(procs):
         so, se = p.communicate(timeout=240)
