@@ -151,11 +151,13 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
 #ifndef DDGI_WF_THREADS
-#define DDGI_WF_THREADS 128
+#define DDGI_WF_THREADS 32
 #endif
-constexpr int kWfThreads = DDGI_WF_THREADS;  // (the warps of a block share nothing: the block size only decides how many
-                                             // warps must have drained before the SM takes the next block; 32 / 64 / 128
-                                             // measured within 0.6 % of each other, profiles/r2_ab.md h)
+constexpr int kWfThreads = DDGI_WF_THREADS;  // one warp per block: the warps of a block share nothing, so the block size
+                                             // only decides how many warps must have drained before the SM takes the
+                                             // next block (of this launch or, with two frames in flight, of the next
+                                             // frame's).  32 / 64 / 128 threads: 6.361 / 6.418 / 6.410 ms on field_32
+                                             // (profiles/r2_ab.md h, p); 28 blocks of 32 are resident per SM
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
