@@ -100,7 +100,7 @@ struct PixelJob {
 // grid_limit > 0 caps the resident blocks per SM the persistent kernel launches (tuning)
 cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
                                 int march_min, int grid_limit, cudaStream_t s, int* launches);
-uint32_t wavefront_warps(uint32_t n_rays, int grid_limit, int* lanes = nullptr);
+uint32_t wavefront_warps(uint32_t n_rays, int grid_limit, int* lanes = nullptr, int* threads = nullptr);
 cudaError_t launch_render_frame(const FrameParams& P, const PixelJob& J, cudaStream_t s, int* launches);
 cudaError_t launch_bake_scene(int scene, const int dims[3], const int org[3], uint8_t* types,
                               cudaStream_t s, int* launches);

@@ -150,14 +150,16 @@ __global__ void __launch_bounds__(256) probe_update_direct(const __grid_constant
 // is issued once for both.
 // Finished rays store their texel in WF_FETCH and take the next ray index there (the
 // warp draws indices from the global counter 32 at a time).
+// Threads per block: the kernel is compiled for up to kWfThreads; the warps of a block share nothing, so the block size
+// only decides how many warps must have drained before the SM takes the next block (of this launch or, with two frames in
+// flight, of the next frame's).  The launcher picks ONE warp per block when there are at least 7 rays per resident lane
+// (field_32 6.410 -> 6.361 ms; 28 blocks of 32 threads are resident per SM) and four warps per block for smaller
+// workloads, which are bound by their longest ray and measured up to 10 % slower with one-warp blocks
+// (profiles/r2_ab.md h, p).  DDGI_WF_THREADS forces one size (A/B builds).
 #ifndef DDGI_WF_THREADS
-#define DDGI_WF_THREADS 32
+#define DDGI_WF_THREADS 0
 #endif
-constexpr int kWfThreads = DDGI_WF_THREADS;  // one warp per block: the warps of a block share nothing, so the block size
-                                             // only decides how many warps must have drained before the SM takes the
-                                             // next block (of this launch or, with two frames in flight, of the next
-                                             // frame's).  32 / 64 / 128 threads: 6.361 / 6.418 / 6.410 ms on field_32
-                                             // (profiles/r2_ab.md h, p); 28 blocks of 32 are resident per SM
+constexpr int kWfThreads = 128;
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
@@ -168,7 +170,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 #define DDGI_ENOUGH_HOISTED 1
 #endif
 #ifndef DDGI_WF_MIN_BLOCKS
-#define DDGI_WF_MIN_BLOCKS (768 / DDGI_WF_THREADS)  // asks for 6 blocks of 128; the kernel needs 72 registers, so 7 are resident (with a bound of 7 ptxas works AT its register limit and generates two more instructions in the march loop): 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
+#define DDGI_WF_MIN_BLOCKS 6  // asks for 6 blocks of 128; the kernel needs 72 registers, so 7 are resident (with a bound of 7 ptxas works AT its register limit and generates two more instructions in the march loop): 72 registers / thread, 28 resident warps per SM: measured faster than 8 (64 registers, spills)
 #endif
 
 // kCount: the per-ray voxel-lookup count is kept (debug buffers, the calibration launch of the schedule); the
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
 #define DDGI_WARP_TIME(slot)                                                                                  \
     do {                                                                                                      \
         if (kTimed)                                                                                           \
-            J.warp_times[3 * (size_t)((blockIdx.x * kWfThreads + threadIdx.x) >> 5) + (slot)] = globaltimer_ns(); \
+            J.warp_times[3 * (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + (slot)] = globaltimer_ns(); \
     } while (0)
     if (lane == 0) DDGI_WARP_TIME(0);
 
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kWfThreads, DDGI_WF_MIN_BLOCKS) probe_update_w
                 // number asked for once fewer than two rays per resident lane remain — a warp
                 // must not sit on reserved rays while others run dry, or it alone is the tail.
                 const uint32_t more = cnt - avail;
-                const uint32_t take = (n_rays - chunk_end <= 2u * gridDim.x * kWfThreads) ? more : (uint32_t)lanes_used;
+                const uint32_t take = (n_rays - chunk_end <= 2u * gridDim.x * blockDim.x) ? more : (uint32_t)lanes_used;
                 uint32_t base = n_rays;
                 if (!exhausted) {
                     if (lane == 0) base = atomicAdd(next_ray, take);
@@ -622,7 +624,7 @@ __global__ void edit_voxels_kernel(int dx, int dy, int x0, int y0, int z0, int e
 // *lanes = lanes per warp that hold rays: 32, or fewer (a multiple of 4, at least 8) when n is below the number
 // of resident lanes, so that a small workload uses every resident warp with few rays each instead of a quarter
 // of the warps with 32 each (cave_64: 65 536 rays on 132 608 resident lanes).
-uint32_t wavefront_warps(uint32_t n, int grid_limit, int* lanes)
+uint32_t wavefront_warps(uint32_t n, int grid_limit, int* lanes, int* threads)
 {
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
@@ -632,7 +634,7 @@ uint32_t wavefront_warps(uint32_t n, int grid_limit, int* lanes)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, probe_update_wavefront<false, false, false>, kWfThreads, 0);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    int per_sm = grid_limit > 0 && grid_limit < blocks_per_sm ? grid_limit : blocks_per_sm;
+    int per_sm = grid_limit > 0 && grid_limit < blocks_per_sm ? grid_limit : blocks_per_sm;  // (in blocks of kWfThreads)
     uint32_t resident_warps = (uint32_t)(sms * per_sm) * (kWfThreads / 32);
     int use = 32;
     if (n < resident_warps * 32u) {
@@ -641,11 +643,14 @@ uint32_t wavefront_warps(uint32_t n, int grid_limit, int* lanes)
         use = use < 8 ? 8 : (use > 32 ? 32 : use);
     }
     if (lanes) *lanes = use;
+    // one warp per block from 7 rays per resident lane on, else four (see kWfThreads: sweep_64 / sweep_128, 2 - 4 rays per
+    // lane, are 7 - 10 % slower with one-warp blocks, 8 rays per lane are even, field_32 with 63 gains 0.8 %)
+    int t = DDGI_WF_THREADS ? DDGI_WF_THREADS : (n >= resident_warps * 224u ? 32 : kWfThreads);
+    if (threads) *threads = t;
     uint32_t warps_needed = (n + use - 1) / use;
-    uint32_t blocks_needed = (warps_needed + kWfThreads / 32 - 1) / (kWfThreads / 32);
-    uint32_t grid = (uint32_t)(sms * per_sm);
-    if (grid > blocks_needed) grid = blocks_needed;
-    return grid * (kWfThreads / 32);
+    uint32_t warps = warps_needed < resident_warps ? warps_needed : resident_warps;
+    uint32_t per_block = (uint32_t)t / 32u;
+    return (warps + per_block - 1) / per_block * per_block;
 }
 
 cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int variant, uint32_t* counter,
@@ -661,11 +666,11 @@ cudaError_t launch_probe_update(const FrameParams& P, const ProbeJob& J, int var
     }
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    int lanes = 32;
-    uint32_t grid = wavefront_warps(n, grid_limit, &lanes) / (kWfThreads / 32);
+    int lanes = 32, threads = kWfThreads;
+    uint32_t grid = wavefront_warps(n, grid_limit, &lanes, &threads) / (uint32_t)(threads / 32);
     const bool literal = P.scene.color_mode != 0, timed = J.warp_times != nullptr;
     const bool count = J.lookups != nullptr || J.slot_cost != nullptr;  // (the timed instantiation always counts)
-#define DDGI_LAUNCH_WF(L, T, C) probe_update_wavefront<L, T, C><<<grid, kWfThreads, 0, s>>>(P, J, counter, march_min, lanes)
+#define DDGI_LAUNCH_WF(L, T, C) probe_update_wavefront<L, T, C><<<grid, threads, 0, s>>>(P, J, counter, march_min, lanes)
     if (literal && timed) DDGI_LAUNCH_WF(true, true, true);
     else if (literal && count) DDGI_LAUNCH_WF(true, false, true);
     else if (literal) DDGI_LAUNCH_WF(true, false, false);
